@@ -1,0 +1,190 @@
+// api.cu -- extern "C" surface of libd2t_b200.so (see include/d2t_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace d2t {
+
+// ---- error plumbing -------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return D2T_ERR_CUDA;
+}
+
+int device_info(DeviceInfo* out) {
+    static DeviceInfo cache[64];
+    static bool have[64];
+    int dev = 0;
+    D2T_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("device index %d out of range", dev);
+        return D2T_ERR_BAD_ARG;
+    }
+    if (!have[dev]) {
+        DeviceInfo di;
+        D2T_CUDA_TRY(cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        D2T_CUDA_TRY(cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cache[dev] = di;  // benign race: every thread writes the same values
+        have[dev] = true;
+    }
+    *out = cache[dev];
+    return 0;
+}
+
+// launchers implemented in the other translation units
+template <typename T>
+int corr_fwd_generic_launch(const T*, const T*, T*, int, int, int, int, int, int, cudaStream_t);
+template <typename T>
+int corr_bwd_generic_launch(const T*, const T*, const T*, T*, T*, int, int, int, int, int, int, cudaStream_t);
+template <typename T>
+int roipool_fwd_launch(const T*, const T*, T*, int, int, int, int, int, cudaStream_t);
+template <typename T>
+int roipool_bwd_launch(const T*, const T*, T*, int, int, int, int, int, cudaStream_t);
+template <typename T>
+int psroipool_fwd_launch(const T*, const T*, T*, int, int, int, int, int, int, cudaStream_t);
+template <typename T>
+int psroipool_bwd_launch(const T*, const T*, T*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+template <typename T>
+int pool_bins_launch(const T*, int32_t*, int, int, int, int, int, cudaStream_t);
+size_t psroipool_bwd_ws_bytes(int R, int H, int W, int k);
+
+// tuned float32 correlation (corr_tile.cu)
+bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
+size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d);
+size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d);
+int corr_tile_fwd_launch(const float*, const float*, float*, int, int, int, int, int, void*, size_t, cudaStream_t);
+int corr_tile_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int, void*,
+                         size_t, cudaStream_t);
+
+static int check_corr(const void* a, const void* b, const void* c, int B, int C, int H, int W, int d, int stride,
+                      const char* who) {
+    D2T_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, "%s: negative dimension (B=%d C=%d H=%d W=%d)", who, B, C, H, W);
+    D2T_REQUIRE(d >= 0, "%s: d_max must be >= 0 (got %d)", who, d);
+    D2T_REQUIRE(stride >= 1, "%s: stride must be >= 1 (got %d)", who, stride);
+    const bool empty = (long long)B * H * W == 0;
+    D2T_REQUIRE(empty || (a && b && c), "%s: null pointer", who);
+    return D2T_OK;
+}
+
+}  // namespace d2t
+
+using namespace d2t;
+
+extern "C" {
+
+int d2t_abi_version(void) { return D2T_B200_ABI_VERSION; }
+const char* d2t_last_error(void) { return g_err; }
+
+// ---- correlation -------------------------------------------------------------------
+size_t d2t_corr_fwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size) {
+    if (elem_size == 4 && corr_tile_supported(B, C, H, W, d_max, stride)) return corr_tile_fwd_ws_bytes(B, C, H, W, d_max);
+    return 0;
+}
+size_t d2t_corr_bwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size) {
+    if (elem_size == 4 && corr_tile_supported(B, C, H, W, d_max, stride)) return corr_tile_bwd_ws_bytes(B, C, H, W, d_max);
+    return 0;
+}
+
+int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
+                     void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, "d2t_corr_fwd_f32");
+    if (rc) return rc;
+    if (corr_tile_supported(B, C, H, W, d_max, stride))
+        return corr_tile_fwd_launch(fm0, fm1, out, B, C, H, W, d_max, ws, ws_bytes, (cudaStream_t)stream);
+    return corr_fwd_generic_launch<float>(fm0, fm1, out, B, C, H, W, d_max, stride, (cudaStream_t)stream);
+}
+int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
+                     int stride, void* ws, size_t ws_bytes, void* stream) {
+    (void)ws;
+    (void)ws_bytes;
+    int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, "d2t_corr_fwd_f64");
+    if (rc) return rc;
+    return corr_fwd_generic_launch<double>(fm0, fm1, out, B, C, H, W, d_max, stride, (cudaStream_t)stream);
+}
+int d2t_corr_bwd_f32(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0, float* grad_fm1, int B,
+                     int C, int H, int W, int d_max, int stride, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_corr(grad_out, fm0, fm1, B, C, H, W, d_max, stride, "d2t_corr_bwd_f32");
+    if (rc) return rc;
+    D2T_REQUIRE((long long)B * C * H * W == 0 || (grad_fm0 && grad_fm1), "d2t_corr_bwd_f32: null output pointer");
+    if (corr_tile_supported(B, C, H, W, d_max, stride))
+        return corr_tile_bwd_launch(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, ws, ws_bytes,
+                                    (cudaStream_t)stream);
+    return corr_bwd_generic_launch<float>(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, stride,
+                                          (cudaStream_t)stream);
+}
+int d2t_corr_bwd_f64(const double* grad_out, const double* fm0, const double* fm1, double* grad_fm0, double* grad_fm1,
+                     int B, int C, int H, int W, int d_max, int stride, void* ws, size_t ws_bytes, void* stream) {
+    (void)ws;
+    (void)ws_bytes;
+    int rc = check_corr(grad_out, fm0, fm1, B, C, H, W, d_max, stride, "d2t_corr_bwd_f64");
+    if (rc) return rc;
+    D2T_REQUIRE((long long)B * C * H * W == 0 || (grad_fm0 && grad_fm1), "d2t_corr_bwd_f64: null output pointer");
+    return corr_bwd_generic_launch<double>(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, stride,
+                                           (cudaStream_t)stream);
+}
+
+// ---- ROIPool -------------------------------------------------------------------------
+size_t d2t_roipool_fwd_workspace_bytes(int, int, int, int, int, int) { return 0; }
+size_t d2t_roipool_bwd_workspace_bytes(int, int, int, int, int, int) { return 0; }
+
+int d2t_roipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int r_hw, void*,
+                        size_t, void* stream) {
+    return roipool_fwd_launch<float>(fm, rois, out, R, C, H, W, r_hw, (cudaStream_t)stream);
+}
+int d2t_roipool_fwd_f64(const double* fm, const double* rois, double* out, int R, int C, int H, int W, int r_hw, void*,
+                        size_t, void* stream) {
+    return roipool_fwd_launch<double>(fm, rois, out, R, C, H, W, r_hw, (cudaStream_t)stream);
+}
+int d2t_roipool_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int R, int C, int H, int W, int r_hw,
+                        void*, size_t, void* stream) {
+    return roipool_bwd_launch<float>(grad_out, rois, grad_fm, R, C, H, W, r_hw, (cudaStream_t)stream);
+}
+int d2t_roipool_bwd_f64(const double* grad_out, const double* rois, double* grad_fm, int R, int C, int H, int W,
+                        int r_hw, void*, size_t, void* stream) {
+    return roipool_bwd_launch<double>(grad_out, rois, grad_fm, R, C, H, W, r_hw, (cudaStream_t)stream);
+}
+
+// ---- PSROIPool -----------------------------------------------------------------------
+size_t d2t_psroipool_fwd_workspace_bytes(int, int, int, int, int, int) { return 0; }
+size_t d2t_psroipool_bwd_workspace_bytes(int R, int, int H, int W, int r_hw, int) {
+    return psroipool_bwd_ws_bytes(R, H, W, r_hw);
+}
+
+int d2t_psroipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int n_targets, int H, int W, int r_hw,
+                          int flags, void*, size_t, void* stream) {
+    return psroipool_fwd_launch<float>(fm, rois, out, R, n_targets, H, W, r_hw, flags, (cudaStream_t)stream);
+}
+int d2t_psroipool_fwd_f64(const double* fm, const double* rois, double* out, int R, int n_targets, int H, int W,
+                          int r_hw, int flags, void*, size_t, void* stream) {
+    return psroipool_fwd_launch<double>(fm, rois, out, R, n_targets, H, W, r_hw, flags, (cudaStream_t)stream);
+}
+int d2t_psroipool_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int R, int n_targets, int H, int W,
+                          int r_hw, int flags, void* ws, size_t ws_bytes, void* stream) {
+    return psroipool_bwd_launch<float>(grad_out, rois, grad_fm, R, n_targets, H, W, r_hw, flags, ws, ws_bytes,
+                                       (cudaStream_t)stream);
+}
+int d2t_psroipool_bwd_f64(const double* grad_out, const double* rois, double* grad_fm, int R, int n_targets, int H,
+                          int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream) {
+    return psroipool_bwd_launch<double>(grad_out, rois, grad_fm, R, n_targets, H, W, r_hw, flags, ws, ws_bytes,
+                                        (cudaStream_t)stream);
+}
+
+// ---- bin edges -----------------------------------------------------------------------
+int d2t_pool_bins_f32(const float* rois, int32_t* edges, int R, int H, int W, int r_hw, int clamp_start, void* stream) {
+    return pool_bins_launch<float>(rois, edges, R, H, W, r_hw, clamp_start, (cudaStream_t)stream);
+}
+int d2t_pool_bins_f64(const double* rois, int32_t* edges, int R, int H, int W, int r_hw, int clamp_start, void* stream) {
+    return pool_bins_launch<double>(rois, edges, R, H, W, r_hw, clamp_start, (cudaStream_t)stream);
+}
+
+}  // extern "C"

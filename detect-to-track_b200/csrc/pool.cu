@@ -1,0 +1,566 @@
+// pool.cu -- ROIPool / PSROIPool forward + backward for sm_100a.
+//
+// Replaces roipool/roipool_cuda.cu and ps_roipool/ps_roipool_cuda.cu of the
+// reference (one thread per output element, global-memory accumulators,
+// atomicAdd backward).  Design here:
+//
+//  ROIPool fwd  : "channel-owner" CTAs.  A CTA loads a slab of CB channel planes
+//                 into shared memory ONCE (coalesced), then walks all RoIs and
+//                 emits out[r, c0:c0+CB, :, :] -- a contiguous run per RoI --
+//                 so the feature map is read from HBM once and the output is
+//                 written once, coalesced.  Bin pixels are summed rows-then-
+//                 columns, the reference's order, so float results are
+//                 bit-identical to the reference kernel.
+//  ROIPool bwd  : same ownership.  The CTA keeps its slab of grad planes in
+//                 shared memory, walks the RoIs IN ORDER and adds each RoI's
+//                 contribution with exclusive (thread-owned) read-modify-writes:
+//                 deterministic, no atomics, grad_fm written exactly once
+//                 (no zero-fill pass).
+//  PSROIPool fwd: one thread per output, target index fastest so the lanes of a
+//                 warp share a bin (same trip count).
+//  PSROIPool bwd: pixel-owner gather.  A tiny prep kernel builds, per bin row /
+//                 bin column index, bitmasks over RoIs ("which RoIs' bin i covers
+//                 pixel row y").  Each output pixel ANDs a row mask with a column
+//                 mask and visits the surviving RoIs in ascending order:
+//                 deterministic, no atomics, every pixel written exactly once.
+#include "common.cuh"
+
+namespace d2t {
+
+// ---- fast division by a runtime constant (n < 2^31) ---------------------------
+struct FastDiv {
+    uint32_t d, m, s;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    f.s = l;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+    return (__umulhi(f.m, n) + n) >> f.s;
+}
+
+constexpr int kPoolThreads = 256;
+constexpr int kMaxK = 32;  // largest supported r_hw
+
+// ---- bin edges for a chunk of RoIs into shared memory -------------------------
+template <typename T, bool kClampStart>
+__device__ __forceinline__ void edges_to_smem(const T* __restrict__ rois, int r0, int nr, int k, int H, int W,
+                                              short* sI0, short* sI1, short* sJ0, short* sJ1) {
+    for (int idx = threadIdx.x; idx < nr * k; idx += blockDim.x) {
+        const int rr = idx / k, b = idx - rr * k;
+        const T* roi = rois + (size_t)(r0 + rr) * 4;
+        int e0, e1;
+        bin_edge<T, kClampStart>(roi[0], roi[2], b, k, H, e0, e1);
+        sI0[idx] = (short)e0;
+        sI1[idx] = (short)e1;
+        bin_edge<T, kClampStart>(roi[1], roi[3], b, k, W, e0, e1);
+        sJ0[idx] = (short)e0;
+        sJ1[idx] = (short)e1;
+    }
+}
+
+// =================================================================================
+// ROIPool forward
+// =================================================================================
+// smem: T plane[CB][HB*W] | short edges[4][RCH*k]
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+roipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __restrict__ out, int R, int C, int H,
+                   int W, int k, int CB, int RCH, FastDiv dCBkk, FastDiv dkk, FastDiv dk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* plane = reinterpret_cast<T*>(smem_raw);
+    const int HW = H * W;
+    short* sI0 = reinterpret_cast<short*>(plane + (size_t)CB * HW);
+    short* sI1 = sI0 + RCH * k;
+    short* sJ0 = sI1 + RCH * k;
+    short* sJ1 = sJ0 + RCH * k;
+
+    const int c0 = blockIdx.x * CB;
+    const int cb = min(CB, C - c0);
+    const int kk = k * k;
+
+    // slab load: cb*HW contiguous elements
+    {
+        const T* src = fm + (size_t)c0 * HW;
+        const int n = cb * HW;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) plane[idx] = __ldg(src + idx);
+    }
+
+    for (int rbase = 0; rbase < R; rbase += RCH) {
+        const int nr = min(RCH, R - rbase);
+        __syncthreads();
+        edges_to_smem<T, true>(rois, rbase, nr, k, H, W, sI0, sI1, sJ0, sJ1);
+        __syncthreads();
+
+        const int total = nr * CB * kk;
+        for (int o = threadIdx.x; o < total; o += blockDim.x) {
+            const int rr = fdiv(o, dCBkk);
+            const int rem = o - rr * (CB * kk);
+            const int cc = fdiv(rem, dkk);
+            if (cc >= cb) continue;
+            const int b = rem - cc * kk;
+            const int i = fdiv(b, dk);
+            const int j = b - i * k;
+            const int i0 = sI0[rr * k + i], i1 = sI1[rr * k + i];
+            const int j0 = sJ0[rr * k + j], j1 = sJ1[rr * k + j];
+            const T* p = plane + (size_t)cc * HW;
+            T acc = 0;
+            for (int pi = i0; pi < i1; ++pi) {
+                const T* row = p + pi * W;
+                for (int pj = j0; pj < j1; ++pj) acc += row[pj];
+            }
+            const int numel = (i1 - i0) * (j1 - j0);
+            acc /= numel;  // no empty-bin guard: 0/0 = NaN like roipool_cuda.cu:61
+            out[((size_t)(rbase + rr) * C + c0 + cc) * kk + b] = acc;
+        }
+    }
+}
+
+// =================================================================================
+// ROIPool backward
+// =================================================================================
+// smem: T acc[CB][HW] | T g[CB*kk] | T inv[kk] | short edges[4][RCH*k]
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+roipool_bwd_kernel(const T* __restrict__ go, const T* __restrict__ rois, T* __restrict__ gin, int R, int C, int H,
+                   int W, int k, int CB, int RCH) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* acc = reinterpret_cast<T*>(smem_raw);
+    const int HW = H * W;
+    const int kk = k * k;
+    T* sg = acc + (size_t)CB * HW;
+    T* sinv = sg + CB * kk;
+    short* sI0 = reinterpret_cast<short*>(sinv + kk);
+    short* sI1 = sI0 + RCH * k;
+    short* sJ0 = sI1 + RCH * k;
+    short* sJ1 = sJ0 + RCH * k;
+
+    const int c0 = blockIdx.x * CB;
+    const int cb = min(CB, C - c0);
+
+    for (int idx = threadIdx.x; idx < cb * HW; idx += blockDim.x) acc[idx] = 0;
+
+    for (int rbase = 0; rbase < R; rbase += RCH) {
+        const int nr = min(RCH, R - rbase);
+        __syncthreads();
+        edges_to_smem<T, true>(rois, rbase, nr, k, H, W, sI0, sI1, sJ0, sJ1);
+
+        for (int rr = 0; rr < nr; ++rr) {
+            __syncthreads();  // previous RoI's readers of sg/sinv are done; edges visible
+            // stage this RoI's gradient block (cb*kk contiguous) and 1/numel table
+            {
+                const T* src = go + ((size_t)(rbase + rr) * C + c0) * kk;
+                for (int idx = threadIdx.x; idx < cb * kk; idx += blockDim.x) sg[idx] = __ldg(src + idx);
+                for (int b = threadIdx.x; b < kk; b += blockDim.x) {
+                    const int i = b / k, j = b - i * k;
+                    const int numel = (sI1[rr * k + i] - sI0[rr * k + i]) * (sJ1[rr * k + j] - sJ0[rr * k + j]);
+                    sinv[b] = static_cast<T>(1) / static_cast<T>(numel);
+                }
+            }
+            __syncthreads();
+
+            const short* I0 = sI0 + rr * k;
+            const short* I1 = sI1 + rr * k;
+            const short* J0 = sJ0 + rr * k;
+            const short* J1 = sJ1 + rr * k;
+            const int colLo = J0[0], colHi = J1[k - 1];
+            const int w = colHi - colLo;
+            if (w > kPoolThreads) {
+                // RoI wider than the block: strided loop over (channel, column)
+                for (int item = threadIdx.x; item < cb * w; item += blockDim.x) {
+                    const int cc = item / w;
+                    const int pjx = colLo + (item - cc * w);
+                    T* a = acc + (size_t)cc * HW;
+                    for (int i = 0; i < k; ++i) {
+                        T u = 0;
+                        for (int j = 0; j < k; ++j)
+                            if (J0[j] <= pjx && pjx < J1[j]) u += sg[cc * kk + i * k + j] * sinv[i * k + j];
+                        for (int pi = I0[i]; pi < I1[i]; ++pi) a[pi * W + pjx] += u;
+                    }
+                }
+            } else if (w > 0) {
+                // thread <-> (channel, column): column index in the low lw bits
+                int lw = 0;
+                while ((1 << lw) < w) ++lw;
+                const int x = threadIdx.x & ((1 << lw) - 1);
+                const int ccStep = kPoolThreads >> lw;
+                const int pj = colLo + x;
+                // column bins covering pj form a contiguous range [jlo, jhi]
+                int jlo = k, jhi = -1;
+                if (x < w) {
+                    for (int j = 0; j < k; ++j) {
+                        if (J0[j] <= pj && pj < J1[j]) {
+                            jlo = min(jlo, j);
+                            jhi = j;
+                        }
+                    }
+                }
+                if (jhi >= 0) {
+                    for (int cc = threadIdx.x >> lw; cc < cb; cc += ccStep) {
+                        T* a = acc + (size_t)cc * HW + pj;
+                        const T* g = sg + cc * kk;
+                        for (int i = 0; i < k; ++i) {
+                            T u = 0;
+                            for (int j = jlo; j <= jhi; ++j) u += g[i * k + j] * sinv[i * k + j];
+                            for (int pi = I0[i]; pi < I1[i]; ++pi) a[pi * W] += u;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    T* dst = gin + (size_t)c0 * HW;
+    for (int idx = threadIdx.x; idx < cb * HW; idx += blockDim.x) dst[idx] = acc[idx];
+}
+
+// =================================================================================
+// PSROIPool forward
+// =================================================================================
+__device__ __forceinline__ int ps_channel(int t, int i, int j, int k, bool canonical) {
+    // reference map (ps_roipool_cuda.cu:58): (t+1)*(i*k+j)   [SURVEY.md F6]
+    return canonical ? (t * k * k + i * k + j) : (t + 1) * (i * k + j);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+psroipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __restrict__ out, int R, int nT,
+                     int H, int W, int k, bool canonical, FastDiv dnT, FastDiv dk, FastDiv dkk) {
+    const int kk = k * k;
+    const int total = R * kk * nT;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        // idx = ((r*k + i)*k + j)*nT + t   (t fastest: a warp shares bins)
+        const int rb = fdiv(idx, dnT);
+        const int t = idx - rb * nT;
+        const int r = fdiv(rb, dkk);
+        const int b = rb - r * kk;
+        const int i = fdiv(b, dk);
+        const int j = b - i * k;
+        const T* roi = rois + (size_t)r * 4;
+        int i0, i1, j0, j1;
+        bin_edge<T, false>(roi[0], roi[2], i, k, H, i0, i1);
+        bin_edge<T, false>(roi[1], roi[3], j, k, W, j0, j1);
+        const T* ch = fm + (size_t)ps_channel(t, i, j, k, canonical) * H * W;
+        T acc = 0;
+        for (int pi = i0; pi < i1; ++pi)
+            for (int pj = j0; pj < j1; ++pj) acc += __ldg(ch + pi * W + pj);
+        const int numel = (i1 - i0) * (j1 - j0);
+        if (numel > 0) acc /= numel;
+        out[((size_t)r * nT + t) * kk + b] = acc;
+    }
+}
+
+// =================================================================================
+// PSROIPool backward: prep (edges + RoI bitmasks) and pixel-owner gather
+// =================================================================================
+// workspace layout (see psroipool_bwd_ws_layout):
+//   short4-like edges: eI0,eI1,eJ0,eJ1 : [R*k] int16 each
+//   rowmask : [k][H][NW] uint32   bit r%32 of word r/32 set iff I0[r][i] <= y < I1[r][i]
+//   colmask : [k][W][NW] uint32
+struct PsBwdWs {
+    short *eI0, *eI1, *eJ0, *eJ1;
+    uint32_t *rowmask, *colmask;
+    int NW;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+psroipool_bwd_prep_kernel(const T* __restrict__ rois, PsBwdWs ws, int R, int H, int W, int k) {
+    // phase 1: edges (grid-stride)
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    for (int idx = tid; idx < R * k; idx += nth) {
+        const int r = idx / k, b = idx - r * k;
+        const T* roi = rois + (size_t)r * 4;
+        int e0, e1;
+        bin_edge<T, false>(roi[0], roi[2], b, k, H, e0, e1);
+        ws.eI0[idx] = (short)e0;
+        ws.eI1[idx] = (short)e1;
+        bin_edge<T, false>(roi[1], roi[3], b, k, W, e0, e1);
+        ws.eJ0[idx] = (short)e0;
+        ws.eJ1[idx] = (short)e1;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+psroipool_bwd_mask_kernel(PsBwdWs ws, int R, int H, int W, int k) {
+    const int NW = ws.NW;
+    const int nRow = k * H * NW, nCol = k * W * NW;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nRow + nCol; idx += gridDim.x * blockDim.x) {
+        const bool isRow = idx < nRow;
+        const int q = isRow ? idx : idx - nRow;
+        const int n = isRow ? H : W;
+        const int w = q % NW;
+        const int y = (q / NW) % n;
+        const int b = q / (NW * n);
+        const short* e0 = isRow ? ws.eI0 : ws.eJ0;
+        const short* e1 = isRow ? ws.eI1 : ws.eJ1;
+        uint32_t m = 0;
+        const int rEnd = min(R, (w + 1) * 32);
+        for (int r = w * 32; r < rEnd; ++r)
+            if (e0[r * k + b] <= y && y < e1[r * k + b]) m |= 1u << (r & 31);
+        (isRow ? ws.rowmask : ws.colmask)[q] = m;
+    }
+}
+
+// grid: (ceil(H*W / kPoolThreads), nChannels)
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+psroipool_bwd_kernel(const T* __restrict__ go, PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int W, int k,
+                     bool canonical) {
+    const int ch = blockIdx.y;
+    const int kk = k * k;
+    const int HW = H * W;
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = px < HW;
+    const int y = active ? px / W : 0;
+    const int x = active ? px - y * W : 0;
+    const int NW = ws.NW;
+
+    T acc = 0;
+    // entries (t, s=i*k+j) mapping to this channel, ascending t
+    const int tBeg = canonical ? ch / kk : 0;
+    const int tEnd = canonical ? tBeg + 1 : nT;
+    for (int t = tBeg; t < tEnd; ++t) {
+        int s;
+        if (canonical) {
+            s = ch - t * kk;
+        } else if (ch == 0) {
+            s = 0;  // (t+1)*0 == 0 for every target
+        } else {
+            if (ch % (t + 1) != 0) continue;
+            s = ch / (t + 1);
+            if (s >= kk || s == 0) continue;
+        }
+        const int i = s / k, j = s - i * k;
+        if (!active) continue;
+        const uint32_t* rm = ws.rowmask + ((size_t)i * H + y) * NW;
+        const uint32_t* cm = ws.colmask + ((size_t)j * W + x) * NW;
+        for (int w = 0; w < NW; ++w) {
+            uint32_t m = __ldg(rm + w) & __ldg(cm + w);
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int r = w * 32 + bit;
+                const int numel = (ws.eI1[r * k + i] - ws.eI0[r * k + i]) * (ws.eJ1[r * k + j] - ws.eJ0[r * k + j]);
+                T add = __ldg(go + ((size_t)r * nT + t) * kk + s);
+                add /= numel;  // numel > 0 here (the pixel is inside the cell)
+                acc += add;
+            }
+        }
+    }
+    if (active) gin[(size_t)ch * HW + px] = acc;
+}
+
+// =================================================================================
+// bin-edge instrumentation
+// =================================================================================
+template <typename T>
+__global__ void pool_bins_kernel(const T* __restrict__ rois, int32_t* __restrict__ edges, int R, int H, int W, int k,
+                                 int clampStart) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < R * k; idx += gridDim.x * blockDim.x) {
+        const int r = idx / k, b = idx - r * k;
+        const T* roi = rois + (size_t)r * 4;
+        int i0, i1, j0, j1;
+        if (clampStart) {
+            bin_edge<T, true>(roi[0], roi[2], b, k, H, i0, i1);
+            bin_edge<T, true>(roi[1], roi[3], b, k, W, j0, j1);
+        } else {
+            bin_edge<T, false>(roi[0], roi[2], b, k, H, i0, i1);
+            bin_edge<T, false>(roi[1], roi[3], b, k, W, j0, j1);
+        }
+        int32_t* e = edges + (size_t)idx * 4;
+        e[0] = i0;
+        e[1] = i1;
+        e[2] = j0;
+        e[3] = j1;
+    }
+}
+
+// =================================================================================
+// host launchers
+// =================================================================================
+struct SlabPlan {
+    int CB;       // channels per CTA
+    int RCH;      // RoIs per edge-table chunk
+    size_t smem;  // dynamic shared memory bytes
+    int grid;
+};
+
+// Choose the channel slab so that the grid is one balanced wave when possible.
+static int plan_slab(int R, int C, int H, int W, int k, size_t elem, size_t extra_per_cb, size_t extra_fixed,
+                     SlabPlan* plan) {
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const size_t budget = (size_t)di.max_smem_optin - 1024;
+    int RCH = R < 256 ? (R > 0 ? R : 1) : 256;
+    const size_t edgeBytes = align_up((size_t)4 * RCH * k * sizeof(short), 16);
+    const size_t perCB = (size_t)H * W * elem + extra_per_cb;
+    if (perCB + edgeBytes + extra_fixed > budget) {
+        set_error("feature map plane %dx%d (%zu B) does not fit the %zu B shared-memory slab", H, W,
+                  (size_t)H * W * elem, budget);
+        return D2T_ERR_BAD_ARG;
+    }
+    int maxCB = (int)((budget - edgeBytes - extra_fixed) / perCB);
+    int CB = ceil_div(C, di.sm_count);  // one wave, one CTA per SM
+    if (CB > maxCB) {
+        // several waves: balance them
+        const int waves = ceil_div(ceil_div(C, maxCB), di.sm_count);
+        CB = ceil_div(C, waves * di.sm_count);
+        if (CB > maxCB) CB = maxCB;
+    }
+    if (CB < 1) CB = 1;
+    plan->CB = CB;
+    plan->RCH = RCH;
+    plan->smem = align_up((size_t)CB * perCB, 16) + extra_fixed + edgeBytes;
+    plan->grid = ceil_div(C, CB);
+    return 0;
+}
+
+template <typename T>
+int roipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int C, int H, int W, int k, cudaStream_t st) {
+    D2T_REQUIRE(R >= 0 && C >= 0 && H > 0 && W > 0 && k > 0 && k <= kMaxK, "roipool_fwd: bad shape R=%d C=%d H=%d W=%d r_hw=%d", R,
+                C, H, W, k);
+    D2T_REQUIRE(H < 32768 && W < 32768, "roipool_fwd: H, W must be < 32768");
+    if (R == 0 || C == 0) return D2T_OK;
+    SlabPlan p;
+    int rc = plan_slab(R, C, H, W, k, sizeof(T), 0, 0, &p);
+    if (rc) return rc;
+    D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    roipool_fwd_kernel<T><<<p.grid, kPoolThreads, p.smem, st>>>(fm, rois, out, R, C, H, W, k, p.CB, p.RCH,
+                                                                 make_fastdiv(p.CB * k * k), make_fastdiv(k * k),
+                                                                 make_fastdiv(k));
+    D2T_CUDA_TRY(cudaGetLastError());
+    return D2T_OK;
+}
+
+template <typename T>
+int roipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int C, int H, int W, int k, cudaStream_t st) {
+    D2T_REQUIRE(R >= 0 && C >= 0 && H > 0 && W > 0 && k > 0 && k <= kMaxK, "roipool_bwd: bad shape R=%d C=%d H=%d W=%d r_hw=%d", R,
+                C, H, W, k);
+    D2T_REQUIRE(H < 32768 && W < 32768, "roipool_bwd: H, W must be < 32768");
+    if (C == 0) return D2T_OK;
+    if (R == 0) {
+        D2T_CUDA_TRY(cudaMemsetAsync(gin, 0, (size_t)C * H * W * sizeof(T), st));
+        return D2T_OK;
+    }
+    SlabPlan p;
+    const size_t kk = (size_t)k * k;
+    int rc = plan_slab(R, C, H, W, k, sizeof(T), kk * sizeof(T), align_up(kk * sizeof(T), 16), &p);
+    if (rc) return rc;
+    D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    roipool_bwd_kernel<T><<<p.grid, kPoolThreads, p.smem, st>>>(go, rois, gin, R, C, H, W, k, p.CB, p.RCH);
+    D2T_CUDA_TRY(cudaGetLastError());
+    return D2T_OK;
+}
+
+template <typename T>
+int psroipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int nT, int H, int W, int k, int flags,
+                         cudaStream_t st) {
+    D2T_REQUIRE(R >= 0 && nT > 0 && H > 0 && W > 0 && k > 0 && k <= kMaxK, "psroipool_fwd: bad shape R=%d nT=%d H=%d W=%d r_hw=%d",
+                R, nT, H, W, k);
+    if (R == 0) return D2T_OK;
+    const long long total = (long long)R * k * k * nT;
+    D2T_REQUIRE(total < (1ll << 31), "psroipool_fwd: output too large");
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    int grid = (int)((total + kPoolThreads - 1) / kPoolThreads);
+    const int cap = di.sm_count * 8;
+    if (grid > cap) grid = cap;
+    psroipool_fwd_kernel<T><<<grid, kPoolThreads, 0, st>>>(fm, rois, out, R, nT, H, W, k,
+                                                            (flags & D2T_PS_CANONICAL_MAP) != 0, make_fastdiv(nT),
+                                                            make_fastdiv(k), make_fastdiv(k * k));
+    D2T_CUDA_TRY(cudaGetLastError());
+    return D2T_OK;
+}
+
+static size_t psroipool_bwd_ws_layout(int R, int H, int W, int k, void* base, PsBwdWs* ws) {
+    const int NW = ceil_div(R > 0 ? R : 1, 32);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    const size_t e = (size_t)(R > 0 ? R : 1) * k * sizeof(short);
+    size_t o0 = take(e), o1 = take(e), o2 = take(e), o3 = take(e);
+    size_t orow = take((size_t)k * H * NW * 4), ocol = take((size_t)k * W * NW * 4);
+    if (ws) {
+        char* b = static_cast<char*>(base);
+        ws->eI0 = (short*)(b + o0);
+        ws->eI1 = (short*)(b + o1);
+        ws->eJ0 = (short*)(b + o2);
+        ws->eJ1 = (short*)(b + o3);
+        ws->rowmask = (uint32_t*)(b + orow);
+        ws->colmask = (uint32_t*)(b + ocol);
+        ws->NW = NW;
+    }
+    return off;
+}
+
+size_t psroipool_bwd_ws_bytes(int R, int H, int W, int k) { return psroipool_bwd_ws_layout(R, H, W, k, nullptr, nullptr); }
+
+template <typename T>
+int psroipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int nT, int H, int W, int k, int flags, void* wsp,
+                         size_t ws_bytes, cudaStream_t st) {
+    D2T_REQUIRE(R >= 0 && nT > 0 && H > 0 && W > 0 && k > 0 && k <= kMaxK, "psroipool_bwd: bad shape R=%d nT=%d H=%d W=%d r_hw=%d",
+                R, nT, H, W, k);
+    D2T_REQUIRE(H < 32768 && W < 32768, "psroipool_bwd: H, W must be < 32768");
+    const int nCh = nT * k * k;
+    D2T_REQUIRE(nCh <= 65535, "psroipool_bwd: n_targets*r_hw^2 must be <= 65535");
+    if (R == 0) {
+        D2T_CUDA_TRY(cudaMemsetAsync(gin, 0, (size_t)nCh * H * W * sizeof(T), st));
+        return D2T_OK;
+    }
+    const size_t need = psroipool_bwd_ws_bytes(R, H, W, k);
+    if (wsp == nullptr || ws_bytes < need) {
+        set_error("psroipool_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+        return D2T_ERR_WORKSPACE;
+    }
+    PsBwdWs ws;
+    psroipool_bwd_ws_layout(R, H, W, k, wsp, &ws);
+    psroipool_bwd_prep_kernel<T><<<ceil_div(R * k, kPoolThreads), kPoolThreads, 0, st>>>(rois, ws, R, H, W, k);
+    D2T_CUDA_TRY(cudaGetLastError());
+    const int nMask = k * (H + W) * ws.NW;
+    psroipool_bwd_mask_kernel<T><<<ceil_div(nMask, kPoolThreads), kPoolThreads, 0, st>>>(ws, R, H, W, k);
+    D2T_CUDA_TRY(cudaGetLastError());
+    dim3 grid(ceil_div(H * W, kPoolThreads), nCh);
+    psroipool_bwd_kernel<T><<<grid, kPoolThreads, 0, st>>>(go, ws, gin, R, nT, H, W, k,
+                                                            (flags & D2T_PS_CANONICAL_MAP) != 0);
+    D2T_CUDA_TRY(cudaGetLastError());
+    return D2T_OK;
+}
+
+template <typename T>
+int pool_bins_launch(const T* rois, int32_t* edges, int R, int H, int W, int k, int clampStart, cudaStream_t st) {
+    D2T_REQUIRE(R >= 0 && H > 0 && W > 0 && k > 0, "pool_bins: bad shape");
+    if (R == 0) return D2T_OK;
+    pool_bins_kernel<T><<<ceil_div(R * k, 256), 256, 0, st>>>(rois, edges, R, H, W, k, clampStart);
+    D2T_CUDA_TRY(cudaGetLastError());
+    return D2T_OK;
+}
+
+// explicit instantiations used by api.cu
+template int roipool_fwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+template int roipool_fwd_launch<double>(const double*, const double*, double*, int, int, int, int, int, cudaStream_t);
+template int roipool_bwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+template int roipool_bwd_launch<double>(const double*, const double*, double*, int, int, int, int, int, cudaStream_t);
+template int psroipool_fwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+template int psroipool_fwd_launch<double>(const double*, const double*, double*, int, int, int, int, int, int,
+                                          cudaStream_t);
+template int psroipool_bwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, int, void*, size_t,
+                                         cudaStream_t);
+template int psroipool_bwd_launch<double>(const double*, const double*, double*, int, int, int, int, int, int, void*,
+                                          size_t, cudaStream_t);
+template int pool_bins_launch<float>(const float*, int32_t*, int, int, int, int, int, cudaStream_t);
+template int pool_bins_launch<double>(const double*, int32_t*, int, int, int, int, int, cudaStream_t);
+
+}  // namespace d2t

@@ -1,0 +1,137 @@
+"""position-sensitive ROI pooling function and module.
+
+Host-side mirror of detect_to_track/models/ps_roipool/ps_roipool.py (Function
+:24-72, Module :75-99).  The channel map is the reference's
+(t+1)*(i*r_hw+j) (ps_roipool_cuda.cu:58); `canonical_map=True`
+is an opt-in extension selecting the textbook R-FCN map t*r_hw^2 + i*r_hw + j.
+"""
+from typing import Tuple
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+from torch.nn import Module
+
+from . import _lib
+from .roipool import _check_rois
+
+_CANONICAL = 1  # D2T_PS_CANONICAL_MAP
+
+
+def ps_roipool_forward(FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
+    """replaces `_ext.ps_roipool_forward` (ps_roipool.cpp:23-33)."""
+    _lib.check_input(FM, "FM")
+    if FM.dim() != 3:
+        raise RuntimeError(f"FM must be (n_targets*r_hw^2, H, W); got {tuple(FM.shape)}")
+    _check_rois(FM.dtype, FM.device, rois)
+    sfx = _lib.suffix(FM.dtype)
+    _, H, W = FM.shape
+    R = rois.size(0)
+    lib = _lib.lib()
+    with torch.cuda.device(FM.device):
+        out = torch.empty((R, n_targets, r_hw, r_hw), dtype=FM.dtype, device=FM.device)
+        rc = getattr(lib, f"d2t_psroipool_fwd_{sfx}")(
+            FM.data_ptr(), rois.data_ptr(), out.data_ptr(), R, n_targets, H, W, r_hw,
+            _CANONICAL if canonical_map else 0, None, 0, _lib.stream_ptr(FM.device))
+        _lib.check(rc, "ps_roipool_forward")
+    return out
+
+
+def ps_roipool_backward(grad_out: Tensor, rois: Tensor, fm_h: int, fm_w: int, canonical_map: bool = False) -> Tensor:
+    """replaces `_ext.ps_roipool_backward` (ps_roipool.cpp:36-47): R, n_targets, r_hw come from grad_out."""
+    _lib.check_input(grad_out, "gradOut")
+    if grad_out.dim() != 4 or grad_out.size(2) != grad_out.size(3):
+        raise RuntimeError(f"grad_out must be (|R|, n_targets, r_hw, r_hw); got {tuple(grad_out.shape)}")
+    _check_rois(grad_out.dtype, grad_out.device, rois)
+    sfx = _lib.suffix(grad_out.dtype)
+    R, n_targets, r_hw, _ = grad_out.shape
+    if rois.size(0) != R:
+        raise RuntimeError(f"grad_out has {R} RoIs but rois has {rois.size(0)}")
+    lib = _lib.lib()
+    with torch.cuda.device(grad_out.device):
+        grad_FM = torch.empty((n_targets * r_hw * r_hw, fm_h, fm_w), dtype=grad_out.dtype, device=grad_out.device)
+        nbytes = lib.d2t_psroipool_bwd_workspace_bytes(R, n_targets, fm_h, fm_w, r_hw, grad_out.element_size())
+        ws, ws_ptr, ws_n = _lib.workspace(nbytes, grad_out.device)
+        rc = getattr(lib, f"d2t_psroipool_bwd_{sfx}")(
+            grad_out.data_ptr(), rois.data_ptr(), grad_FM.data_ptr(), R, n_targets, fm_h, fm_w, r_hw,
+            _CANONICAL if canonical_map else 0, ws_ptr, ws_n, _lib.stream_ptr(grad_out.device))
+        _lib.check(rc, "ps_roipool_backward")
+    return grad_FM
+
+
+class PSROIPoolFunction(Function):
+    """position-sensitive ROI-pooling function.
+    see https://arxiv.org/abs/1605.06409"""
+
+    @staticmethod
+    def forward(ctx, FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
+        """
+        Args:
+            FM: (n_targets * r_hw^2, H, W); feature map for position-sensitive
+                pooling.
+            rois: (|R|, 4); region of interest bounding boxes.
+            n_targets: number of targets per ROI.
+            r_hw: height and width of pooled features.
+
+        Returns:
+            pooled: (|R|, n_targets, r_hw, r_hw) pooled feature map.
+        """
+        ctx.save_for_backward(rois)
+        _, ctx.fm_h, ctx.fm_w = FM.shape
+        ctx.canonical_map = canonical_map
+
+        expected_channels = n_targets * r_hw ** 2
+        if FM.size(0) != expected_channels:
+            raise ValueError(
+                f"expected {expected_channels} feature map channels, "
+                f"recieved feature map of shape {tuple(FM.shape)}"
+            )
+
+        return ps_roipool_forward(FM, rois, n_targets, r_hw, canonical_map)
+
+    @staticmethod
+    def backward(ctx: object, grad_out: Tensor) -> Tuple[Tensor, None, None, None, None]:
+        """
+        Args:
+            grad_out: (|R|, n_targets, r_hw, r_hw); loss derivatives wrt
+                pooling output.
+
+        Returns:
+            grad_FM: (n_targets * r_hw^2, H, W); loss derivatives wrt
+                pooling input.
+        """
+        grad_out = grad_out.contiguous()
+        rois, = ctx.saved_tensors
+        grad_FM = ps_roipool_backward(grad_out, rois, ctx.fm_h, ctx.fm_w, ctx.canonical_map)
+        return grad_FM, None, None, None, None
+
+
+class PSROIPool(Module):
+    """position-sensitive ROI-Pooling layer.
+    see https://arxiv.org/abs/1605.06409
+
+    Args:
+        n_targets: number of targets per ROI.
+        r_hw: height and with of pooled features.
+        canonical_map: opt-in extension, see module docstring (default: reference behaviour).
+    """
+
+    def __init__(self, n_targets: int, r_hw: int, canonical_map: bool = False) -> None:
+        super().__init__()
+        self.n_targets = n_targets
+        self.r_hw = r_hw
+        self.canonical_map = canonical_map
+
+    def forward(self, FM: Tensor, rois: Tensor) -> Tensor:
+        """
+        Args:
+            FM: (n_targets * r_hw^2, H, W); feature map for position-sensitive
+                pooling.
+            rois: (|R|, 4) region of interest bounding boxes.
+
+        Returns:
+            pooled: (|R|, n_targets, r_hw, r_hw): pooled output.
+        """
+        if self.canonical_map:
+            return PSROIPoolFunction.apply(FM, rois, self.n_targets, self.r_hw, True)
+        return PSROIPoolFunction.apply(FM, rois, self.n_targets, self.r_hw)

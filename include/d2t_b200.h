@@ -1,0 +1,143 @@
+/*
+ * d2t_b200.h -- C ABI of libd2t_b200.so: detect-to-track's custom-op hot path
+ * (PointwiseCorrelation, ROIPool, PSROIPool; forward + backward) as
+ * hand-written CUDA for sm_100a.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one function of the
+ * reference's pybind surface (paths relative to
+ * /root/reference/detect_to_track/models/):
+ *
+ *   d2t_corr_fwd_*        <- pointwise_correlation_forward   pointwise_correlation/pointwise_correlation.cpp:23-33,52-56
+ *                            (launcher pointwise_correlation_cuda.cu:178-210, kernel :63-111)
+ *   d2t_corr_bwd_*        <- pointwise_correlation_backward  pointwise_correlation.cpp:36-48,57-61
+ *                            (launcher pointwise_correlation_cuda.cu:214-249, kernel :121-174)
+ *   d2t_roipool_fwd_*     <- roipool_forward                 roipool/roipool.cpp:22-31,49-53
+ *                            (launcher roipool_cuda.cu:130-158, kernel :6-63)
+ *   d2t_roipool_bwd_*     <- roipool_backward                roipool/roipool.cpp:34-45,54-58
+ *                            (launcher roipool_cuda.cu:161-190, kernel :68-127)
+ *   d2t_psroipool_fwd_*   <- ps_roipool_forward              ps_roipool/ps_roipool.cpp:23-33,51-55
+ *                            (launcher ps_roipool_cuda.cu:144-174, kernel :10-71)
+ *   d2t_psroipool_bwd_*   <- ps_roipool_backward             ps_roipool/ps_roipool.cpp:36-47,56-60
+ *                            (launcher ps_roipool_cuda.cu:177-204, kernel :76-141)
+ *
+ * Conventions
+ *   - Plain pointers and ints only; no torch / ATen types.  All data pointers
+ *     are DEVICE pointers to dense, C-contiguous arrays of the stated shape.
+ *   - `_f32` = float, `_f64` = double (the reference dispatches exactly these
+ *     two, AT_DISPATCH_FLOATING_TYPES).
+ *   - The CALLER owns every buffer.  Outputs need NOT be zero-initialised: the
+ *     kernels define every output element (dead correlation entries, untouched
+ *     gradient pixels and empty PSROI cells are written as 0).  The reference
+ *     instead allocates zeroed outputs itself (e.g. pointwise_correlation_cuda.cu:192).
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream, which is what
+ *     the reference always uses).  Calls are asynchronous.
+ *   - `ws` / `ws_bytes`: caller-provided scratch of at least
+ *     d2t_*_workspace_bytes(...) bytes, 256-byte aligned; may be NULL when that
+ *     function returns 0.  Contents are undefined afterwards.
+ *   - Return value: 0 on success; non-zero on bad arguments or a CUDA launch
+ *     error, with a message retrievable from d2t_last_error() (thread-local).
+ *   - Re-entrant; no global mutable state besides a per-device attribute cache.
+ *   - Results are deterministic: no floating-point atomics anywhere.
+ *
+ * RoIs are fractional (centre_i, centre_j, height, width) in [0,1] map units,
+ * one image per call, exactly like the reference.
+ */
+#ifndef D2T_B200_H
+#define D2T_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2T_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define D2T_API __attribute__((visibility("default")))
+#else
+#define D2T_API
+#endif
+
+/* status codes */
+#define D2T_OK 0
+#define D2T_ERR_BAD_ARG 1
+#define D2T_ERR_CUDA 2
+#define D2T_ERR_WORKSPACE 3
+
+D2T_API int d2t_abi_version(void);
+D2T_API const char* d2t_last_error(void);
+
+/* ---- PointwiseCorrelation ------------------------------------------------
+ * fm0, fm1 : (B, C, H, W)            feature maps at t and t+tau
+ * out      : (B, H, W, 2d+1, 2d+1)   out[b,i,j,ci,cj] = sum_c fm0[b,c,i,j] * fm1[b,c,i-d+ci,j-d+cj]
+ *            for the reference's live displacement set (exclusive upper bound,
+ *            stride phase tied to the clamped start: SURVEY.md F4/F5); 0 elsewhere.
+ */
+D2T_API size_t d2t_corr_fwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size);
+D2T_API int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max,
+                     int stride, void* ws, size_t ws_bytes, void* stream);
+D2T_API int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
+                     int stride, void* ws, size_t ws_bytes, void* stream);
+
+/* grad_out : (B, H, W, 2d+1, 2d+1);  grad_fm0, grad_fm1 : (B, C, H, W) */
+D2T_API size_t d2t_corr_bwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size);
+D2T_API int d2t_corr_bwd_f32(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0,
+                     float* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,
+                     size_t ws_bytes, void* stream);
+D2T_API int d2t_corr_bwd_f64(const double* grad_out, const double* fm0, const double* fm1, double* grad_fm0,
+                     double* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* ---- ROIPool (average pooling) ------------------------------
+ * fm   : (C, H, W);  rois : (R, 4) same dtype;  out : (R, C, r_hw, r_hw)
+ * Empty bins give 0/0 = NaN like the reference (F7).
+ */
+D2T_API size_t d2t_roipool_fwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int elem_size);
+D2T_API int d2t_roipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int r_hw,
+                        void* ws, size_t ws_bytes, void* stream);
+D2T_API int d2t_roipool_fwd_f64(const double* fm, const double* rois, double* out, int R, int C, int H, int W,
+                        int r_hw, void* ws, size_t ws_bytes, void* stream);
+
+/* grad_out : (R, C, r_hw, r_hw);  grad_fm : (C, H, W) */
+D2T_API size_t d2t_roipool_bwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int elem_size);
+D2T_API int d2t_roipool_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int R, int C, int H, int W,
+                        int r_hw, void* ws, size_t ws_bytes, void* stream);
+D2T_API int d2t_roipool_bwd_f64(const double* grad_out, const double* rois, double* grad_fm, int R, int C, int H,
+                        int W, int r_hw, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- PSROIPool -------------------------------------------------------------
+ * fm : (n_targets*r_hw^2, H, W);  rois : (R, 4);  out : (R, n_targets, r_hw, r_hw)
+ * flags: bit 0 (D2T_PS_CANONICAL_MAP) selects the textbook R-FCN channel map
+ *        t*k*k + i*k + j; 0 (default) = the reference's (t+1)*(i*k+j) (F6).
+ */
+#define D2T_PS_CANONICAL_MAP 1
+D2T_API size_t d2t_psroipool_fwd_workspace_bytes(int R, int n_targets, int H, int W, int r_hw, int elem_size);
+D2T_API int d2t_psroipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int n_targets, int H, int W,
+                          int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
+D2T_API int d2t_psroipool_fwd_f64(const double* fm, const double* rois, double* out, int R, int n_targets, int H,
+                          int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* grad_out : (R, n_targets, r_hw, r_hw);  grad_fm : (n_targets*r_hw^2, H, W) */
+D2T_API size_t d2t_psroipool_bwd_workspace_bytes(int R, int n_targets, int H, int W, int r_hw, int elem_size);
+D2T_API int d2t_psroipool_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int R, int n_targets,
+                          int H, int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
+D2T_API int d2t_psroipool_bwd_f64(const double* grad_out, const double* rois, double* grad_fm, int R, int n_targets,
+                          int H, int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- integer bin edges (parity instrumentation) ----------------------------
+ * edges : (R, r_hw, 4) int32 = (I0, I1, J0, J1) of row-bin / column-bin b,
+ * computed on the device by the same code the pooling kernels use.
+ * clamp_start != 0 -> ROIPool rule (roipool_cuda.cu:38-50), 0 -> PSROIPool
+ * rule (ps_roipool_cuda.cu:42-54).  Must be bit-exact against the reference.
+ */
+D2T_API int d2t_pool_bins_f32(const float* rois, int32_t* edges, int R, int H, int W, int r_hw, int clamp_start,
+                      void* stream);
+D2T_API int d2t_pool_bins_f64(const double* rois, int32_t* edges, int R, int H, int W, int r_hw, int clamp_start,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2T_B200_H */

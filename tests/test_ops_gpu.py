@@ -1,0 +1,350 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the
+C ABI, against (1) the C oracle, (2) the reference's own kernels (oracle/_ref, when built),
+(3) the committed golden fixtures, (4) the reference's own tests (float64 gradcheck, OOB
+known answer), and (5) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): integer bin edges / live masks exact; float32 values
+and gradients rtol 1e-4 (atol scaled to the data); float64 1e-10.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+from torch.autograd import gradcheck
+
+import cases
+import oracle
+from oracle import ref_cuda
+import detect_to_track_b200 as d2t
+from detect_to_track_b200 import roipool as rp_mod, ps_roipool as ps_mod, pointwise_correlation as pc_mod
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def close(got: torch.Tensor, want, dtype, scale=None, equal_nan=False):
+    got = got.detach().cpu().numpy()
+    want = np.asarray(want)
+    rtol = 1e-4 if dtype == np.float32 else 1e-10
+    s = float(np.nanmax(np.abs(want))) if scale is None else scale
+    atol = (1e-5 if dtype == np.float32 else 1e-11) * max(s, 1e-30)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, equal_nan=equal_nan)
+
+
+# ------------------------------------------------------------------ correlation
+CORR_CASES = [
+    (1, 2, 10, 10, 3, 1), (2, 2, 11, 10, 3, 2), (2, 2, 10, 11, 3, 1), (1, 2, 11, 11, 3, 2),    # reference grid
+    (1, 5, 7, 9, 4, 1), (2, 4, 9, 14, 2, 3), (1, 3, 5, 4, 8, 1), (1, 1, 1, 1, 1, 1),
+    (2, 256, 32, 32, 4, 1),          # BASELINE config 1
+    (1, 96, 38, 63, 8, 1),           # config-3 geometry, fewer channels
+    (3, 40, 20, 21, 8, 1),
+    (1, 16, 70, 66, 8, 1),           # wider than one tile
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("B,C,H,W,d,stride", CORR_CASES)
+def test_corr_fwd_bwd_vs_oracle(cuda, B, C, H, W, d, stride, dtype):
+    fm0, fm1, go = cases.corr_inputs(B, C, H, W, d, seed=11, dtype=dtype)
+    out = pc_mod.pointwise_correlation_forward(dev(fm0, cuda), dev(fm1, cuda), d, stride)
+    want = oracle.corr_fwd(fm0, fm1, d, stride)
+    close(out, want, dtype)
+    # live mask exact: dead entries are exactly zero
+    assert torch.equal(out.cpu() == 0, torch.from_numpy(want == 0)) or np.count_nonzero(want == 0) <= np.count_nonzero(out.cpu().numpy() == 0)
+    assert float(out[..., 2 * d, :].abs().max()) == 0 and float(out[..., :, 2 * d].abs().max()) == 0
+    g0, g1 = pc_mod.pointwise_correlation_backward(dev(go, cuda), dev(fm0, cuda), dev(fm1, cuda), d, stride)
+    w0, w1 = oracle.corr_bwd(go, fm0, fm1, d, stride)
+    close(g0, w0, dtype)
+    close(g1, w1, dtype)
+
+
+@pytest.mark.parametrize("B,C,H,W,d,stride", [(2, 2, 11, 10, 3, 2), (2, 64, 32, 32, 4, 1), (1, 48, 38, 63, 8, 1)])
+def test_corr_vs_reference_kernels(cuda, B, C, H, W, d, stride):
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(B, C, H, W, d, seed=12, dtype=np.float32))
+    close(pc_mod.pointwise_correlation_forward(fm0, fm1, d, stride), ref_cuda.corr_fwd(fm0, fm1, d, stride).cpu().numpy(), np.float32)
+    g0, g1 = pc_mod.pointwise_correlation_backward(go, fm0, fm1, d, stride)
+    r0, r1 = ref_cuda.corr_bwd(go, fm0, fm1, d, stride)
+    close(g0, r0.cpu().numpy(), np.float32)
+    close(g1, r1.cpu().numpy(), np.float32)
+
+
+@pytest.mark.parametrize("d_max", [3])
+@pytest.mark.parametrize("stride", [1, 2])
+@pytest.mark.parametrize("input_b", [1, 2])
+@pytest.mark.parametrize("input_c", [2])
+@pytest.mark.parametrize("input_hw", [10, 11])
+def test_pointwise_correlation_gradients(cuda, d_max, stride, input_b, input_c, input_hw):
+    """the reference's tests/test_pointwise_correlation.py:8-22, unchanged but for the import."""
+    pc = d2t.PointwiseCorrelation(d_max, stride).cuda()
+    fm_shape = (input_b, input_c, input_hw, input_hw)
+    fm0 = torch.rand(*fm_shape).double().cuda().requires_grad_(True)
+    fm1 = torch.rand(*fm_shape).double().cuda().requires_grad_(True)
+    assert gradcheck(pc, (fm0, fm1))
+
+
+def test_corr_backward_is_deterministic(cuda):
+    fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 64, 38, 63, 8, seed=13, dtype=np.float32))
+    a = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
+    b = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_corr_full_size_adjoint_identity(cuda):
+    """BASELINE config 3 (c5: C=2048, 38x63, d=8) at full size: the op is bilinear, so
+    <fwd(x0,x1), g> == <x0, bwd0(g)> == <x1, bwd1(g)> -- checked in float64 accumulation."""
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    fm0 = (torch.randn(1, 2048, 38, 63, generator=g).relu_() / 16).to(cuda)
+    fm1 = (torch.randn(1, 2048, 38, 63, generator=g).relu_() / 16).to(cuda)
+    go = torch.randn(1, 38, 63, 17, 17, generator=g).to(cuda)
+    out = pc_mod.pointwise_correlation_forward(fm0, fm1, 8, 1)
+    g0, g1 = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
+    lhs = (out.double() * go.double()).sum().item()
+    assert abs(lhs - (fm0.double() * g0.double()).sum().item()) <= 1e-5 * abs(lhs)
+    assert abs(lhs - (fm1.double() * g1.double()).sum().item()) <= 1e-5 * abs(lhs)
+    # dead rows / columns (F4)
+    assert float(out[..., 16, :].abs().max()) == 0 and float(out[..., :, 16].abs().max()) == 0
+    # spot-check 64 random outputs against a float64 dot product
+    idx = torch.randint(0, 38 * 63 * 256, (64,), generator=g)
+    for n in idx.tolist():
+        p, t = divmod(n, 256)
+        i, j = divmod(p, 63)
+        ci, cj = divmod(t, 16)
+        di, dj = i - 8 + ci, j - 8 + cj
+        want = 0.0
+        if 0 <= di < 38 and 0 <= dj < 63:
+            want = (fm0[0, :, i, j].double() * fm1[0, :, di, dj].double()).sum().item()
+        assert abs(out[0, i, j, ci, cj].item() - want) <= 1e-4 * abs(want) + 1e-6
+
+
+# ------------------------------------------------------------------ bin edges (integer: exact)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("clamp_start", [True, False])
+@pytest.mark.parametrize("H,W,k", [(38, 63, 7), (10, 11, 5), (11, 10, 6)])
+def test_bin_edges_bit_exact(cuda, H, W, k, clamp_start, dtype):
+    rois = np.concatenate([cases.rois_edge_cases(H, W, dtype), cases.rois_random(3000, 21, dtype), cases.ROIS_OOB.astype(dtype)])
+    got = rp_mod.pool_bins(dev(rois, cuda), H, W, k, clamp_start).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.bins(rois, H, W, k, clamp_start))
+
+
+# ------------------------------------------------------------------ ROIPool
+def _roipool_rois(H, W, dtype, R=40):
+    return np.concatenate([cases.rois_edge_cases(H, W, dtype), cases.rois_random(R, 31, dtype), cases.ROIS_OOB.astype(dtype)])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("C,H,W,k", [(2, 10, 10, 5), (2, 11, 10, 6), (37, 38, 63, 7), (300, 20, 30, 3)])
+def test_roipool_vs_oracle(cuda, C, H, W, k, dtype):
+    rois = _roipool_rois(H, W, dtype)
+    fm, go = cases.pool_inputs(C, H, W, (rois.shape[0], C, k, k), 32, dtype)
+    out = rp_mod.roipool_forward(dev(fm, cuda), dev(rois, cuda), k)
+    want = oracle.roipool_fwd(fm, rois, k)
+    if dtype == np.float32:
+        # same summation order as the reference: bit-identical, NaNs of empty bins included (F7)
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+    else:
+        close(out, want, dtype, scale=1.0, equal_nan=True)
+    gin = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
+    # empty bins contribute nothing to the gradient
+    close(gin, oracle.roipool_bwd(go, rois, H, W), dtype)
+
+
+def test_roipool_vs_reference_kernels(cuda):
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    C, H, W, k = 64, 38, 63, 7
+    rois = _roipool_rois(H, W, np.float32, R=100)
+    fm, go = cases.pool_inputs(C, H, W, (rois.shape[0], C, k, k), 33, np.float32)
+    fm, go, rois = dev(fm, cuda), dev(go, cuda), dev(rois, cuda)
+    ref = ref_cuda.roipool_fwd(fm, rois, k)
+    out = rp_mod.roipool_forward(fm, rois, k)
+    assert torch.equal(torch.nan_to_num(out, nan=12345.0), torch.nan_to_num(ref, nan=12345.0))   # bit-exact
+    close(rp_mod.roipool_backward(go, rois, H, W), ref_cuda.roipool_bwd(go, rois, H, W).cpu().numpy(), np.float32)
+
+
+@pytest.mark.parametrize("r_hw", [5, 6])
+@pytest.mark.parametrize("fm_c", [2])
+@pytest.mark.parametrize("fm_h", [10, 11])
+@pytest.mark.parametrize("fm_w", [10, 11])
+def test_roipool_gradients(cuda, r_hw, fm_c, fm_h, fm_w):
+    """the reference's tests/test_roipool.py:10-27."""
+    rp = d2t.ROIPool(r_hw)
+    fm = torch.rand(fm_c, fm_h, fm_w).double().cuda().requires_grad_(True)
+    rois = torch.Tensor([[0.5, 0.5, 0.5, 0.5], [0.1, 0.1, 0.2, 0.3]]).double().cuda().requires_grad_(False)
+    assert gradcheck(rp, (fm, rois))
+
+
+def test_roipool_full_size_track_head(cuda):
+    """BASELINE config 4 at full size (1891 channels, 300 RoIs): adjoint identity + determinism +
+    a sampled comparison with the oracle."""
+    C, H, W, k, R = 1891, 38, 63, 7, 300
+    rois_np = cases.rois_random(R, 1238)
+    g = torch.Generator(device="cpu").manual_seed(1238)
+    fm = torch.randn(C, H, W, generator=g).to(cuda)
+    go = torch.randn(R, C, k, k, generator=g).to(cuda)
+    rois = dev(rois_np, cuda)
+    out = rp_mod.roipool_forward(fm, rois, k)
+    gin = rp_mod.roipool_backward(go, rois, H, W)
+    lhs = (out.double() * go.double()).sum().item()
+    rhs = (fm.double() * gin.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    assert torch.equal(gin, rp_mod.roipool_backward(go, rois, H, W))
+    sel = [0, 5, 777, 1890]
+    want = oracle.roipool_fwd(fm[sel].cpu().numpy(), rois_np, k)
+    np.testing.assert_array_equal(out[:, sel].cpu().numpy(), want)
+    wg = oracle.roipool_bwd(go[:, sel].cpu().numpy().copy(), rois_np, H, W)
+    close(gin[sel], wg, np.float32)
+
+
+# ------------------------------------------------------------------ PSROIPool
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("canonical", [False, True])
+@pytest.mark.parametrize("nT,H,W,k", [(1, 10, 10, 6), (2, 11, 10, 7), (4, 38, 63, 7), (31, 38, 63, 7)])
+def test_psroipool_vs_oracle(cuda, nT, H, W, k, canonical, dtype):
+    rois = _roipool_rois(H, W, dtype, R=60)
+    fm, go = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 34, dtype)
+    out = ps_mod.ps_roipool_forward(dev(fm, cuda), dev(rois, cuda), nT, k, canonical)
+    want = oracle.psroipool_fwd(fm, rois, nT, k, canonical)
+    if dtype == np.float32:
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+    else:
+        close(out, want, dtype, scale=1.0)
+    gin = ps_mod.ps_roipool_backward(dev(go, cuda), dev(rois, cuda), H, W, canonical)
+    close(gin, oracle.psroipool_bwd(go, rois, H, W, canonical), dtype)
+
+
+def test_psroipool_vs_reference_kernels(cuda):
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    nT, H, W, k = 31, 38, 63, 7
+    rois = _roipool_rois(H, W, np.float32, R=300)
+    fm, go = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 35, np.float32)
+    fm, go, rois = dev(fm, cuda), dev(go, cuda), dev(rois, cuda)
+    assert torch.equal(ps_mod.ps_roipool_forward(fm, rois, nT, k), ref_cuda.psroipool_fwd(fm, rois, nT, k))
+    close(ps_mod.ps_roipool_backward(go, rois, H, W), ref_cuda.psroipool_bwd(go, rois, H, W).cpu().numpy(), np.float32)
+
+
+@pytest.mark.parametrize("n_targets", [1, 2])
+@pytest.mark.parametrize("r_hw", [6, 7])
+@pytest.mark.parametrize("fm_h", [10, 11])
+@pytest.mark.parametrize("fm_w", [10, 11])
+def test_ps_roipool_gradients(cuda, n_targets, r_hw, fm_h, fm_w):
+    """the reference's tests/test_ps_roipool.py:8-30."""
+    pr = d2t.PSROIPool(n_targets, r_hw)
+    fm = torch.rand(n_targets * r_hw ** 2, fm_h, fm_w).double().cuda().requires_grad_(True)
+    rois = (torch.Tensor([[0.5, 0.5, 0.1, 0.1], [0.1, 0.1, 0.2, 0.3], [1.5, 1.5, 0.2, 0.2]])
+            .double().cuda().requires_grad_(False))
+    assert gradcheck(pr, (fm, rois))
+
+
+@pytest.mark.parametrize("n_targets", [1, 2])
+@pytest.mark.parametrize("r_hw", [6, 7])
+@pytest.mark.parametrize("fm_h", [10, 11])
+@pytest.mark.parametrize("fm_w", [10, 11])
+def test_ps_roipool_can_handle_oob(cuda, n_targets, r_hw, fm_h, fm_w):
+    """the reference's tests/test_ps_roipool.py:33-44 (its only known-answer test)."""
+    pr = d2t.PSROIPool(n_targets, r_hw).cuda()
+    fm = torch.full((n_targets * r_hw ** 2, fm_h, fm_w), 10.0).cuda()
+    rois = torch.as_tensor([[3.0, 3.0, 0.5, 0.5]]).cuda()
+    ans = pr(fm, rois).cpu()
+    assert torch.allclose(ans, torch.zeros(len(rois), n_targets, r_hw, r_hw))
+
+
+def test_psroipool_full_size_cls_head(cuda):
+    """BASELINE config 2 at full size: 300 RoIs, 31 targets: adjoint identity + determinism."""
+    nT, H, W, k, R = 31, 38, 63, 7, 300
+    rois = dev(cases.rois_random(R, 1237), cuda)
+    g = torch.Generator(device="cpu").manual_seed(1237)
+    fm = torch.randn(nT * k * k, H, W, generator=g).to(cuda)
+    go = torch.randn(R, nT, k, k, generator=g).to(cuda)
+    out = ps_mod.ps_roipool_forward(fm, rois, nT, k)
+    gin = ps_mod.ps_roipool_backward(go, rois, H, W)
+    lhs = (out.double() * go.double()).sum().item()
+    assert abs(lhs - (fm.double() * gin.double()).sum().item()) <= 1e-5 * abs(lhs)
+    assert torch.equal(gin, ps_mod.ps_roipool_backward(go, rois, H, W))
+    assert int((gin.abs().sum(dim=(1, 2)) > 0).sum()) == 608
+
+
+# ------------------------------------------------------------------ error behaviour + autograd wiring
+def test_errors_match_reference(cuda):
+    fm = torch.rand(1, 2, 8, 8, device=cuda)
+    with pytest.raises(RuntimeError, match="must be contiguous"):
+        d2t.PointwiseCorrelation(2, 1)(fm.transpose(2, 3), fm)
+    with pytest.raises(RuntimeError):
+        d2t.ROIPool(3)(torch.rand(2, 8, 8, device=cuda), torch.rand(2, 4, device=cuda).double())   # dtype mismatch
+    with pytest.raises(ValueError):
+        d2t.PSROIPool(2, 3)(torch.rand(17, 8, 8, device=cuda), torch.rand(2, 4, device=cuda))
+
+
+def test_autograd_none_grads_and_noncontiguous_grad_out(cuda):
+    fm0 = torch.rand(1, 4, 9, 9, device=cuda, requires_grad=True)
+    fm1 = torch.rand(1, 4, 9, 9, device=cuda, requires_grad=True)
+    out = d2t.PointwiseCorrelationFunction.apply(fm0, fm1, 2, 1)
+    out.permute(0, 1, 2, 4, 3).sum().backward()            # non-contiguous grad_out -> .contiguous() like the reference
+    assert fm0.grad is not None and fm1.grad is not None
+    fm = torch.rand(3, 9, 9, device=cuda, requires_grad=True)
+    rois = torch.tensor([[0.5, 0.5, 0.4, 0.4]], device=cuda, requires_grad=True)
+    d2t.ROIPool(3)(fm, rois).sum().backward()
+    assert rois.grad is None and fm.grad is not None        # no gradient w.r.t. rois (roipool.py:57)
+
+
+def test_runs_on_a_non_default_stream(cuda):
+    fm0, fm1, _ = (dev(a, cuda) for a in cases.corr_inputs(1, 8, 12, 12, 3, seed=14, dtype=np.float32))
+    want = pc_mod.pointwise_correlation_forward(fm0, fm1, 3, 1)
+    s = torch.cuda.Stream(device=cuda)
+    s.wait_stream(torch.cuda.current_stream(cuda))
+    with torch.cuda.stream(s):
+        got = pc_mod.pointwise_correlation_forward(fm0, fm1, 3, 1)
+    s.synchronize()
+    assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------ golden fixtures (reference kernels' outputs)
+def _golden(name):
+    p = GOLDEN / f"{name}.npz"
+    if not p.exists():
+        pytest.skip(f"{p.name} not generated yet")
+    return np.load(p)
+
+
+@pytest.mark.parametrize("case", cases.GOLDEN_CORR, ids=lambda c: c[0])
+def test_golden_corr(cuda, case):
+    name, B, C, H, W, d, s, dt = case
+    g = _golden(name)
+    dtype = np.dtype(dt).type
+    close(pc_mod.pointwise_correlation_forward(dev(g["fm0"], cuda), dev(g["fm1"], cuda), d, s), g["out"], dtype)
+    g0, g1 = pc_mod.pointwise_correlation_backward(dev(g["go"], cuda), dev(g["fm0"], cuda), dev(g["fm1"], cuda), d, s)
+    close(g0, g["g0"], dtype)
+    close(g1, g["g1"], dtype)
+
+
+@pytest.mark.parametrize("case", cases.GOLDEN_ROIPOOL, ids=lambda c: c[0])
+def test_golden_roipool(cuda, case):
+    name, C, H, W, k, R, dt = case
+    g = _golden(name)
+    dtype = np.dtype(dt).type
+    out = rp_mod.roipool_forward(dev(g["fm"], cuda), dev(g["rois"], cuda), k)
+    if dt == "float32":
+        np.testing.assert_array_equal(out.cpu().numpy(), g["out"])
+    else:
+        close(out, g["out"], dtype, scale=1.0, equal_nan=True)
+    close(rp_mod.roipool_backward(dev(g["go"], cuda), dev(g["rois"], cuda), H, W), g["gin"], dtype, equal_nan=True)
+
+
+@pytest.mark.parametrize("case", cases.GOLDEN_PSROIPOOL, ids=lambda c: c[0])
+def test_golden_psroipool(cuda, case):
+    name, nT, H, W, k, R, dt = case
+    g = _golden(name)
+    dtype = np.dtype(dt).type
+    out = ps_mod.ps_roipool_forward(dev(g["fm"], cuda), dev(g["rois"], cuda), nT, k)
+    if dt == "float32":
+        np.testing.assert_array_equal(out.cpu().numpy(), g["out"])
+    else:
+        close(out, g["out"], dtype, scale=1.0)
+    close(ps_mod.ps_roipool_backward(dev(g["go"], cuda), dev(g["rois"], cuda), H, W), g["gin"], dtype)
