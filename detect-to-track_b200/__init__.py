@@ -9,9 +9,11 @@ include/d2t_b200.h.  No Triton, no CPU fallback.
 from .pointwise_correlation import PointwiseCorrelation, PointwiseCorrelationFunction
 from .roipool import ROIPool, ROIPoolFunction
 from .ps_roipool import PSROIPool, PSROIPoolFunction
+from .models import RFCN, CorrelationTracker
 
 __all__ = [
     "PointwiseCorrelation", "PointwiseCorrelationFunction",
     "ROIPool", "ROIPoolFunction",
     "PSROIPool", "PSROIPoolFunction",
+    "RFCN", "CorrelationTracker",
 ]

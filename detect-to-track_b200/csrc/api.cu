@@ -60,6 +60,7 @@ size_t psroipool_bwd_ws_bytes(int R, int H, int W, int k);
 
 // tuned float32 correlation (corr_tile.cu)
 bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
+bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride);
 size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d);
 size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d);
 int corr_tile_fwd_launch(const float*, const float*, float*, int, int, int, int, int, void*, size_t, cudaStream_t);
@@ -91,7 +92,7 @@ size_t d2t_corr_fwd_workspace_bytes(int B, int C, int H, int W, int d_max, int s
     return 0;
 }
 size_t d2t_corr_bwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size) {
-    if (elem_size == 4 && corr_tile_supported(B, C, H, W, d_max, stride)) return corr_tile_bwd_ws_bytes(B, C, H, W, d_max);
+    if (elem_size == 4 && corr_tile_bwd_supported(B, C, H, W, d_max, stride)) return corr_tile_bwd_ws_bytes(B, C, H, W, d_max);
     return 0;
 }
 
@@ -116,7 +117,7 @@ int d2t_corr_bwd_f32(const float* grad_out, const float* fm0, const float* fm1, 
     int rc = check_corr(grad_out, fm0, fm1, B, C, H, W, d_max, stride, "d2t_corr_bwd_f32");
     if (rc) return rc;
     D2T_REQUIRE((long long)B * C * H * W == 0 || (grad_fm0 && grad_fm1), "d2t_corr_bwd_f32: null output pointer");
-    if (corr_tile_supported(B, C, H, W, d_max, stride))
+    if (corr_tile_bwd_supported(B, C, H, W, d_max, stride))
         return corr_tile_bwd_launch(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, ws, ws_bytes,
                                     (cudaStream_t)stream);
     return corr_bwd_generic_launch<float>(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, stride,

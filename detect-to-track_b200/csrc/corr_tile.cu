@@ -1,19 +1,568 @@
-// corr_tile.cu -- tuned float32 PointwiseCorrelation kernels (placeholder: not yet enabled).
+// corr_tile.cu -- tuned float32 PointwiseCorrelation for sm_100a (stride 1, d_max in {4, 8}).
+//
+// The reference (pointwise_correlation_cuda.cu:63-111) runs one thread per query
+// position, accumulating (2d)^2 * C products in GLOBAL memory: 3 thread blocks on a
+// 148-SM part for a 38x63 map.  Here the correlation is treated as what it is, a
+// banded contraction over channels, and laid out for the FP32 pipe:
+//
+//   tile    : QROWS x 16 query positions (8x16 for d=8) and their (QROWS+2d-1) x (16+2d-1)
+//             key halo patch, staged per channel chunk in shared memory (NCHW is already
+//             the right operand layout: for one channel both operands are row vectors
+//             over positions, so every FMA is an outer-product term, no transposes).
+//   thread  : 8 consecutive queries of one row x all 2d column displacements of ONE row
+//             displacement = 8 x 2d accumulators in registers (128 for d=8).  Per channel
+//             it needs 8 query values and 8+2d-1 key values (Toeplitz reuse): 8 LDS.128
+//             for 128 FFMA.
+//   warp    : 4 query rows x 4 row displacements x 2 column halves, so its lanes share
+//             4 query rows and 7 key rows (shared-memory broadcast).
+//   grid    : stream-K.  The (tile, channel-chunk) iteration space is cut into equal
+//             contiguous ranges, one per SM, so B=1 (19-20 tiles) fills 148 SMs and
+//             B=8 has no wave-quantisation tail.  A tile whose channels are split over
+//             several CTAs goes through fixed-order partial buffers (deterministic, no
+//             atomics); tiles owned by one CTA are written straight to `out`.
+//   output  : accumulators are transposed through shared memory into the final
+//             (B,H,W,2d+1,2d+1) layout, dead entries (row/column 2d, out-of-image
+//             displacements: SURVEY.md F4) written as exact zeros, and streamed out as
+//             long coalesced runs.  No memset of `out`.
 #include "common.cuh"
 
 namespace d2t {
 
-bool corr_tile_supported(int, int, int, int, int, int) { return false; }
-size_t corr_tile_fwd_ws_bytes(int, int, int, int, int) { return 0; }
-size_t corr_tile_bwd_ws_bytes(int, int, int, int, int) { return 0; }
-int corr_tile_fwd_launch(const float*, const float*, float*, int, int, int, int, int, void*, size_t, cudaStream_t) {
-    set_error("corr_tile_fwd: not built");
-    return D2T_ERR_BAD_ARG;
+constexpr int kCorrThreads = 256;
+
+template <int D>
+struct FwdCfg {
+    static constexpr int TD = 2 * D;              // live column / row displacements
+    static constexpr int K1 = 2 * D + 1;          // output map side
+    static constexpr int KK = K1 * K1;            // output map size
+    static constexpr int QROWS = 128 / TD;        // query rows per tile
+    static constexpr int QCOLS = 16;              // query cols per tile
+    static constexpr int KROWS = QROWS + TD - 1;  // key rows per tile
+    static constexpr int KCOLS = QCOLS + TD - 1;  // key cols per tile
+    static constexpr int KP = (D == 8) ? 36 : 28; // key row pitch (floats): >= 16+TD, = 4 mod 8
+    static constexpr int QP = 20;                 // query row pitch (floats): 16 used, = 4 mod 8
+    static constexpr int KPATCH = KROWS * KP + 8;  // key rows >= 16 are shifted by 8 floats (bank-group skew)
+    static constexpr int CH_FLOATS = QROWS * QP + KPATCH;  // staged floats per channel
+    static constexpr int KV = (8 + TD) / 4;       // LDS.128 per thread per channel for keys
+    static constexpr int KPASS = (KROWS + 7) / 8; // staging passes over key rows (8 rows x 32 lanes each)
+    static constexpr int QPASS = (QROWS * QCOLS + kCorrThreads - 1) / kCorrThreads;
+    static constexpr int TILE_FLOATS = QROWS * QCOLS * KK;     // one tile of output / one partial slot
+    static_assert(D == 4 || D == 8, "tuned kernel covers d_max 4 and 8");
+    static_assert(KP >= 16 + TD && KP % 4 == 0, "key pitch");
+};
+
+// shared-memory offset of key-patch row r (rows >= 16 skewed by two 16-byte chunks so that rows r and
+// r+16, which one quarter-warp can touch together, fall in different bank groups)
+template <int D>
+__device__ __forceinline__ int krow_off(int r) {
+    return r * FwdCfg<D>::KP + ((r >> 4) << 3);
 }
-int corr_tile_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int, void*,
-                         size_t, cudaStream_t) {
-    set_error("corr_tile_bwd: not built");
-    return D2T_ERR_BAD_ARG;
+
+struct CorrPlan {
+    int B, C, H, W;
+    int tilesX, tilesY, T;  // tiles per image in x / y, total tiles
+    int NI;                 // channel chunks per tile
+    int G;                  // CTAs
+    int ipc;                // (tile, chunk) iterations per CTA
+};
+
+template <int D, int CK>
+__global__ void __launch_bounds__(kCorrThreads, 1)
+corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm1, float* __restrict__ out,
+                     float* __restrict__ partial, CorrPlan p) {
+    using Cfg = FwdCfg<D>;
+    constexpr int TD = Cfg::TD, K1 = Cfg::K1, KK = Cfg::KK;
+    constexpr int STAGE_FLOATS = CK * Cfg::CH_FLOATS;
+    extern __shared__ __align__(16) float smem[];  // 2 operand stages, later aliased by the output tile
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    // Task = (query row qrow, row displacement ti); its key row inside the staged patch is
+    // kr = qrow + ti.  Measured on B200 (profiles/r1_microbench.txt): an LDS.128 costs 4 cycles when
+    // the 8 lanes of a quarter-warp read 8 different 16-byte chunks, 2.5 when they read <= 4, and
+    // doubles on a bank-group clash.  So a quarter-warp holds 4 query rows x 2 adjacent anti-diagonal
+    // classes (qrow + ti == dcls mod 16) of one column half l: its lanes read 4 query chunks and
+    // 2-4 key chunks, all in different bank groups.
+    const int mlo = tid & 3;
+    const int dl = (tid >> 2) & 1;
+    const int mhi = (tid >> 3) & 1;
+    const int l = (tid >> 4) & 1;
+    const int dcls = 2 * warp + dl;  // 0..15
+    const int m = mlo + 4 * mhi;     // 0..7
+    const int qrow = (Cfg::QROWS == 8) ? m : ((dcls - m) & 15);
+    const int ti = (Cfg::QROWS == 8) ? ((dcls - m) & 15) : m;
+    const int kr = qrow + ti;  // = dcls or dcls + 16
+
+    const int H = p.H, W = p.W, C = p.C;
+    const size_t plane = (size_t)H * W;
+
+    long long it = (long long)blockIdx.x * p.ipc;
+    const long long itEnd = min((long long)p.T * p.NI, it + p.ipc);
+
+    while (it < itEnd) {
+        const int tile = (int)(it / p.NI);
+        const int chunkBeg = (int)(it - (long long)tile * p.NI);
+        const int chunkEnd = (int)min((long long)p.NI, chunkBeg + (itEnd - it));
+        it += chunkEnd - chunkBeg;
+
+        const int b = tile / (p.tilesX * p.tilesY);
+        const int trem = tile - b * p.tilesX * p.tilesY;
+        const int i0 = (trem / p.tilesX) * Cfg::QROWS;
+        const int j0 = (trem % p.tilesX) * Cfg::QCOLS;
+
+        const float* q_img = fm0 + (size_t)b * C * plane;
+        const float* k_img = fm1 + (size_t)b * C * plane;
+
+        // ---- staging map: this thread's key / query elements inside one channel plane -------
+        int koff[Cfg::KPASS];  // global offset inside the plane, or -1
+        int ksm[Cfg::KPASS];   // shared offset inside the channel block, or -1 (row beyond patch)
+#pragma unroll
+        for (int ps = 0; ps < Cfg::KPASS; ++ps) {
+            const int r = ps * 8 + warp, x = lane;
+            const int gi = i0 - D + r, gj = j0 - D + x;
+            const bool inPatch = r < Cfg::KROWS && x < Cfg::KP;
+            const bool inImg = inPatch && x < Cfg::KCOLS && gi >= 0 && gi < H && gj >= 0 && gj < W;
+            ksm[ps] = inPatch ? Cfg::QROWS * Cfg::QP + krow_off<D>(r) + x : -1;
+            koff[ps] = inImg ? gi * W + gj : -1;
+        }
+        int qoff[Cfg::QPASS], qsm[Cfg::QPASS];
+#pragma unroll
+        for (int ps = 0; ps < Cfg::QPASS; ++ps) {
+            const int e = ps * kCorrThreads + tid;
+            const int r = e / Cfg::QCOLS, x = e % Cfg::QCOLS;
+            const bool inTile = e < Cfg::QROWS * Cfg::QCOLS;
+            const bool inImg = inTile && i0 + r < H && j0 + x < W;
+            qsm[ps] = inTile ? r * Cfg::QP + x : -1;
+            qoff[ps] = inImg ? (i0 + r) * W + (j0 + x) : -1;
+        }
+
+        const bool taskLive = (i0 + qrow < H) && (i0 - D + kr >= 0) && (i0 - D + kr < H);
+        const bool warpLive = __any_sync(0xffffffffu, taskLive);
+
+        float acc[8][TD];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int t = 0; t < TD; ++t) acc[a][t] = 0.f;
+
+        float kreg[CK][Cfg::KPASS], qreg[CK][Cfg::QPASS];
+
+        auto load_chunk = [&](int chunk) {
+            const int c0 = chunk * CK;
+#pragma unroll
+            for (int cc = 0; cc < CK; ++cc) {
+                const bool cvalid = c0 + cc < C;
+                const float* kp = k_img + (size_t)(c0 + cc) * plane;
+                const float* qp = q_img + (size_t)(c0 + cc) * plane;
+#pragma unroll
+                for (int ps = 0; ps < Cfg::KPASS; ++ps)
+                    kreg[cc][ps] = (cvalid && koff[ps] >= 0) ? __ldg(kp + koff[ps]) : 0.f;
+#pragma unroll
+                for (int ps = 0; ps < Cfg::QPASS; ++ps)
+                    qreg[cc][ps] = (cvalid && qoff[ps] >= 0) ? __ldg(qp + qoff[ps]) : 0.f;
+            }
+        };
+        auto store_chunk = [&](float* stage) {
+#pragma unroll
+            for (int cc = 0; cc < CK; ++cc) {
+                float* s = stage + cc * Cfg::CH_FLOATS;
+#pragma unroll
+                for (int ps = 0; ps < Cfg::KPASS; ++ps)
+                    if (ksm[ps] >= 0) s[ksm[ps]] = kreg[cc][ps];
+#pragma unroll
+                for (int ps = 0; ps < Cfg::QPASS; ++ps)
+                    if (qsm[ps] >= 0) s[qsm[ps]] = qreg[cc][ps];
+            }
+        };
+
+        __syncthreads();  // previous segment's epilogue has finished reading the aliased tile
+        load_chunk(chunkBeg);
+        store_chunk(smem);
+        __syncthreads();
+
+        for (int chunk = chunkBeg; chunk < chunkEnd; ++chunk) {
+            const float* stage = smem + ((chunk - chunkBeg) & 1) * STAGE_FLOATS;
+            const bool more = chunk + 1 < chunkEnd;
+            if (more) load_chunk(chunk + 1);
+            if (warpLive) {
+#pragma unroll
+                for (int cc = 0; cc < CK; ++cc) {
+                    const float* s = stage + cc * Cfg::CH_FLOATS;
+                    const float4* sq = reinterpret_cast<const float4*>(s + qrow * Cfg::QP + 8 * l);
+                    const float4* sk = reinterpret_cast<const float4*>(s + Cfg::QROWS * Cfg::QP + krow_off<D>(kr) + 8 * l);
+                    float q[8], kv[4 * Cfg::KV];
+                    *reinterpret_cast<float4*>(q) = sq[0];
+                    *reinterpret_cast<float4*>(q + 4) = sq[1];
+#pragma unroll
+                    for (int v = 0; v < Cfg::KV; ++v) *reinterpret_cast<float4*>(kv + 4 * v) = sk[v];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int t = 0; t < TD; ++t) acc[a][t] = fmaf(q[a], kv[a + t], acc[a][t]);
+                }
+            }
+            if (more) store_chunk(smem + ((chunk + 1 - chunkBeg) & 1) * STAGE_FLOATS);
+            __syncthreads();
+        }
+
+        // ---- epilogue: registers -> shared tile in final layout -> global ----------------------
+        float* tileS = smem;  // [QROWS][QCOLS][K1][K1]
+        {
+            float* base = tileS + ((qrow * Cfg::QCOLS + 8 * l) * K1 + ti) * K1;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int gj = j0 + 8 * l + a;
+#pragma unroll
+                for (int t = 0; t < TD; ++t) {
+                    const int dj = gj - D + t;
+                    const bool live = taskLive && dj >= 0 && dj < W;
+                    base[a * KK + t] = live ? acc[a][t] : 0.f;
+                }
+            }
+            // dead row 2d and dead column 2d of every map in the tile
+            for (int e = tid; e < Cfg::QROWS * Cfg::QCOLS * (2 * K1 - 1); e += kCorrThreads) {
+                const int pos = e / (2 * K1 - 1), z = e % (2 * K1 - 1);
+                const int off = z < K1 ? (K1 - 1) * K1 + z : (z - K1) * K1 + (K1 - 1);
+                tileS[pos * KK + off] = 0.f;
+            }
+        }
+        __syncthreads();
+
+        const bool whole = (chunkBeg == 0 && chunkEnd == p.NI);
+        if (whole) {
+            const int ncols = min(Cfg::QCOLS, W - j0);
+            const int run = ncols * KK;
+#pragma unroll 1
+            for (int r = 0; r < Cfg::QROWS; ++r) {
+                if (i0 + r >= H) break;
+                float* dst = out + (((size_t)b * H + (i0 + r)) * W + j0) * KK;
+                const float* src = tileS + r * Cfg::QCOLS * KK;
+                for (int e = tid; e < run; e += kCorrThreads) dst[e] = src[e];
+            }
+        } else {
+            // fixed slot per (cta, tile): slot = cta + tile (unique because tile is monotone in cta)
+            float4* dst = reinterpret_cast<float4*>(partial + (size_t)(blockIdx.x + tile) * Cfg::TILE_FLOATS);
+            const float4* src = reinterpret_cast<const float4*>(tileS);
+            for (int e = tid; e < Cfg::TILE_FLOATS / 4; e += kCorrThreads) dst[e] = src[e];
+        }
+    }
+}
+
+// Sum the partial slots of every tile that was split over several CTAs (ascending CTA = ascending
+// channel order: deterministic) and write the result in the final layout.
+template <int D>
+__global__ void __launch_bounds__(256)
+corr_fwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, CorrPlan p) {
+    using Cfg = FwdCfg<D>;
+    constexpr int KK = Cfg::KK;
+    const int tile = blockIdx.x;
+    const long long itBeg = (long long)tile * p.NI, itLast = itBeg + p.NI - 1;
+    const int gFirst = (int)(itBeg / p.ipc), gLast = (int)(itLast / p.ipc);
+    if (gFirst == gLast) return;  // written directly by its only CTA
+    const int b = tile / (p.tilesX * p.tilesY);
+    const int trem = tile - b * p.tilesX * p.tilesY;
+    const int i0 = (trem / p.tilesX) * Cfg::QROWS;
+    const int j0 = (trem % p.tilesX) * Cfg::QCOLS;
+    const int ncols = min(Cfg::QCOLS, p.W - j0);
+    const int run = ncols * KK;
+    for (int r = blockIdx.y; r < Cfg::QROWS; r += gridDim.y) {
+        if (i0 + r >= p.H) break;
+        float* dst = out + (((size_t)b * p.H + (i0 + r)) * p.W + j0) * KK;
+        const float* src = partial + (size_t)r * Cfg::QCOLS * KK;
+        for (int e = threadIdx.x; e < run; e += blockDim.x) {
+            float s = 0.f;
+            for (int g = gFirst; g <= gLast; ++g) s += src[(size_t)(g + tile) * Cfg::TILE_FLOATS + e];
+            dst[e] = s;
+        }
+    }
+}
+
+
+// =================================================================================================
+// Backward.  Both gradients are one "banded apply":
+//     OUT[c, pos] = sum_{si,sj in [0,2d)} G[pos, si, sj] * X[c, pos + (si,sj) - OFF]
+//   grad_FM0 (MODE 0): X = FM1, OFF = d,   G[pos,si,sj] = gradOut[pos, si, sj]
+//   grad_FM1 (MODE 1): X = FM0, OFF = d-1, G[pos,si,sj] = gradOut[pos + (si,sj) - (d-1), 2d-1-si, 2d-1-sj]
+//                      (the queries whose window contains key `pos`; asymmetric because of F4)
+// so grad_FM1 is a GATHER too: no atomicAdd (the reference needs C*P of them,
+// pointwise_correlation_cuda.cu:169), bitwise reproducible.
+//
+// Same tile, same key-patch staging and same thread <-> (row, column half, row displacement) map as
+// the forward kernel, with the roles turned round: the thread's 8 x 2d block of G is loaded ONCE per
+// tile and stays in registers for the whole channel loop; per channel it reads its 8+2d-1 patch
+// values, forms 8 partial sums over the column displacements, and the 2d row-displacement partials
+// of every output are summed in a fixed order through shared memory.  Every channel chunk produces
+// final values, so the (tile, chunk) space is stream-K partitioned with no partial buffers at all.
+template <int D, int CK, int MODE>
+__global__ void __launch_bounds__(kCorrThreads, 1)
+corr_bwd_tile_kernel(const float* __restrict__ go, const float* __restrict__ xsrc, float* __restrict__ gout,
+                     CorrPlan p) {
+    using Cfg = FwdCfg<D>;
+    constexpr int TD = Cfg::TD, K1 = Cfg::K1, KK = Cfg::KK;
+    constexpr int OFF = (MODE == 0) ? D : D - 1;
+    constexpr int XCH = Cfg::KPATCH;
+    constexpr int STAGE_FLOATS = CK * XCH;
+    constexpr int RP = CK * 8 + 4;  // reduce-block pitch in floats; RP/4 odd => conflict-free 16-byte rows
+    static_assert((RP / 4) % 2 == 1, "reduce pitch");
+    extern __shared__ __align__(16) float smem[];
+    float* red = smem + 2 * STAGE_FLOATS;  // [256 threads][RP]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int mlo = tid & 3, dl = (tid >> 2) & 1, mhi = (tid >> 3) & 1, l = (tid >> 4) & 1;
+    const int dcls = 2 * warp + dl;
+    const int m = mlo + 4 * mhi;
+    const int qrow = (Cfg::QROWS == 8) ? m : ((dcls - m) & 15);
+    const int ti = (Cfg::QROWS == 8) ? ((dcls - m) & 15) : m;
+    const int kr = qrow + ti;
+
+    // reducer role: this thread sums the 2d partials of RV*4 outputs
+    constexpr int RV = (Cfg::QROWS == 8) ? 1 : 2;  // float4 per reducer thread
+    const int r_ql = (Cfg::QROWS == 8) ? (tid >> 4) : (tid >> 3);
+    const int r_cc = (Cfg::QROWS == 8) ? ((tid >> 1) & 7) : (tid & 7);
+    const int r_h = (Cfg::QROWS == 8) ? (tid & 1) : 0;
+    const int r_qrow = r_ql >> 1, r_l = r_ql & 1;
+
+    const int H = p.H, W = p.W, C = p.C;
+    const size_t plane = (size_t)H * W;
+
+    long long it = (long long)blockIdx.x * p.ipc;
+    const long long itEnd = min((long long)p.T * p.NI, it + p.ipc);
+
+    while (it < itEnd) {
+        const int tile = (int)(it / p.NI);
+        const int chunkBeg = (int)(it - (long long)tile * p.NI);
+        const int chunkEnd = (int)min((long long)p.NI, chunkBeg + (itEnd - it));
+        it += chunkEnd - chunkBeg;
+
+        const int b = tile / (p.tilesX * p.tilesY);
+        const int trem = tile - b * p.tilesX * p.tilesY;
+        const int i0 = (trem / p.tilesX) * Cfg::QROWS;
+        const int j0 = (trem % p.tilesX) * Cfg::QCOLS;
+        const float* x_img = xsrc + (size_t)b * C * plane;
+
+        // ---- this thread's block of G, register-resident for the whole channel loop --------------
+        float g[8][TD];
+        const int pi = i0 + qrow;
+        const int xi = pi + ti - OFF;  // patch row in the image
+        const bool taskLive = pi < H && xi >= 0 && xi < H;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int pj = j0 + 8 * l + a;
+#pragma unroll
+            for (int t = 0; t < TD; ++t) {
+                const int xj = pj + t - OFF;
+                const bool live = taskLive && pj < W && xj >= 0 && xj < W;
+                size_t idx;
+                if (MODE == 0)
+                    idx = (((size_t)b * H + pi) * W + pj) * KK + ti * K1 + t;
+                else
+                    idx = (((size_t)b * H + xi) * W + xj) * KK + (TD - 1 - ti) * K1 + (TD - 1 - t);
+                g[a][t] = live ? __ldg(go + idx) : 0.f;
+            }
+        }
+        const bool warpLive = __any_sync(0xffffffffu, taskLive);
+
+        // ---- staging map for the patch ---------------------------------------------------------------
+        int koff[Cfg::KPASS], ksm[Cfg::KPASS];
+#pragma unroll
+        for (int ps = 0; ps < Cfg::KPASS; ++ps) {
+            const int r = ps * 8 + warp, x = lane;
+            const int gi = i0 - OFF + r, gj = j0 - OFF + x;
+            const bool inPatch = r < Cfg::KROWS && x < Cfg::KP;
+            const bool inImg = inPatch && x < Cfg::KCOLS && gi >= 0 && gi < H && gj >= 0 && gj < W;
+            ksm[ps] = inPatch ? krow_off<D>(r) + x : -1;
+            koff[ps] = inImg ? gi * W + gj : -1;
+        }
+        float kreg[CK][Cfg::KPASS];
+        auto load_chunk = [&](int chunk) {
+            const int c0 = chunk * CK;
+#pragma unroll
+            for (int cc = 0; cc < CK; ++cc) {
+                const bool cvalid = c0 + cc < C;
+                const float* kp = x_img + (size_t)(c0 + cc) * plane;
+#pragma unroll
+                for (int ps = 0; ps < Cfg::KPASS; ++ps)
+                    kreg[cc][ps] = (cvalid && koff[ps] >= 0) ? __ldg(kp + koff[ps]) : 0.f;
+            }
+        };
+        auto store_chunk = [&](float* stage) {
+#pragma unroll
+            for (int cc = 0; cc < CK; ++cc) {
+#pragma unroll
+                for (int ps = 0; ps < Cfg::KPASS; ++ps)
+                    if (ksm[ps] >= 0) stage[cc * XCH + ksm[ps]] = kreg[cc][ps];
+            }
+        };
+
+        // reducer's output coordinates and the thread ids holding its partials
+        const int o_row = i0 + r_qrow;
+        const int o_col = j0 + 8 * r_l + 4 * r_h;
+
+        __syncthreads();
+        load_chunk(chunkBeg);
+        store_chunk(smem);
+        __syncthreads();
+
+        for (int chunk = chunkBeg; chunk < chunkEnd; ++chunk) {
+            const float* stage = smem + ((chunk - chunkBeg) & 1) * STAGE_FLOATS;
+            const bool more = chunk + 1 < chunkEnd;
+            if (more) load_chunk(chunk + 1);
+            {
+                float4* myred = reinterpret_cast<float4*>(red + tid * RP);
+#pragma unroll
+                for (int cc = 0; cc < CK; ++cc) {
+                    float part[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) part[a] = 0.f;
+                    if (warpLive) {
+                        const float4* sk = reinterpret_cast<const float4*>(stage + cc * XCH + krow_off<D>(kr) + 8 * l);
+                        float kv[4 * Cfg::KV];
+#pragma unroll
+                        for (int v = 0; v < Cfg::KV; ++v) *reinterpret_cast<float4*>(kv + 4 * v) = sk[v];
+#pragma unroll
+                        for (int t = 0; t < TD; ++t)
+#pragma unroll
+                            for (int a = 0; a < 8; ++a) part[a] = fmaf(g[a][t], kv[a + t], part[a]);
+                    }
+                    myred[2 * cc] = make_float4(part[0], part[1], part[2], part[3]);
+                    myred[2 * cc + 1] = make_float4(part[4], part[5], part[6], part[7]);
+                }
+            }
+            __syncthreads();  // partials complete
+            {
+                const int c = chunk * CK + r_cc;
+#pragma unroll
+                for (int hv = 0; hv < RV; ++hv) {
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int t = 0; t < TD; ++t) {
+                        // thread id holding (r_qrow, r_l, row displacement t)
+                        const int dc = (r_qrow + t) & 15;
+                        const int mm = (Cfg::QROWS == 8) ? r_qrow : t;
+                        const int src = (mm & 3) | ((dc & 1) << 2) | ((mm >> 2) << 3) | (r_l << 4) | ((dc >> 1) << 5);
+                        const float4 v = *reinterpret_cast<const float4*>(red + src * RP + r_cc * 8 + 4 * (r_h + hv));
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    }
+                    if (c < C && o_row < H) {
+                        float* dst = gout + ((size_t)b * C + c) * plane + (size_t)o_row * W + o_col + 4 * hv;
+                        const int col = o_col + 4 * hv;
+                        if (col + 0 < W) dst[0] = s.x;
+                        if (col + 1 < W) dst[1] = s.y;
+                        if (col + 2 < W) dst[2] = s.z;
+                        if (col + 3 < W) dst[3] = s.w;
+                    }
+                }
+            }
+            if (more) store_chunk(smem + ((chunk + 1 - chunkBeg) & 1) * STAGE_FLOATS);
+            __syncthreads();  // next stage visible; reduce buffer free again
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+constexpr int kFwdCK = 8;
+
+template <int D>
+static int make_plan(int B, int C, int H, int W, int CK, CorrPlan* p) {
+    using Cfg = FwdCfg<D>;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    p->B = B; p->C = C; p->H = H; p->W = W;
+    p->tilesX = ceil_div(W, Cfg::QCOLS);
+    p->tilesY = ceil_div(H, Cfg::QROWS);
+    p->T = B * p->tilesX * p->tilesY;
+    p->NI = ceil_div(C, CK);
+    const long long total = (long long)p->T * p->NI;
+    long long G = di.sm_count;
+    if (G > total) G = total;
+    p->G = (int)G;
+    p->ipc = (int)((total + G - 1) / G);
+    p->G = (int)((total + p->ipc - 1) / p->ipc);
+    return 0;
+}
+
+bool corr_tile_supported(int B, int C, int H, int W, int d, int stride) {
+    if (stride != 1 || (d != 4 && d != 8)) return false;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return false;
+    if ((long long)B * C * H * W >= (1ll << 31)) return false;
+    return true;
+}
+
+template <int D>
+static size_t fwd_ws_bytes(int B, int C, int H, int W) {
+    CorrPlan p;
+    if (make_plan<D>(B, C, H, W, kFwdCK, &p)) return 0;
+    return (size_t)(p.G + p.T) * FwdCfg<D>::TILE_FLOATS * sizeof(float);
+}
+
+size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d) {
+    return d == 8 ? fwd_ws_bytes<8>(B, C, H, W) : fwd_ws_bytes<4>(B, C, H, W);
+}
+bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride) {
+    return corr_tile_supported(B, C, H, W, d, stride);
+}
+size_t corr_tile_bwd_ws_bytes(int, int, int, int, int) { return 0; }
+
+template <int D>
+static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+    using Cfg = FwdCfg<D>;
+    constexpr int CK = kFwdCK;
+    CorrPlan p;
+    int rc = make_plan<D>(B, C, H, W, CK, &p);
+    if (rc) return rc;
+    const size_t need = (size_t)(p.G + p.T) * Cfg::TILE_FLOATS * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("corr_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
+        return D2T_ERR_WORKSPACE;
+    }
+    const size_t opBytes = (size_t)2 * CK * Cfg::CH_FLOATS * sizeof(float);
+    const size_t tileBytes = (size_t)Cfg::TILE_FLOATS * sizeof(float);
+    const size_t smem = opBytes > tileBytes ? opBytes : tileBytes;
+    auto kern = corr_fwd_tile_kernel<D, CK>;
+    D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<p.G, kCorrThreads, smem, st>>>(fm0, fm1, out, static_cast<float*>(ws), p);
+    D2T_CUDA_TRY(cudaGetLastError());
+    if (p.ipc % p.NI != 0) {  // some tile is split over CTAs
+        dim3 grid(p.T, Cfg::QROWS);
+        corr_fwd_finalize_kernel<D><<<grid, 256, 0, st>>>(static_cast<const float*>(ws), out, p);
+        D2T_CUDA_TRY(cudaGetLastError());
+    }
+    return D2T_OK;
+}
+
+int corr_tile_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+    return d == 8 ? fwd_launch<8>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st)
+                  : fwd_launch<4>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);
+}
+
+template <int D>
+static int bwd_launch(const float* go, const float* fm0, const float* fm1, float* g0, float* g1, int B, int C, int H,
+                      int W, cudaStream_t st) {
+    using Cfg = FwdCfg<D>;
+    constexpr int CK = 8;
+    CorrPlan p;
+    int rc = make_plan<D>(B, C, H, W, CK, &p);
+    if (rc) return rc;
+    const size_t smem = ((size_t)2 * CK * Cfg::KPATCH + (size_t)kCorrThreads * (CK * 8 + 4)) * sizeof(float);
+    auto k0 = corr_bwd_tile_kernel<D, CK, 0>;
+    auto k1 = corr_bwd_tile_kernel<D, CK, 1>;
+    D2T_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k0<<<p.G, kCorrThreads, smem, st>>>(go, fm1, g0, p);
+    D2T_CUDA_TRY(cudaGetLastError());
+    k1<<<p.G, kCorrThreads, smem, st>>>(go, fm0, g1, p);
+    D2T_CUDA_TRY(cudaGetLastError());
+    return D2T_OK;
+}
+
+int corr_tile_bwd_launch(const float* go, const float* fm0, const float* fm1, float* g0, float* g1, int B, int C,
+                         int H, int W, int d, void*, size_t, cudaStream_t st) {
+    return d == 8 ? bwd_launch<8>(go, fm0, fm1, g0, g1, B, C, H, W, st)
+                  : bwd_launch<4>(go, fm0, fm1, g0, g1, B, C, H, W, st);
 }
 
 }  // namespace d2t

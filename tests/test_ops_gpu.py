@@ -191,9 +191,13 @@ def test_roipool_full_size_track_head(cuda):
     rois = dev(rois_np, cuda)
     out = rp_mod.roipool_forward(fm, rois, k)
     gin = rp_mod.roipool_backward(go, rois, H, W)
-    lhs = (out.double() * go.double()).sum().item()
+    # RoIs crossing the bottom/right border have EMPTY bins -> 0/0 = NaN in the reference (F7); those
+    # bins receive no gradient, so they drop out of the adjoint identity.
+    empty = torch.isnan(out)
+    assert 0 < int(empty.sum()) < out.numel() // 4
+    lhs = (torch.where(empty, torch.zeros_like(out), out).double() * go.double()).sum().item()
     rhs = (fm.double() * gin.double()).sum().item()
-    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
     assert torch.equal(gin, rp_mod.roipool_backward(go, rois, H, W))
     sel = [0, 5, 777, 1890]
     want = oracle.roipool_fwd(fm[sel].cpu().numpy(), rois_np, k)

@@ -68,6 +68,12 @@ __device__ __forceinline__ int chunk_of(int pattern, int lane) {
         case 7: return (lane >> 4) * 21 + (lane & 7) * 2;
         case 8: return (lane >> 2);                            // 8 distinct, each read by 4 adjacent lanes
         case 9: return (lane & 3) * 21 + (lane >> 2) * 2;      // bwd pattern: 4 channel groups x 8 column blocks, pitch 84
+        case 10: return lane >> 1;                             // 4 distinct per quarter-warp (16 total), contiguous
+        case 11: return (lane & 7) >> 1;                       // the same 4 chunks in every quarter-warp
+        case 12: return ((lane >> 2) & 1) * 8 + (lane >> 3);   // 2 distinct per quarter, SAME bank group (2-way)
+        case 13: return ((lane >> 1) & 3) * 9 + (lane >> 3) * 36;  // 4 distinct per quarter, rows 9 chunks apart
+        case 14: return (lane & 7) * 9 + (lane >> 3) * 2;      // 8 distinct per quarter, pitch-36 rows, conflict-free
+        case 15: return (lane & 7) * 65 + (lane >> 3) * 4;     // 8 distinct per quarter, pitch-260 blocks
         default: return lane;
     }
 }
@@ -129,7 +135,7 @@ int main() {
     // LDS.128 patterns: 1 CTA per SM, 8 warps
     long long* cyc;
     CK(cudaMalloc(&cyc, sizeof(long long) * nsm));
-    for (int pattern = 0; pattern < 10; ++pattern) {
+    for (int pattern = 0; pattern < 16; ++pattern) {
         const int iters = 4000;
         lds128_kernel<<<nsm, 256>>>(out, iters, pattern, cyc);
         CK(cudaDeviceSynchronize());
