@@ -58,6 +58,19 @@ __device__ __forceinline__ int krow_off(int r) {
     return r * FwdCfg<D>::KP + ((r >> 4) << 3);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 4-byte asynchronous global->shared copy, zero-filled when !valid (src must still be a mapped address)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kStages = 3;  // operand ring depth (cp.async groups in flight: kStages - 1)
+
 struct CorrPlan {
     int B, C, H, W;
     int tilesX, tilesY, T;  // tiles per image in x / y, total tiles
@@ -145,45 +158,42 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
 #pragma unroll
             for (int t = 0; t < TD; ++t) acc[a][t] = 0.f;
 
-        float kreg[CK][Cfg::KPASS], qreg[CK][Cfg::QPASS];
-
-        auto load_chunk = [&](int chunk) {
-            const int c0 = chunk * CK;
+        // asynchronous staging of one channel chunk (cp.async: no staging registers, no scoreboard
+        // coupling with the LDS of the compute loop)
+        const uint32_t smemBase = smem_u32(smem);
+        auto issue_chunk = [&](int chunk) {
+            if (chunk < chunkEnd) {
+                const int c0 = chunk * CK;
+                const uint32_t stage = smemBase + (uint32_t)((chunk - chunkBeg) % kStages) * STAGE_FLOATS * 4u;
 #pragma unroll
-            for (int cc = 0; cc < CK; ++cc) {
-                const bool cvalid = c0 + cc < C;
-                const float* kp = k_img + (size_t)(c0 + cc) * plane;
-                const float* qp = q_img + (size_t)(c0 + cc) * plane;
+                for (int cc = 0; cc < CK; ++cc) {
+                    const bool cvalid = c0 + cc < C;
+                    const float* kp = k_img + (size_t)(cvalid ? c0 + cc : 0) * plane;
+                    const float* qp = q_img + (size_t)(cvalid ? c0 + cc : 0) * plane;
 #pragma unroll
-                for (int ps = 0; ps < Cfg::KPASS; ++ps)
-                    kreg[cc][ps] = (cvalid && koff[ps] >= 0) ? __ldg(kp + koff[ps]) : 0.f;
+                    for (int ps = 0; ps < Cfg::KPASS; ++ps)
+                        if (ksm[ps] >= 0)
+                            cp_async4(stage + (cc * Cfg::CH_FLOATS + ksm[ps]) * 4u, kp + (koff[ps] >= 0 ? koff[ps] : 0),
+                                      cvalid && koff[ps] >= 0);
 #pragma unroll
-                for (int ps = 0; ps < Cfg::QPASS; ++ps)
-                    qreg[cc][ps] = (cvalid && qoff[ps] >= 0) ? __ldg(qp + qoff[ps]) : 0.f;
+                    for (int ps = 0; ps < Cfg::QPASS; ++ps)
+                        if (qsm[ps] >= 0)
+                            cp_async4(stage + (cc * Cfg::CH_FLOATS + qsm[ps]) * 4u, qp + (qoff[ps] >= 0 ? qoff[ps] : 0),
+                                      cvalid && qoff[ps] >= 0);
+                }
             }
-        };
-        auto store_chunk = [&](float* stage) {
-#pragma unroll
-            for (int cc = 0; cc < CK; ++cc) {
-                float* s = stage + cc * Cfg::CH_FLOATS;
-#pragma unroll
-                for (int ps = 0; ps < Cfg::KPASS; ++ps)
-                    if (ksm[ps] >= 0) s[ksm[ps]] = kreg[cc][ps];
-#pragma unroll
-                for (int ps = 0; ps < Cfg::QPASS; ++ps)
-                    if (qsm[ps] >= 0) s[qsm[ps]] = qreg[cc][ps];
-            }
+            cp_async_commit();  // always commit: keeps the group count in step with the chunk index
         };
 
         __syncthreads();  // previous segment's epilogue has finished reading the aliased tile
-        load_chunk(chunkBeg);
-        store_chunk(smem);
-        __syncthreads();
+#pragma unroll
+        for (int s0 = 0; s0 < kStages - 1; ++s0) issue_chunk(chunkBeg + s0);
 
         for (int chunk = chunkBeg; chunk < chunkEnd; ++chunk) {
-            const float* stage = smem + ((chunk - chunkBeg) & 1) * STAGE_FLOATS;
-            const bool more = chunk + 1 < chunkEnd;
-            if (more) load_chunk(chunk + 1);
+            cp_async_wait<kStages - 2>();  // this thread's copies of `chunk` have landed
+            __syncthreads();               // ... everyone's have; and compute(chunk-1) is finished
+            issue_chunk(chunk + kStages - 1);  // refills the stage compute(chunk-1) just released
+            const float* stage = smem + ((chunk - chunkBeg) % kStages) * STAGE_FLOATS;
             if (warpLive) {
 #pragma unroll
                 for (int cc = 0; cc < CK; ++cc) {
@@ -201,9 +211,9 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                         for (int t = 0; t < TD; ++t) acc[a][t] = fmaf(q[a], kv[a + t], acc[a][t]);
                 }
             }
-            if (more) store_chunk(smem + ((chunk + 1 - chunkBeg) & 1) * STAGE_FLOATS);
-            __syncthreads();
         }
+        cp_async_wait<0>();
+        __syncthreads();  // all warps are done with the operand ring before it is reused as the output tile
 
         // ---- epilogue: registers -> shared tile in final layout -> global ----------------------
         float* tileS = smem;  // [QROWS][QCOLS][K1][K1]
@@ -305,7 +315,8 @@ corr_bwd_tile_kernel(const float* __restrict__ go, const float* __restrict__ xsr
     constexpr int RP = CK * 8 + 4;  // reduce-block pitch in floats; RP/4 odd => conflict-free 16-byte rows
     static_assert((RP / 4) % 2 == 1, "reduce pitch");
     extern __shared__ __align__(16) float smem[];
-    float* red = smem + 2 * STAGE_FLOATS;  // [256 threads][RP]
+    float* red = smem + kStages * STAGE_FLOATS;  // 2 x [256 threads][RP]: partials of chunk n / n+1
+    constexpr int RED_FLOATS = kCorrThreads * RP;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -374,89 +385,87 @@ corr_bwd_tile_kernel(const float* __restrict__ go, const float* __restrict__ xsr
             ksm[ps] = inPatch ? krow_off<D>(r) + x : -1;
             koff[ps] = inImg ? gi * W + gj : -1;
         }
-        float kreg[CK][Cfg::KPASS];
-        auto load_chunk = [&](int chunk) {
-            const int c0 = chunk * CK;
-#pragma unroll
-            for (int cc = 0; cc < CK; ++cc) {
-                const bool cvalid = c0 + cc < C;
-                const float* kp = x_img + (size_t)(c0 + cc) * plane;
-#pragma unroll
-                for (int ps = 0; ps < Cfg::KPASS; ++ps)
-                    kreg[cc][ps] = (cvalid && koff[ps] >= 0) ? __ldg(kp + koff[ps]) : 0.f;
-            }
-        };
-        auto store_chunk = [&](float* stage) {
-#pragma unroll
-            for (int cc = 0; cc < CK; ++cc) {
-#pragma unroll
-                for (int ps = 0; ps < Cfg::KPASS; ++ps)
-                    if (ksm[ps] >= 0) stage[cc * XCH + ksm[ps]] = kreg[cc][ps];
-            }
-        };
-
-        // reducer's output coordinates and the thread ids holding its partials
-        const int o_row = i0 + r_qrow;
-        const int o_col = j0 + 8 * r_l + 4 * r_h;
-
-        __syncthreads();
-        load_chunk(chunkBeg);
-        store_chunk(smem);
-        __syncthreads();
-
-        for (int chunk = chunkBeg; chunk < chunkEnd; ++chunk) {
-            const float* stage = smem + ((chunk - chunkBeg) & 1) * STAGE_FLOATS;
-            const bool more = chunk + 1 < chunkEnd;
-            if (more) load_chunk(chunk + 1);
-            {
-                float4* myred = reinterpret_cast<float4*>(red + tid * RP);
+        const uint32_t smemBase = smem_u32(smem);
+        auto issue_chunk = [&](int chunk) {
+            if (chunk < chunkEnd) {
+                const int c0 = chunk * CK;
+                const uint32_t stage = smemBase + (uint32_t)((chunk - chunkBeg) % kStages) * STAGE_FLOATS * 4u;
 #pragma unroll
                 for (int cc = 0; cc < CK; ++cc) {
-                    float part[8];
+                    const bool cvalid = c0 + cc < C;
+                    const float* kp = x_img + (size_t)(cvalid ? c0 + cc : 0) * plane;
 #pragma unroll
-                    for (int a = 0; a < 8; ++a) part[a] = 0.f;
-                    if (warpLive) {
-                        const float4* sk = reinterpret_cast<const float4*>(stage + cc * XCH + krow_off<D>(kr) + 8 * l);
-                        float kv[4 * Cfg::KV];
-#pragma unroll
-                        for (int v = 0; v < Cfg::KV; ++v) *reinterpret_cast<float4*>(kv + 4 * v) = sk[v];
-#pragma unroll
-                        for (int t = 0; t < TD; ++t)
-#pragma unroll
-                            for (int a = 0; a < 8; ++a) part[a] = fmaf(g[a][t], kv[a + t], part[a]);
-                    }
-                    myred[2 * cc] = make_float4(part[0], part[1], part[2], part[3]);
-                    myred[2 * cc + 1] = make_float4(part[4], part[5], part[6], part[7]);
+                    for (int ps = 0; ps < Cfg::KPASS; ++ps)
+                        if (ksm[ps] >= 0)
+                            cp_async4(stage + (cc * XCH + ksm[ps]) * 4u, kp + (koff[ps] >= 0 ? koff[ps] : 0),
+                                      cvalid && koff[ps] >= 0);
                 }
             }
-            __syncthreads();  // partials complete
-            {
-                const int c = chunk * CK + r_cc;
+            cp_async_commit();
+        };
+
+        // reducer: fixed-order sum over the 2d row displacements of chunk `chunk`, then store
+        const int o_row = i0 + r_qrow;
+        const int o_col = j0 + 8 * r_l + 4 * r_h;
+        auto reduce_chunk = [&](int chunk) {
+            const float* rbuf = red + ((chunk - chunkBeg) & 1) * RED_FLOATS;
+            const int c = chunk * CK + r_cc;
 #pragma unroll
-                for (int hv = 0; hv < RV; ++hv) {
-                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int hv = 0; hv < RV; ++hv) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int t = 0; t < TD; ++t) {
-                        // thread id holding (r_qrow, r_l, row displacement t)
-                        const int dc = (r_qrow + t) & 15;
-                        const int mm = (Cfg::QROWS == 8) ? r_qrow : t;
-                        const int src = (mm & 3) | ((dc & 1) << 2) | ((mm >> 2) << 3) | (r_l << 4) | ((dc >> 1) << 5);
-                        const float4 v = *reinterpret_cast<const float4*>(red + src * RP + r_cc * 8 + 4 * (r_h + hv));
-                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                    }
-                    if (c < C && o_row < H) {
-                        float* dst = gout + ((size_t)b * C + c) * plane + (size_t)o_row * W + o_col + 4 * hv;
-                        const int col = o_col + 4 * hv;
-                        if (col + 0 < W) dst[0] = s.x;
-                        if (col + 1 < W) dst[1] = s.y;
-                        if (col + 2 < W) dst[2] = s.z;
-                        if (col + 3 < W) dst[3] = s.w;
-                    }
+                for (int t = 0; t < TD; ++t) {
+                    // thread id holding (r_qrow, r_l, row displacement t)
+                    const int dc = (r_qrow + t) & 15;
+                    const int mm = (Cfg::QROWS == 8) ? r_qrow : t;
+                    const int src = (mm & 3) | ((dc & 1) << 2) | ((mm >> 2) << 3) | (r_l << 4) | ((dc >> 1) << 5);
+                    const float4 v = *reinterpret_cast<const float4*>(rbuf + src * RP + r_cc * 8 + 4 * (r_h + hv));
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+                if (c < C && o_row < H) {
+                    const int col = o_col + 4 * hv;
+                    float* dst = gout + ((size_t)b * C + c) * plane + (size_t)o_row * W + col;
+                    if (col + 0 < W) dst[0] = s.x;
+                    if (col + 1 < W) dst[1] = s.y;
+                    if (col + 2 < W) dst[2] = s.z;
+                    if (col + 3 < W) dst[3] = s.w;
                 }
             }
-            if (more) store_chunk(smem + ((chunk + 1 - chunkBeg) & 1) * STAGE_FLOATS);
-            __syncthreads();  // next stage visible; reduce buffer free again
+        };
+
+        __syncthreads();  // the previous segment's last reduce has finished reading `red`
+#pragma unroll
+        for (int s0 = 0; s0 < kStages - 1; ++s0) issue_chunk(chunkBeg + s0);
+
+        for (int chunk = chunkBeg; chunk < chunkEnd; ++chunk) {
+            cp_async_wait<kStages - 2>();
+            __syncthreads();  // patch of `chunk` visible; partials of chunk-1 complete; compute(chunk-1) done
+            issue_chunk(chunk + kStages - 1);
+            if (chunk > chunkBeg) reduce_chunk(chunk - 1);  // overlaps with the FMAs below (no barrier between)
+            const float* stage = smem + ((chunk - chunkBeg) % kStages) * STAGE_FLOATS;
+            float4* myred = reinterpret_cast<float4*>(red + ((chunk - chunkBeg) & 1) * RED_FLOATS + tid * RP);
+#pragma unroll
+            for (int cc = 0; cc < CK; ++cc) {
+                float part[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) part[a] = 0.f;
+                if (warpLive) {
+                    const float4* sk = reinterpret_cast<const float4*>(stage + cc * XCH + krow_off<D>(kr) + 8 * l);
+                    float kv[4 * Cfg::KV];
+#pragma unroll
+                    for (int v = 0; v < Cfg::KV; ++v) *reinterpret_cast<float4*>(kv + 4 * v) = sk[v];
+#pragma unroll
+                    for (int t = 0; t < TD; ++t)
+#pragma unroll
+                        for (int a = 0; a < 8; ++a) part[a] = fmaf(g[a][t], kv[a + t], part[a]);
+                }
+                myred[2 * cc] = make_float4(part[0], part[1], part[2], part[3]);
+                myred[2 * cc + 1] = make_float4(part[4], part[5], part[6], part[7]);
+            }
         }
+        cp_async_wait<0>();
+        __syncthreads();
+        reduce_chunk(chunkEnd - 1);
     }
 }
 
@@ -518,7 +527,7 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
         set_error("corr_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
         return D2T_ERR_WORKSPACE;
     }
-    const size_t opBytes = (size_t)2 * CK * Cfg::CH_FLOATS * sizeof(float);
+    const size_t opBytes = (size_t)kStages * CK * Cfg::CH_FLOATS * sizeof(float);
     const size_t tileBytes = (size_t)Cfg::TILE_FLOATS * sizeof(float);
     const size_t smem = opBytes > tileBytes ? opBytes : tileBytes;
     auto kern = corr_fwd_tile_kernel<D, CK>;
@@ -547,7 +556,7 @@ static int bwd_launch(const float* go, const float* fm0, const float* fm1, float
     CorrPlan p;
     int rc = make_plan<D>(B, C, H, W, CK, &p);
     if (rc) return rc;
-    const size_t smem = ((size_t)2 * CK * Cfg::KPATCH + (size_t)kCorrThreads * (CK * 8 + 4)) * sizeof(float);
+    const size_t smem = ((size_t)kStages * CK * Cfg::KPATCH + (size_t)2 * kCorrThreads * (CK * 8 + 4)) * sizeof(float);
     auto k0 = corr_bwd_tile_kernel<D, CK, 0>;
     auto k1 = corr_bwd_tile_kernel<D, CK, 1>;
     D2T_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
