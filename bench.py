@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- detect-to-track custom-op hot path on B200: frame-pairs/s, roofline, CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One STEP = the whole hot path, forward + backward, for 8 frame pairs on one GPU
+(BASELINE.json configs 2+3+4 together, SURVEY.md section 8d shapes):
+    PointwiseCorrelation d=8 on c3/c4/c5 (C=512/1024/2048, 38x63), batch of 8 pairs      3 fwd + 3 bwd calls
+    PSROIPool 7x7, cls (31 targets) + reg (4 targets), 300 RoIs, 2 frames per pair        32 fwd + 32 bwd calls
+    ROIPool 7x7 track head, 1891 channels, 300 RoIs per pair                              8 fwd +  8 bwd calls
+Pairs shard over GPUs with no data-path collective: weak scaling, value =
+pairs processed by all ranks / max-over-ranks device time.
+
+`value`   : inputs resident in HBM, ops called through the Python mirror of the reference API
+            (which calls the C ABI); CUDA events; working set per step (> 2 GB) exceeds L2.
+`e2e`     : the same work driven from HOST buffers through the public nn.Module API wired as the
+            reference wires it (CorrelationTracker + R-FCN heads): every step copies that step's
+            inputs from pinned host memory and reads the scalar loss back.
+`roofline`: the dominant kernel (correlation backward, c5) timed live with CUDA events.
+`cpu_baseline` / `--impl reference`: the reference has NO CPU implementation of these ops
+            (CUDA-only, README); the CPU arm is the C restatement in oracle/ (kind "port"), OpenMP
+            over all host cores, on a bounded sample (one frame pair per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import numpy as np  # noqa: E402
+
+PAIRS_PER_GPU = 8
+H, W, D, K, R = 38, 63, 8, 7, 300
+CORR_C = (("c3", 512), ("c4", 1024), ("c5", 2048))
+N_CLS, N_REG = 31, 4
+REG_CH = 512
+TRACK_C = 3 * (2 * D + 1) ** 2 + 2 * REG_CH  # 1891
+METRIC = "corr+PSROI fwd+bwd frame-pairs/s"
+WORKLOAD = ("D&T op hot path fwd+bwd per frame pair: PointwiseCorrelation d=8 on c3/c4/c5 (512/1024/2048 ch, 38x63, "
+            "from 608x1008 frames) + PSROIPool 7x7 cls(31)+reg(4) x 2 frames, 300 RoIs + ROIPool 7x7 track head "
+            "(1891 ch, 300 RoIs); 8 pairs per GPU")
+
+
+def live_pairs(n_h, n_w, d):
+    v = lambda n: sum(len(range(max(0, i - d), min(i + d, n))) for i in range(n))
+    return v(n_h) * v(n_w)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU port)
+def cpu_pair_inputs(seed=1234):
+    import cases
+    rng = np.random.default_rng(seed)
+    inp = {"corr": [], "rois": cases.rois_random(R, 1237), "track_rois": cases.rois_random(R, 1238)}
+    for _, C in CORR_C:
+        fm0 = (np.maximum(rng.standard_normal((1, C, H, W)), 0) / 16).astype(np.float32)
+        fm1 = (np.maximum(rng.standard_normal((1, C, H, W)), 0) / 16).astype(np.float32)
+        go = rng.standard_normal((1, H, W, 2 * D + 1, 2 * D + 1)).astype(np.float32)
+        inp["corr"].append((fm0, fm1, go))
+    inp["ps"] = []
+    for nT in (N_CLS, N_REG):
+        for _frame in range(2):
+            inp["ps"].append((nT, rng.standard_normal((nT * K * K, H, W)).astype(np.float32),
+                              rng.standard_normal((R, nT, K, K)).astype(np.float32)))
+    inp["track"] = (rng.standard_normal((TRACK_C, H, W)).astype(np.float32),
+                    rng.standard_normal((R, TRACK_C, K, K)).astype(np.float32))
+    return inp
+
+
+def cpu_pair_step(oracle, inp):
+    """the hot path for ONE frame pair on the host (oracle port, OpenMP)."""
+    for fm0, fm1, go in inp["corr"]:
+        oracle.corr_fwd(fm0, fm1, D, 1)
+        oracle.corr_bwd(go, fm0, fm1, D, 1)
+    for nT, fm, go in inp["ps"]:
+        oracle.psroipool_fwd(fm, inp["rois"], nT, K)
+        oracle.psroipool_bwd(go, inp["rois"], H, W)
+    fm, go = inp["track"]
+    oracle.roipool_fwd(fm, inp["track_rois"], K)
+    oracle.roipool_bwd(go, inp["track_rois"], H, W)
+
+
+def time_cpu(steps, warmup):
+    import oracle
+    oracle.set_threads(os.cpu_count() or 1)
+    inp = cpu_pair_inputs()
+    for _ in range(warmup):
+        cpu_pair_step(oracle, inp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pair_step(oracle, inp)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps, oracle.max_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # bounded: one frame pair per step (1/8 of the GPU step), a few seconds each
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    steps = min(steps, 30)
+    pps, sec, cores = time_cpu(steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": pps, "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": 1,
+                   "note": "the reference ops are CUDA-only; this arm is the CPU restatement oracle/d2t_oracle.c (OpenMP)"},
+        "cpu_baseline": {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                         "sample": "1 frame pair per step (all 3 correlations, 4 PSROIPool, 1 ROIPool; fwd+bwd)"},
+        "e2e": {"value": pps, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- multi-rank plumbing
+def global_max(values, device):
+    """max over ranks of per-rank device times (the job is as slow as its slowest shard)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), device=device, dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def job_throughput(world, steps, ms):
+    """whole-job frame pairs per second: every rank processes PAIRS_PER_GPU pairs per step (weak scaling)."""
+    return world * PAIRS_PER_GPU * steps / (ms * 1e-3)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def build_device_inputs(torch, dev, seed):
+    import cases
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B = PAIRS_PER_GPU
+    inp = {"corr": [], "ps": [], "track": []}
+    for _, C in CORR_C:
+        fm0 = (torch.randn(B, C, H, W, generator=g).relu_() / 16).to(dev)
+        fm1 = (torch.randn(B, C, H, W, generator=g).relu_() / 16).to(dev)
+        go = torch.randn(B, H, W, 2 * D + 1, 2 * D + 1, generator=g).to(dev)
+        inp["corr"].append((fm0, fm1, go))
+    for f in range(2 * B):
+        rois = torch.from_numpy(cases.rois_random(R, 1237 + f)).to(dev)
+        for nT in (N_CLS, N_REG):
+            inp["ps"].append((nT, torch.randn(nT * K * K, H, W, generator=g).to(dev), rois,
+                              torch.randn(R, nT, K, K, generator=g).to(dev)))
+    for pr in range(B):
+        rois = torch.from_numpy(cases.rois_random(R, 1238 + pr)).to(dev)
+        inp["track"].append((torch.randn(TRACK_C, H, W, generator=g).to(dev), rois,
+                             torch.randn(R, TRACK_C, K, K, generator=g).to(dev)))
+    return inp
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from detect_to_track_b200 import _lib
+    from detect_to_track_b200 import pointwise_correlation as pc, roipool as rp, ps_roipool as ps
+    import detect_to_track_b200 as d2t
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the extension is missing
+
+    inp = build_device_inputs(torch, dev, 1234 + rank)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    dom = {"e0": [], "e1": []}  # events around the dominant kernel pair (corr bwd, c5)
+
+    def step(record_dom=False):
+        keep = []
+        for idx, (fm0, fm1, go) in enumerate(inp["corr"]):
+            keep.append(pc.pointwise_correlation_forward(fm0, fm1, D, 1))
+            if record_dom and idx == 2:
+                a, b = ev(), ev()
+                a.record()
+                keep.append(pc.pointwise_correlation_backward(go, fm0, fm1, D, 1))
+                b.record()
+                dom["e0"].append(a); dom["e1"].append(b)
+            else:
+                keep.append(pc.pointwise_correlation_backward(go, fm0, fm1, D, 1))
+        for nT, fm, rois, go in inp["ps"]:
+            keep.append(ps.ps_roipool_forward(fm, rois, nT, K))
+            keep.append(ps.ps_roipool_backward(go, rois, H, W))
+        for fm, rois, go in inp["track"]:
+            keep.append(rp.roipool_forward(fm, rois, K))
+            keep.append(rp.roipool_backward(go, rois, H, W))
+        return keep
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        step(record_dom=True)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    dom_ms = sum(a.elapsed_time(b) for a, b in zip(dom["e0"], dom["e1"])) / max(1, len(dom["e0"]))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end from host buffers through the nn.Module API ------------------------------------
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_ms, h2d, d2h = run_e2e(torch, dev, d2t, e2e_steps, barrier, rank)
+
+    ms, e2e_ms = global_max([ms, e2e_ms], dev)
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        which = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        B, C5 = PAIRS_PER_GPU, 2048
+        P = live_pairs(H, W, D) * B
+        k2 = (2 * D + 1) ** 2
+        # dominant kernel = corr_bwd_tile_kernel on c5; the backward call is two launches of it (grad_FM0, grad_FM1).
+        # algorithmic bytes per launch: grad_out + one feature map read, one gradient map written
+        bytes_launch = (B * H * W * k2 + 2 * B * C5 * H * W) * 4
+        flops_launch = 2.0 * C5 * P
+        t_launch = dom_ms * 1e-3 / 2
+        fp32_peak = 72.5  # TFLOP/s, FFMA micro-benchmark on this pool's B200 (profiles/r1_microbench.txt)
+        line = {
+            "metric": METRIC, "value": job_throughput(world, args.steps, ms), "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "rois": R, "d_max": D, "r_hw": K,
+                       "l2": "per-step working set > 2 GB, far above the 126 MB L2 (no explicit flush needed)",
+                       "parallelism": f"{world} independent pair shards, no data-path collective"},
+            "roofline": {"bound": "hbm", "kernel": "corr_bwd_tile_kernel<8,8,*> (c5: C=2048, B=8)",
+                         "achieved": bytes_launch / t_launch * 1e-9, "peak": hbm, "unit": "GB/s",
+                         "frac": bytes_launch / t_launch * 1e-9 / hbm, "traffic": None, "peak_source": which,
+                         "us_per_launch": t_launch * 1e6,
+                         "note": "SIMT FP32 kernel: the binding roof is the FP32 pipe, see roofline_fp32"},
+            "roofline_fp32": {"bound": "fp32", "achieved": flops_launch / t_launch * 1e-12, "peak": fp32_peak,
+                              "unit": "TFLOP/s", "frac": flops_launch / t_launch * 1e-12 / fp32_peak,
+                              "peak_source": "measured FFMA micro-benchmark (profiles/r1_microbench.txt)"},
+            "e2e": {"value": job_throughput(world, e2e_steps, e2e_ms), "unit": "frame-pairs/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            pps, sec, cores = time_cpu(steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                                    "sample": "2 timed frame pairs (1 warm-up) of the same per-pair workload, "
+                                              "oracle/d2t_oracle.c with OpenMP on all host cores"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(torch, dev, d2t, steps, barrier, rank):
+    """Host buffers -> public nn.Module API (wired like correlation_tracker.py / rfcn.py) -> scalar loss on the host.
+
+    Per pair the host supplies the backbone pyramids of both frames (c3 at stride 8, down-sampled on the device
+    exactly as the reference does), the two RPN feature maps, the R-FCN score maps of both frames and the RoIs;
+    the device returns the loss.  All gradients flow through the custom ops' backward kernels on the device."""
+    import cases
+    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    tracker = d2t.CorrelationTracker(D, K, REG_CH).to(dev)
+    cls_pool, reg_pool = d2t.PSROIPool(N_CLS, K), d2t.PSROIPool(N_REG, K)
+    host = []
+    for pr in range(PAIRS_PER_GPU):
+        pin = lambda *shape: torch.randn(*shape, generator=g).pin_memory()
+        item = {
+            "c3": [pin(512, 2 * H, 2 * W).relu_() for _ in range(2)],     # stride-8 level, 76x126
+            "c4": [pin(1024, H, W).relu_() for _ in range(2)],
+            "c5": [pin(2048, H, W).relu_() for _ in range(2)],
+            "reg": [pin(REG_CH, H, W) for _ in range(2)],
+            "cls_map": [pin(N_CLS * K * K, H, W) for _ in range(2)],
+            "reg_map": [pin(N_REG * K * K, H, W) for _ in range(2)],
+            "rois": [torch.from_numpy(cases.rois_random(R, 2000 + 2 * pr + f)).pin_memory() for f in range(2)],
+        }
+        host.append(item)
+    h2d = sum(t.numel() * t.element_size() for it in host for v in it.values() for t in v)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def one_step():
+        total = torch.zeros((), device=dev)
+        for it in host:
+            d = {k: [t.to(dev, non_blocking=True) for t in v] for k, v in it.items()}
+            for k in ("c3", "c4", "c5", "reg", "cls_map", "reg_map"):
+                for t in d[k]:
+                    t.requires_grad_(True)
+            pyr0 = {"c3": d["c3"][0], "c4": d["c4"][0], "c5": d["c5"][0]}
+            pyr1 = {"c3": d["c3"][1], "c4": d["c4"][1], "c5": d["c5"][1]}
+            t_hat = tracker(pyr0, pyr1, d["reg"][0], d["reg"][1], d["rois"][0])
+            loss = t_hat.square().mean()
+            for f in range(2):
+                loss = loss + cls_pool(d["cls_map"][f], d["rois"][f]).mean(-1).mean(-1).square().mean()
+                loss = loss + reg_pool(d["reg_map"][f], d["rois"][f]).mean(-1).mean(-1).square().mean()
+            loss.backward()
+            total = total + loss.detach()
+        loss_host.copy_(total.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    one_step()
+    tracker.zero_grad(set_to_none=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+        tracker.zero_grad(set_to_none=True)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), h2d, 4
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,6 +33,7 @@ _WS7 = [_c_int] * 7
 SIGNATURES = {
     "d2t_abi_version": (_c_int, []),
     "d2t_last_error": (ctypes.c_char_p, []),
+    "d2t_launch_count": (ctypes.c_ulonglong, []),
     "d2t_corr_fwd_workspace_bytes": (_c_size_t, _WS7),
     "d2t_corr_bwd_workspace_bytes": (_c_size_t, _WS7),
     "d2t_corr_fwd_f32": (_c_int, _CORR_FWD),
@@ -93,6 +94,11 @@ def lib() -> ctypes.CDLL:
             raise RuntimeError(f"libd2t_b200.so ABI version {got} != expected {ABI_VERSION}")
         _lib = handle
     return _lib
+
+
+def launch_count() -> int:
+    """kernels launched by libd2t_b200.so so far in this process."""
+    return int(lib().d2t_launch_count())
 
 
 def last_error() -> str:

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace d2t {
@@ -15,6 +17,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
@@ -56,7 +61,7 @@ template <typename T>
 int psroipool_bwd_launch(const T*, const T*, T*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 template <typename T>
 int pool_bins_launch(const T*, int32_t*, int, int, int, int, int, cudaStream_t);
-size_t psroipool_bwd_ws_bytes(int R, int H, int W, int k);
+size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k);
 
 // tuned float32 correlation (corr_tile.cu)
 bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
@@ -85,6 +90,7 @@ extern "C" {
 
 int d2t_abi_version(void) { return D2T_B200_ABI_VERSION; }
 const char* d2t_last_error(void) { return g_err; }
+unsigned long long d2t_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- correlation -------------------------------------------------------------------
 size_t d2t_corr_fwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size) {
@@ -157,8 +163,8 @@ int d2t_roipool_bwd_f64(const double* grad_out, const double* rois, double* grad
 
 // ---- PSROIPool -----------------------------------------------------------------------
 size_t d2t_psroipool_fwd_workspace_bytes(int, int, int, int, int, int) { return 0; }
-size_t d2t_psroipool_bwd_workspace_bytes(int R, int, int H, int W, int r_hw, int) {
-    return psroipool_bwd_ws_bytes(R, H, W, r_hw);
+size_t d2t_psroipool_bwd_workspace_bytes(int R, int n_targets, int H, int W, int r_hw, int) {
+    return psroipool_bwd_ws_bytes(R, n_targets, H, W, r_hw);
 }
 
 int d2t_psroipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int n_targets, int H, int W, int r_hw,

@@ -11,6 +11,7 @@ namespace d2t {
 // ---- error plumbing ---------------------------------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void note_launch(int n = 1);  // kernel-launch counter behind d2t_launch_count()
 
 #define D2T_CUDA_TRY(expr)                                         \
     do {                                                           \

@@ -103,6 +103,7 @@ int corr_fwd_generic_launch(const T* fm0, const T* fm1, T* out, int B, int C, in
     if (blocks > cap) blocks = cap;
     corr_fwd_generic_kernel<T><<<(int)blocks, kThreads, 0, st>>>(fm0, fm1, out, B, C, H, W, d, stride);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 
@@ -119,6 +120,7 @@ int corr_bwd_generic_launch(const T* go, const T* fm0, const T* fm1, T* g0, T* g
     if (blocks > cap) blocks = cap;
     corr_bwd_generic_kernel<T><<<(int)blocks, kThreads, 0, st>>>(go, fm0, fm1, g0, g1, B, C, H, W, d, stride);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 

@@ -63,6 +63,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, bool valid) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
 }
+__device__ __forceinline__ void cp_async4s(uint32_t dst, const float* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -127,26 +130,31 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         const float* k_img = fm1 + (size_t)b * C * plane;
 
         // ---- staging map: this thread's key / query elements inside one channel plane -------
-        int koff[Cfg::KPASS];  // global offset inside the plane, or -1
-        int ksm[Cfg::KPASS];   // shared offset inside the channel block, or -1 (row beyond patch)
+        // Loop-invariant per segment: a running global pointer (advanced one plane per channel), the
+        // shared-memory byte offset inside a channel block and the copy size (4, or 0 = zero-fill).
+        const float* kptr[Cfg::KPASS];
+        uint32_t kdst[Cfg::KPASS], ksz[Cfg::KPASS];
 #pragma unroll
         for (int ps = 0; ps < Cfg::KPASS; ++ps) {
             const int r = ps * 8 + warp, x = lane;
             const int gi = i0 - D + r, gj = j0 - D + x;
             const bool inPatch = r < Cfg::KROWS && x < Cfg::KP;
             const bool inImg = inPatch && x < Cfg::KCOLS && gi >= 0 && gi < H && gj >= 0 && gj < W;
-            ksm[ps] = inPatch ? Cfg::QROWS * Cfg::QP + krow_off<D>(r) + x : -1;
-            koff[ps] = inImg ? gi * W + gj : -1;
+            kdst[ps] = inPatch ? (uint32_t)(Cfg::QROWS * Cfg::QP + krow_off<D>(r) + x) * 4u : 0xffffffffu;
+            ksz[ps] = inImg ? 4u : 0u;
+            kptr[ps] = k_img + (size_t)chunkBeg * CK * plane + (inImg ? gi * W + gj : 0);
         }
-        int qoff[Cfg::QPASS], qsm[Cfg::QPASS];
+        const float* qptr[Cfg::QPASS];
+        uint32_t qdst[Cfg::QPASS], qsz[Cfg::QPASS];
 #pragma unroll
         for (int ps = 0; ps < Cfg::QPASS; ++ps) {
             const int e = ps * kCorrThreads + tid;
             const int r = e / Cfg::QCOLS, x = e % Cfg::QCOLS;
             const bool inTile = e < Cfg::QROWS * Cfg::QCOLS;
             const bool inImg = inTile && i0 + r < H && j0 + x < W;
-            qsm[ps] = inTile ? r * Cfg::QP + x : -1;
-            qoff[ps] = inImg ? (i0 + r) * W + (j0 + x) : -1;
+            qdst[ps] = inTile ? (uint32_t)(r * Cfg::QP + x) * 4u : 0xffffffffu;
+            qsz[ps] = inImg ? 4u : 0u;
+            qptr[ps] = q_img + (size_t)chunkBeg * CK * plane + (inImg ? (i0 + r) * W + (j0 + x) : 0);
         }
 
         const bool taskLive = (i0 + qrow < H) && (i0 - D + kr >= 0) && (i0 - D + kr < H);
@@ -159,27 +167,28 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
             for (int t = 0; t < TD; ++t) acc[a][t] = 0.f;
 
         // asynchronous staging of one channel chunk (cp.async: no staging registers, no scoreboard
-        // coupling with the LDS of the compute loop)
+        // coupling with the LDS of the compute loop).  Chunks are issued strictly in order, so the
+        // running pointers are simply advanced.
         const uint32_t smemBase = smem_u32(smem);
         auto issue_chunk = [&](int chunk) {
             if (chunk < chunkEnd) {
-                const int c0 = chunk * CK;
-                const uint32_t stage = smemBase + (uint32_t)((chunk - chunkBeg) % kStages) * STAGE_FLOATS * 4u;
+                const uint32_t stage = smemBase + (uint32_t)((chunk - chunkBeg) % kStages) * (STAGE_FLOATS * 4u);
+                const int nvalid = min(CK, C - chunk * CK);  // channels of this chunk that exist
 #pragma unroll
                 for (int cc = 0; cc < CK; ++cc) {
-                    const bool cvalid = c0 + cc < C;
-                    const float* kp = k_img + (size_t)(cvalid ? c0 + cc : 0) * plane;
-                    const float* qp = q_img + (size_t)(cvalid ? c0 + cc : 0) * plane;
+                    const bool cv = cc < nvalid;  // uniform; false only in the last chunk of a ragged C
 #pragma unroll
-                    for (int ps = 0; ps < Cfg::KPASS; ++ps)
-                        if (ksm[ps] >= 0)
-                            cp_async4(stage + (cc * Cfg::CH_FLOATS + ksm[ps]) * 4u, kp + (koff[ps] >= 0 ? koff[ps] : 0),
-                                      cvalid && koff[ps] >= 0);
+                    for (int ps = 0; ps < Cfg::KPASS; ++ps) {
+                        if (kdst[ps] != 0xffffffffu)
+                            cp_async4s(stage + cc * (Cfg::CH_FLOATS * 4u) + kdst[ps], kptr[ps], cv ? ksz[ps] : 0u);
+                        if (cv) kptr[ps] += plane;
+                    }
 #pragma unroll
-                    for (int ps = 0; ps < Cfg::QPASS; ++ps)
-                        if (qsm[ps] >= 0)
-                            cp_async4(stage + (cc * Cfg::CH_FLOATS + qsm[ps]) * 4u, qp + (qoff[ps] >= 0 ? qoff[ps] : 0),
-                                      cvalid && qoff[ps] >= 0);
+                    for (int ps = 0; ps < Cfg::QPASS; ++ps) {
+                        if (qdst[ps] != 0xffffffffu)
+                            cp_async4s(stage + cc * (Cfg::CH_FLOATS * 4u) + qdst[ps], qptr[ps], cv ? qsz[ps] : 0u);
+                        if (cv) qptr[ps] += plane;
+                    }
                 }
             }
             cp_async_commit();  // always commit: keeps the group count in step with the chunk index
@@ -374,31 +383,33 @@ corr_bwd_tile_kernel(const float* __restrict__ go, const float* __restrict__ xsr
         }
         const bool warpLive = __any_sync(0xffffffffu, taskLive);
 
-        // ---- staging map for the patch ---------------------------------------------------------------
-        int koff[Cfg::KPASS], ksm[Cfg::KPASS];
+        // ---- staging map for the patch (see the forward kernel) -----------------------------------------
+        const float* kptr[Cfg::KPASS];
+        uint32_t kdst[Cfg::KPASS], ksz[Cfg::KPASS];
 #pragma unroll
         for (int ps = 0; ps < Cfg::KPASS; ++ps) {
             const int r = ps * 8 + warp, x = lane;
             const int gi = i0 - OFF + r, gj = j0 - OFF + x;
             const bool inPatch = r < Cfg::KROWS && x < Cfg::KP;
             const bool inImg = inPatch && x < Cfg::KCOLS && gi >= 0 && gi < H && gj >= 0 && gj < W;
-            ksm[ps] = inPatch ? krow_off<D>(r) + x : -1;
-            koff[ps] = inImg ? gi * W + gj : -1;
+            kdst[ps] = inPatch ? (uint32_t)(krow_off<D>(r) + x) * 4u : 0xffffffffu;
+            ksz[ps] = inImg ? 4u : 0u;
+            kptr[ps] = x_img + (size_t)chunkBeg * CK * plane + (inImg ? gi * W + gj : 0);
         }
         const uint32_t smemBase = smem_u32(smem);
         auto issue_chunk = [&](int chunk) {
             if (chunk < chunkEnd) {
-                const int c0 = chunk * CK;
-                const uint32_t stage = smemBase + (uint32_t)((chunk - chunkBeg) % kStages) * STAGE_FLOATS * 4u;
+                const uint32_t stage = smemBase + (uint32_t)((chunk - chunkBeg) % kStages) * (STAGE_FLOATS * 4u);
+                const int nvalid = min(CK, C - chunk * CK);
 #pragma unroll
                 for (int cc = 0; cc < CK; ++cc) {
-                    const bool cvalid = c0 + cc < C;
-                    const float* kp = x_img + (size_t)(cvalid ? c0 + cc : 0) * plane;
+                    const bool cv = cc < nvalid;
 #pragma unroll
-                    for (int ps = 0; ps < Cfg::KPASS; ++ps)
-                        if (ksm[ps] >= 0)
-                            cp_async4(stage + (cc * XCH + ksm[ps]) * 4u, kp + (koff[ps] >= 0 ? koff[ps] : 0),
-                                      cvalid && koff[ps] >= 0);
+                    for (int ps = 0; ps < Cfg::KPASS; ++ps) {
+                        if (kdst[ps] != 0xffffffffu)
+                            cp_async4s(stage + cc * (XCH * 4u) + kdst[ps], kptr[ps], cv ? ksz[ps] : 0u);
+                        if (cv) kptr[ps] += plane;
+                    }
                 }
             }
             cp_async_commit();
@@ -534,10 +545,12 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<p.G, kCorrThreads, smem, st>>>(fm0, fm1, out, static_cast<float*>(ws), p);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     if (p.ipc % p.NI != 0) {  // some tile is split over CTAs
         dim3 grid(p.T, Cfg::QROWS);
         corr_fwd_finalize_kernel<D><<<grid, 256, 0, st>>>(static_cast<const float*>(ws), out, p);
         D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
     }
     return D2T_OK;
 }
@@ -563,8 +576,10 @@ static int bwd_launch(const float* go, const float* fm0, const float* fm1, float
     D2T_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k0<<<p.G, kCorrThreads, smem, st>>>(go, fm1, g0, p);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     k1<<<p.G, kCorrThreads, smem, st>>>(go, fm0, g1, p);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 

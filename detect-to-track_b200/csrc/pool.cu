@@ -6,23 +6,25 @@
 //
 //  ROIPool fwd  : "channel-owner" CTAs.  A CTA loads a slab of CB channel planes
 //                 into shared memory ONCE (coalesced), then walks all RoIs and
-//                 emits out[r, c0:c0+CB, :, :] -- a contiguous run per RoI --
-//                 so the feature map is read from HBM once and the output is
-//                 written once, coalesced.  Bin pixels are summed rows-then-
-//                 columns, the reference's order, so float results are
-//                 bit-identical to the reference kernel.
-//  ROIPool bwd  : same ownership.  The CTA keeps its slab of grad planes in
-//                 shared memory, walks the RoIs IN ORDER and adds each RoI's
-//                 contribution with exclusive (thread-owned) read-modify-writes:
-//                 deterministic, no atomics, grad_fm written exactly once
-//                 (no zero-fill pass).
+//                 emits out[r, c0:c0+CB, :, :], so the feature map is read from HBM
+//                 once.  1024 threads per CTA; a thread owns one (RoI, channel,
+//                 column-bin) and produces its r_hw outputs, summing bin pixels
+//                 rows-then-columns -- the reference's order -- so float results
+//                 are bit-identical to the reference kernel.
+//  ROIPool bwd  : same slab ownership, and inside the CTA every thread OWNS one pixel
+//                 column of one channel for ALL RoIs.  It walks the RoIs in order
+//                 and adds each RoI's contribution to its own column: no atomics, no
+//                 barrier per RoI, a fixed summation order (deterministic), and
+//                 grad_fm written exactly once (no zero-fill pass).
 //  PSROIPool fwd: one thread per output, target index fastest so the lanes of a
 //                 warp share a bin (same trip count).
-//  PSROIPool bwd: pixel-owner gather.  A tiny prep kernel builds, per bin row /
-//                 bin column index, bitmasks over RoIs ("which RoIs' bin i covers
-//                 pixel row y").  Each output pixel ANDs a row mask with a column
-//                 mask and visits the surviving RoIs in ascending order:
-//                 deterministic, no atomics, every pixel written exactly once.
+//  PSROIPool bwd: pixel-owner gather.  A tiny prep pass builds (a) the inverse of the
+//                 many-to-one channel map (which (target, bin) pairs read channel ch:
+//                 SURVEY.md F6) and (b) per bin row / bin column index, bitmasks over
+//                 RoIs ("which RoIs' bin i covers pixel row y").  Each output pixel
+//                 ANDs a row mask with a column mask and visits the surviving RoIs in
+//                 ascending order: deterministic, no atomics, every pixel written
+//                 exactly once; channels nobody reads are just zero-filled.
 #include "common.cuh"
 
 namespace d2t {
@@ -45,7 +47,9 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 }
 
 constexpr int kPoolThreads = 256;
+constexpr int kSlabThreads = 1024;  // channel-owner kernels: one CTA per SM, 32 warps to hide latency
 constexpr int kMaxK = 32;  // largest supported r_hw
+__host__ __device__ __forceinline__ size_t align_up_dev(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- bin edges for a chunk of RoIs into shared memory -------------------------
 template <typename T, bool kClampStart>
@@ -67,15 +71,15 @@ __device__ __forceinline__ void edges_to_smem(const T* __restrict__ rois, int r0
 // =================================================================================
 // ROIPool forward
 // =================================================================================
-// smem: T plane[CB][HB*W] | short edges[4][RCH*k]
+// smem: T plane[CB][H*W] | short edges[4][RCH*k]
 template <typename T>
-__global__ void __launch_bounds__(kPoolThreads)
+__global__ void __launch_bounds__(kSlabThreads)
 roipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __restrict__ out, int R, int C, int H,
-                   int W, int k, int CB, int RCH, FastDiv dCBkk, FastDiv dkk, FastDiv dk) {
+                   int W, int k, int CB, int RCH, FastDiv dCBk, FastDiv dk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* plane = reinterpret_cast<T*>(smem_raw);
     const int HW = H * W;
-    short* sI0 = reinterpret_cast<short*>(plane + (size_t)CB * HW);
+    short* sI0 = reinterpret_cast<short*>(smem_raw + align_up_dev((size_t)CB * HW * sizeof(T), 16));
     short* sI1 = sI0 + RCH * k;
     short* sJ0 = sI1 + RCH * k;
     short* sJ1 = sJ0 + RCH * k;
@@ -97,26 +101,28 @@ roipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __re
         edges_to_smem<T, true>(rois, rbase, nr, k, H, W, sI0, sI1, sJ0, sJ1);
         __syncthreads();
 
-        const int total = nr * CB * kk;
-        for (int o = threadIdx.x; o < total; o += blockDim.x) {
-            const int rr = fdiv(o, dCBkk);
-            const int rem = o - rr * (CB * kk);
-            const int cc = fdiv(rem, dkk);
+        // item = (roi, channel, column bin); column bin fastest
+        const int total = nr * CB * k;
+        for (int item = threadIdx.x; item < total; item += blockDim.x) {
+            const int rr = fdiv(item, dCBk);
+            const int rem = item - rr * (CB * k);
+            const int cc = fdiv(rem, dk);
             if (cc >= cb) continue;
-            const int b = rem - cc * kk;
-            const int i = fdiv(b, dk);
-            const int j = b - i * k;
-            const int i0 = sI0[rr * k + i], i1 = sI1[rr * k + i];
+            const int j = rem - cc * k;
             const int j0 = sJ0[rr * k + j], j1 = sJ1[rr * k + j];
             const T* p = plane + (size_t)cc * HW;
-            T acc = 0;
-            for (int pi = i0; pi < i1; ++pi) {
-                const T* row = p + pi * W;
-                for (int pj = j0; pj < j1; ++pj) acc += row[pj];
+            T* o = out + ((size_t)(rbase + rr) * C + c0 + cc) * kk + j;
+            for (int i = 0; i < k; ++i) {
+                const int i0 = sI0[rr * k + i], i1 = sI1[rr * k + i];
+                T acc = 0;
+                for (int pi = i0; pi < i1; ++pi) {
+                    const T* row = p + pi * W;
+                    for (int pj = j0; pj < j1; ++pj) acc += row[pj];
+                }
+                const int numel = (i1 - i0) * (j1 - j0);
+                acc /= numel;  // no empty-bin guard: 0/0 = NaN like roipool_cuda.cu:61
+                o[i * k] = acc;
             }
-            const int numel = (i1 - i0) * (j1 - j0);
-            acc /= numel;  // no empty-bin guard: 0/0 = NaN like roipool_cuda.cu:61
-            out[((size_t)(rbase + rr) * C + c0 + cc) * kk + b] = acc;
         }
     }
 }
@@ -124,18 +130,17 @@ roipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __re
 // =================================================================================
 // ROIPool backward
 // =================================================================================
-// smem: T acc[CB][HW] | T g[CB*kk] | T inv[kk] | short edges[4][RCH*k]
+// smem: T acc[CB][H*W] | T inv[RCH][k*k] | short edges[4][RCH*k]
 template <typename T>
-__global__ void __launch_bounds__(kPoolThreads)
+__global__ void __launch_bounds__(kSlabThreads)
 roipool_bwd_kernel(const T* __restrict__ go, const T* __restrict__ rois, T* __restrict__ gin, int R, int C, int H,
-                   int W, int k, int CB, int RCH) {
+                   int W, int k, int CB, int RCH, FastDiv dW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* acc = reinterpret_cast<T*>(smem_raw);
     const int HW = H * W;
     const int kk = k * k;
-    T* sg = acc + (size_t)CB * HW;
-    T* sinv = sg + CB * kk;
-    short* sI0 = reinterpret_cast<short*>(sinv + kk);
+    T* sinv = reinterpret_cast<T*>(smem_raw + align_up_dev((size_t)CB * HW * sizeof(T), 16));
+    short* sI0 = reinterpret_cast<short*>(reinterpret_cast<unsigned char*>(sinv) + align_up_dev((size_t)RCH * kk * sizeof(T), 16));
     short* sI1 = sI0 + RCH * k;
     short* sJ0 = sI1 + RCH * k;
     short* sJ1 = sJ0 + RCH * k;
@@ -149,67 +154,42 @@ roipool_bwd_kernel(const T* __restrict__ go, const T* __restrict__ rois, T* __re
         const int nr = min(RCH, R - rbase);
         __syncthreads();
         edges_to_smem<T, true>(rois, rbase, nr, k, H, W, sI0, sI1, sJ0, sJ1);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nr * kk; idx += blockDim.x) {
+            const int rr = idx / kk, b = idx - rr * kk;
+            const int i = b / k, j = b - i * k;
+            const int numel = (sI1[rr * k + i] - sI0[rr * k + i]) * (sJ1[rr * k + j] - sJ0[rr * k + j]);
+            sinv[idx] = static_cast<T>(1) / static_cast<T>(numel);
+        }
+        __syncthreads();
 
-        for (int rr = 0; rr < nr; ++rr) {
-            __syncthreads();  // previous RoI's readers of sg/sinv are done; edges visible
-            // stage this RoI's gradient block (cb*kk contiguous) and 1/numel table
-            {
-                const T* src = go + ((size_t)(rbase + rr) * C + c0) * kk;
-                for (int idx = threadIdx.x; idx < cb * kk; idx += blockDim.x) sg[idx] = __ldg(src + idx);
-                for (int b = threadIdx.x; b < kk; b += blockDim.x) {
-                    const int i = b / k, j = b - i * k;
-                    const int numel = (sI1[rr * k + i] - sI0[rr * k + i]) * (sJ1[rr * k + j] - sJ0[rr * k + j]);
-                    sinv[b] = static_cast<T>(1) / static_cast<T>(numel);
-                }
-            }
-            __syncthreads();
-
-            const short* I0 = sI0 + rr * k;
-            const short* I1 = sI1 + rr * k;
-            const short* J0 = sJ0 + rr * k;
-            const short* J1 = sJ1 + rr * k;
-            const int colLo = J0[0], colHi = J1[k - 1];
-            const int w = colHi - colLo;
-            if (w > kPoolThreads) {
-                // RoI wider than the block: strided loop over (channel, column)
-                for (int item = threadIdx.x; item < cb * w; item += blockDim.x) {
-                    const int cc = item / w;
-                    const int pjx = colLo + (item - cc * w);
-                    T* a = acc + (size_t)cc * HW;
-                    for (int i = 0; i < k; ++i) {
-                        T u = 0;
-                        for (int j = 0; j < k; ++j)
-                            if (J0[j] <= pjx && pjx < J1[j]) u += sg[cc * kk + i * k + j] * sinv[i * k + j];
-                        for (int pi = I0[i]; pi < I1[i]; ++pi) a[pi * W + pjx] += u;
-                    }
-                }
-            } else if (w > 0) {
-                // thread <-> (channel, column): column index in the low lw bits
-                int lw = 0;
-                while ((1 << lw) < w) ++lw;
-                const int x = threadIdx.x & ((1 << lw) - 1);
-                const int ccStep = kPoolThreads >> lw;
-                const int pj = colLo + x;
+        // this thread owns pixel column pj of channel cc for every RoI: exclusive read-modify-write
+        for (int item = threadIdx.x; item < cb * W; item += blockDim.x) {
+            const int cc = fdiv(item, dW);
+            const int pj = item - cc * W;
+            T* a = acc + (size_t)cc * HW + pj;
+            const T* gch = go + ((size_t)rbase * C + c0 + cc) * kk;
+            for (int rr = 0; rr < nr; ++rr) {
+                const short* J0 = sJ0 + rr * k;
+                const short* J1 = sJ1 + rr * k;
+                if (pj < J0[0] || pj >= J1[k - 1]) continue;
                 // column bins covering pj form a contiguous range [jlo, jhi]
                 int jlo = k, jhi = -1;
-                if (x < w) {
-                    for (int j = 0; j < k; ++j) {
-                        if (J0[j] <= pj && pj < J1[j]) {
-                            jlo = min(jlo, j);
-                            jhi = j;
-                        }
+                for (int j = 0; j < k; ++j) {
+                    if (J0[j] <= pj && pj < J1[j]) {
+                        jlo = min(jlo, j);
+                        jhi = j;
                     }
                 }
-                if (jhi >= 0) {
-                    for (int cc = threadIdx.x >> lw; cc < cb; cc += ccStep) {
-                        T* a = acc + (size_t)cc * HW + pj;
-                        const T* g = sg + cc * kk;
-                        for (int i = 0; i < k; ++i) {
-                            T u = 0;
-                            for (int j = jlo; j <= jhi; ++j) u += g[i * k + j] * sinv[i * k + j];
-                            for (int pi = I0[i]; pi < I1[i]; ++pi) a[pi * W] += u;
-                        }
-                    }
+                if (jhi < 0) continue;
+                const T* g = gch + (size_t)rr * C * kk;
+                const T* inv = sinv + rr * kk;
+                const short* I0 = sI0 + rr * k;
+                const short* I1 = sI1 + rr * k;
+                for (int i = 0; i < k; ++i) {
+                    T u = 0;
+                    for (int j = jlo; j <= jhi; ++j) u += __ldg(g + i * k + j) * inv[i * k + j];
+                    for (int pi = I0[i]; pi < I1[i]; ++pi) a[pi * W] += u;
                 }
             }
         }
@@ -265,15 +245,37 @@ psroipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __
 struct PsBwdWs {
     short *eI0, *eI1, *eJ0, *eJ1;
     uint32_t *rowmask, *colmask;
+    int* entCount;   // [nCh]      how many (target, bin) pairs read channel ch
+    uint32_t* ent;   // [nCh][nT]  those pairs, ascending target: (t << 16) | (i*k + j)
     int NW;
 };
 
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
-psroipool_bwd_prep_kernel(const T* __restrict__ rois, PsBwdWs ws, int R, int H, int W, int k) {
-    // phase 1: edges (grid-stride)
+psroipool_bwd_prep_kernel(const T* __restrict__ rois, PsBwdWs ws, int R, int nT, int H, int W, int k, bool canonical) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
+    // inverse channel map: reference map (t+1)*(i*k+j) is many-to-one
+    const int kk = k * k;
+    for (int ch = tid; ch < nT * kk; ch += nth) {
+        int n = 0;
+        uint32_t* e = ws.ent + (size_t)ch * nT;
+        if (canonical) {
+            const int t = ch / kk;
+            e[n++] = ((uint32_t)t << 16) | (uint32_t)(ch - t * kk);
+        } else {
+            for (int t = 0; t < nT; ++t) {
+                if (ch == 0) {
+                    e[n++] = (uint32_t)t << 16;  // bin (0,0) of every target reads channel 0
+                } else if (ch % (t + 1) == 0) {
+                    const int sidx = ch / (t + 1);
+                    if (sidx < kk) e[n++] = ((uint32_t)t << 16) | (uint32_t)sidx;
+                }
+            }
+        }
+        ws.entCount[ch] = n;
+    }
+    // bin edges
     for (int idx = tid; idx < R * k; idx += nth) {
         const int r = idx / k, b = idx - r * k;
         const T* roi = rois + (size_t)r * 4;
@@ -312,8 +314,7 @@ psroipool_bwd_mask_kernel(PsBwdWs ws, int R, int H, int W, int k) {
 // grid: (ceil(H*W / kPoolThreads), nChannels)
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
-psroipool_bwd_kernel(const T* __restrict__ go, PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int W, int k,
-                     bool canonical) {
+psroipool_bwd_kernel(const T* __restrict__ go, PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int W, int k) {
     const int ch = blockIdx.y;
     const int kk = k * k;
     const int HW = H * W;
@@ -324,22 +325,12 @@ psroipool_bwd_kernel(const T* __restrict__ go, PsBwdWs ws, T* __restrict__ gin, 
     const int NW = ws.NW;
 
     T acc = 0;
-    // entries (t, s=i*k+j) mapping to this channel, ascending t
-    const int tBeg = canonical ? ch / kk : 0;
-    const int tEnd = canonical ? tBeg + 1 : nT;
-    for (int t = tBeg; t < tEnd; ++t) {
-        int s;
-        if (canonical) {
-            s = ch - t * kk;
-        } else if (ch == 0) {
-            s = 0;  // (t+1)*0 == 0 for every target
-        } else {
-            if (ch % (t + 1) != 0) continue;
-            s = ch / (t + 1);
-            if (s >= kk || s == 0) continue;
-        }
+    const int nEnt = ws.entCount[ch];
+    const uint32_t* ent = ws.ent + (size_t)ch * nT;
+    for (int en = 0; en < nEnt && active; ++en) {
+        const uint32_t pk = __ldg(ent + en);
+        const int t = pk >> 16, s = pk & 0xffff;
         const int i = s / k, j = s - i * k;
-        if (!active) continue;
         const uint32_t* rm = ws.rowmask + ((size_t)i * H + y) * NW;
         const uint32_t* cm = ws.colmask + ((size_t)j * W + x) * NW;
         for (int w = 0; w < NW; ++w) {
@@ -394,32 +385,31 @@ struct SlabPlan {
 };
 
 // Choose the channel slab so that the grid is one balanced wave when possible.
-static int plan_slab(int R, int C, int H, int W, int k, size_t elem, size_t extra_per_cb, size_t extra_fixed,
-                     SlabPlan* plan) {
+// shared memory = CB planes + per-RoI tables for a chunk of RCH RoIs (4 int16 edge arrays + `per_roi` bytes).
+static int plan_slab(int R, int C, int H, int W, int k, size_t elem, size_t per_roi, SlabPlan* plan) {
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
     const size_t budget = (size_t)di.max_smem_optin - 1024;
     int RCH = R < 256 ? (R > 0 ? R : 1) : 256;
-    const size_t edgeBytes = align_up((size_t)4 * RCH * k * sizeof(short), 16);
-    const size_t perCB = (size_t)H * W * elem + extra_per_cb;
-    if (perCB + edgeBytes + extra_fixed > budget) {
-        set_error("feature map plane %dx%d (%zu B) does not fit the %zu B shared-memory slab", H, W,
-                  (size_t)H * W * elem, budget);
+    const size_t perCB = (size_t)H * W * elem;
+    auto tables = [&](int rch) { return align_up((size_t)rch * per_roi, 16) + align_up((size_t)4 * rch * k * sizeof(short), 16); };
+    while (RCH > 8 && perCB + tables(RCH) > budget) RCH /= 2;
+    if (perCB + tables(RCH) > budget) {
+        set_error("feature map plane %dx%d (%zu B) does not fit the %zu B shared-memory slab", H, W, perCB, budget);
         return D2T_ERR_BAD_ARG;
     }
-    int maxCB = (int)((budget - edgeBytes - extra_fixed) / perCB);
+    int maxCB = (int)((budget - tables(RCH)) / perCB);
     int CB = ceil_div(C, di.sm_count);  // one wave, one CTA per SM
     if (CB > maxCB) {
-        // several waves: balance them
-        const int waves = ceil_div(ceil_div(C, maxCB), di.sm_count);
+        const int waves = ceil_div(ceil_div(C, maxCB), di.sm_count);  // several waves: balance them
         CB = ceil_div(C, waves * di.sm_count);
         if (CB > maxCB) CB = maxCB;
     }
     if (CB < 1) CB = 1;
     plan->CB = CB;
     plan->RCH = RCH;
-    plan->smem = align_up((size_t)CB * perCB, 16) + extra_fixed + edgeBytes;
+    plan->smem = align_up((size_t)CB * perCB, 16) + tables(RCH);
     plan->grid = ceil_div(C, CB);
     return 0;
 }
@@ -431,13 +421,13 @@ int roipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int C, int H, 
     D2T_REQUIRE(H < 32768 && W < 32768, "roipool_fwd: H, W must be < 32768");
     if (R == 0 || C == 0) return D2T_OK;
     SlabPlan p;
-    int rc = plan_slab(R, C, H, W, k, sizeof(T), 0, 0, &p);
+    int rc = plan_slab(R, C, H, W, k, sizeof(T), 0, &p);
     if (rc) return rc;
     D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    roipool_fwd_kernel<T><<<p.grid, kPoolThreads, p.smem, st>>>(fm, rois, out, R, C, H, W, k, p.CB, p.RCH,
-                                                                 make_fastdiv(p.CB * k * k), make_fastdiv(k * k),
-                                                                 make_fastdiv(k));
+    roipool_fwd_kernel<T><<<p.grid, kSlabThreads, p.smem, st>>>(fm, rois, out, R, C, H, W, k, p.CB, p.RCH,
+                                                                 make_fastdiv(p.CB * k), make_fastdiv(k));
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 
@@ -452,12 +442,13 @@ int roipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int C, int H, 
         return D2T_OK;
     }
     SlabPlan p;
-    const size_t kk = (size_t)k * k;
-    int rc = plan_slab(R, C, H, W, k, sizeof(T), kk * sizeof(T), align_up(kk * sizeof(T), 16), &p);
+    int rc = plan_slab(R, C, H, W, k, sizeof(T), (size_t)k * k * sizeof(T), &p);
     if (rc) return rc;
     D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    roipool_bwd_kernel<T><<<p.grid, kPoolThreads, p.smem, st>>>(go, rois, gin, R, C, H, W, k, p.CB, p.RCH);
+    roipool_bwd_kernel<T><<<p.grid, kSlabThreads, p.smem, st>>>(go, rois, gin, R, C, H, W, k, p.CB, p.RCH,
+                                                                 make_fastdiv(W));
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 
@@ -479,10 +470,11 @@ int psroipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int nT, int 
                                                             (flags & D2T_PS_CANONICAL_MAP) != 0, make_fastdiv(nT),
                                                             make_fastdiv(k), make_fastdiv(k * k));
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 
-static size_t psroipool_bwd_ws_layout(int R, int H, int W, int k, void* base, PsBwdWs* ws) {
+static size_t psroipool_bwd_ws_layout(int R, int nT, int H, int W, int k, void* base, PsBwdWs* ws) {
     const int NW = ceil_div(R > 0 ? R : 1, 32);
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -493,6 +485,7 @@ static size_t psroipool_bwd_ws_layout(int R, int H, int W, int k, void* base, Ps
     const size_t e = (size_t)(R > 0 ? R : 1) * k * sizeof(short);
     size_t o0 = take(e), o1 = take(e), o2 = take(e), o3 = take(e);
     size_t orow = take((size_t)k * H * NW * 4), ocol = take((size_t)k * W * NW * 4);
+    size_t ocnt = take((size_t)nT * k * k * sizeof(int)), oent = take((size_t)nT * k * k * nT * sizeof(uint32_t));
     if (ws) {
         char* b = static_cast<char*>(base);
         ws->eI0 = (short*)(b + o0);
@@ -501,12 +494,16 @@ static size_t psroipool_bwd_ws_layout(int R, int H, int W, int k, void* base, Ps
         ws->eJ1 = (short*)(b + o3);
         ws->rowmask = (uint32_t*)(b + orow);
         ws->colmask = (uint32_t*)(b + ocol);
+        ws->entCount = (int*)(b + ocnt);
+        ws->ent = (uint32_t*)(b + oent);
         ws->NW = NW;
     }
     return off;
 }
 
-size_t psroipool_bwd_ws_bytes(int R, int H, int W, int k) { return psroipool_bwd_ws_layout(R, H, W, k, nullptr, nullptr); }
+size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k) {
+    return psroipool_bwd_ws_layout(R, nT, H, W, k, nullptr, nullptr);
+}
 
 template <typename T>
 int psroipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int nT, int H, int W, int k, int flags, void* wsp,
@@ -520,22 +517,26 @@ int psroipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int nT, int 
         D2T_CUDA_TRY(cudaMemsetAsync(gin, 0, (size_t)nCh * H * W * sizeof(T), st));
         return D2T_OK;
     }
-    const size_t need = psroipool_bwd_ws_bytes(R, H, W, k);
+    const size_t need = psroipool_bwd_ws_bytes(R, nT, H, W, k);
     if (wsp == nullptr || ws_bytes < need) {
         set_error("psroipool_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
         return D2T_ERR_WORKSPACE;
     }
     PsBwdWs ws;
-    psroipool_bwd_ws_layout(R, H, W, k, wsp, &ws);
-    psroipool_bwd_prep_kernel<T><<<ceil_div(R * k, kPoolThreads), kPoolThreads, 0, st>>>(rois, ws, R, H, W, k);
+    psroipool_bwd_ws_layout(R, nT, H, W, k, wsp, &ws);
+    const int prepItems = R * k > nCh ? R * k : nCh;
+    psroipool_bwd_prep_kernel<T><<<ceil_div(prepItems, kPoolThreads), kPoolThreads, 0, st>>>(
+        rois, ws, R, nT, H, W, k, (flags & D2T_PS_CANONICAL_MAP) != 0);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     const int nMask = k * (H + W) * ws.NW;
     psroipool_bwd_mask_kernel<T><<<ceil_div(nMask, kPoolThreads), kPoolThreads, 0, st>>>(ws, R, H, W, k);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     dim3 grid(ceil_div(H * W, kPoolThreads), nCh);
-    psroipool_bwd_kernel<T><<<grid, kPoolThreads, 0, st>>>(go, ws, gin, R, nT, H, W, k,
-                                                            (flags & D2T_PS_CANONICAL_MAP) != 0);
+    psroipool_bwd_kernel<T><<<grid, kPoolThreads, 0, st>>>(go, ws, gin, R, nT, H, W, k);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 
@@ -545,6 +546,7 @@ int pool_bins_launch(const T* rois, int32_t* edges, int R, int H, int W, int k, 
     if (R == 0) return D2T_OK;
     pool_bins_kernel<T><<<ceil_div(R * k, 256), 256, 0, st>>>(rois, edges, R, H, W, k, clampStart);
     D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     return D2T_OK;
 }
 

@@ -68,6 +68,8 @@ extern "C" {
 
 D2T_API int d2t_abi_version(void);
 D2T_API const char* d2t_last_error(void);
+/* number of kernels this library has launched in this process (monotonic; instrumentation for bench.py) */
+D2T_API unsigned long long d2t_launch_count(void);
 
 /* ---- PointwiseCorrelation ------------------------------------------------
  * fm0, fm1 : (B, C, H, W)            feature maps at t and t+tau
