@@ -377,6 +377,27 @@ __global__ void pool_bins_kernel(const T* __restrict__ rois, int32_t* __restrict
 // =================================================================================
 // host launchers
 // =================================================================================
+// float32 fast path (pool_fast.cu)
+bool roipool_fast_supported(int R, int C, int H, int W, int k);
+int roipool_fast_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int roipool_fast_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+template <typename T>
+struct FastPath {
+    static bool fwd(const T*, const T*, T*, int, int, int, int, int, cudaStream_t, int*) { return false; }
+    static bool bwd(const T*, const T*, T*, int, int, int, int, int, cudaStream_t, int*) { return false; }
+};
+template <>
+struct FastPath<float> {
+    static bool fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t, int*) {
+        return false;  // the 1024-thread slab kernel below is faster than roipool_fast_fwd_kernel so far
+    }
+    static bool bwd(const float* go, const float* rois, float* gin, int R, int C, int H, int W, int k, cudaStream_t st,
+                    int* rc) {
+        if (!roipool_fast_supported(R, C, H, W, k)) return false;
+        *rc = roipool_fast_bwd_launch(go, rois, gin, R, C, H, W, k, st);
+        return true;
+    }
+};
 struct SlabPlan {
     int CB;       // channels per CTA
     int RCH;      // RoIs per edge-table chunk
@@ -420,6 +441,8 @@ int roipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int C, int H, 
                 C, H, W, k);
     D2T_REQUIRE(H < 32768 && W < 32768, "roipool_fwd: H, W must be < 32768");
     if (R == 0 || C == 0) return D2T_OK;
+    int frc = 0;
+    if (FastPath<T>::fwd(fm, rois, out, R, C, H, W, k, st, &frc)) return frc;
     SlabPlan p;
     int rc = plan_slab(R, C, H, W, k, sizeof(T), 0, &p);
     if (rc) return rc;
@@ -441,6 +464,8 @@ int roipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int C, int H, 
         D2T_CUDA_TRY(cudaMemsetAsync(gin, 0, (size_t)C * H * W * sizeof(T), st));
         return D2T_OK;
     }
+    int frc = 0;
+    if (FastPath<T>::bwd(go, rois, gin, R, C, H, W, k, st, &frc)) return frc;
     SlabPlan p;
     int rc = plan_slab(R, C, H, W, k, sizeof(T), (size_t)k * k * sizeof(T), &p);
     if (rc) return rc;
