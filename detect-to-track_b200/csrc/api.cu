@@ -61,7 +61,7 @@ template <typename T>
 int psroipool_bwd_launch(const T*, const T*, T*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 template <typename T>
 int pool_bins_launch(const T*, int32_t*, int, int, int, int, int, cudaStream_t);
-size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k);
+size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k, int elem);
 
 // tuned float32 correlation (corr_tile.cu)
 bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
@@ -163,8 +163,8 @@ int d2t_roipool_bwd_f64(const double* grad_out, const double* rois, double* grad
 
 // ---- PSROIPool -----------------------------------------------------------------------
 size_t d2t_psroipool_fwd_workspace_bytes(int, int, int, int, int, int) { return 0; }
-size_t d2t_psroipool_bwd_workspace_bytes(int R, int n_targets, int H, int W, int r_hw, int) {
-    return psroipool_bwd_ws_bytes(R, n_targets, H, W, r_hw);
+size_t d2t_psroipool_bwd_workspace_bytes(int R, int n_targets, int H, int W, int r_hw, int elem_size) {
+    return psroipool_bwd_ws_bytes(R, n_targets, H, W, r_hw, elem_size);
 }
 
 int d2t_psroipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int n_targets, int H, int W, int r_hw,

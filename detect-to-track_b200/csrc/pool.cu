@@ -243,31 +243,36 @@ psroipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __
 //   rowmask : [k][H][NW] uint32   bit r%32 of word r/32 set iff I0[r][i] <= y < I1[r][i]
 //   colmask : [k][W][NW] uint32
 struct PsBwdWs {
-    short *eI0, *eI1, *eJ0, *eJ1;
-    uint32_t *rowmask, *colmask;
-    int* entCount;   // [nCh]      how many (target, bin) pairs read channel ch
-    uint32_t* ent;   // [nCh][nT]  those pairs, ascending target: (t << 16) | (i*k + j)
-    int NW;
+    uint2* list;      // [k*k][H][R]  per (bin b, pixel row y): ascending RoIs whose row-bin covers y and whose
+                      //              column-bin is non-empty, packed {r, J0 | J1 << 16}
+    int* cnt;         // [k*k][H]
+    int* entCount;    // [nCh]        how many (target, bin) pairs read channel ch
+    uint32_t* ent;    // [nCh][nT]    those pairs, ascending target: (t << 16) | bin ; t = 0xFFFF => "all targets"
+    void* gs;         // [R][nT][k*k] grad_out / cell size (the value each covered pixel receives)
+    void* gs0;        // [R]          sum over targets of gs[r,t,0]  (reference map: every target's bin 0 reads channel 0)
 };
 
+// One launch builds everything the gather needs; the phases are independent of each other (each
+// recomputes the bin edges it needs), so no second launch / grid barrier is required.
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
-psroipool_bwd_prep_kernel(const T* __restrict__ rois, PsBwdWs ws, int R, int nT, int H, int W, int k, bool canonical) {
+psroipool_bwd_prep_kernel(const T* __restrict__ go, const T* __restrict__ rois, PsBwdWs ws, int R, int nT, int H, int W,
+                          int k, bool canonical) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
-    // inverse channel map: reference map (t+1)*(i*k+j) is many-to-one
     const int kk = k * k;
+    // (a) inverse channel map: the reference map (t+1)*(i*k+j) is many-to-one
     for (int ch = tid; ch < nT * kk; ch += nth) {
         int n = 0;
         uint32_t* e = ws.ent + (size_t)ch * nT;
         if (canonical) {
             const int t = ch / kk;
             e[n++] = ((uint32_t)t << 16) | (uint32_t)(ch - t * kk);
+        } else if (ch == 0) {
+            e[n++] = 0xFFFF0000u;  // bin 0 of EVERY target reads channel 0: one merged entry (gs0)
         } else {
             for (int t = 0; t < nT; ++t) {
-                if (ch == 0) {
-                    e[n++] = (uint32_t)t << 16;  // bin (0,0) of every target reads channel 0
-                } else if (ch % (t + 1) == 0) {
+                if (ch % (t + 1) == 0) {
                     const int sidx = ch / (t + 1);
                     if (sidx < kk) e[n++] = ((uint32_t)t << 16) | (uint32_t)sidx;
                 }
@@ -275,78 +280,110 @@ psroipool_bwd_prep_kernel(const T* __restrict__ rois, PsBwdWs ws, int R, int nT,
         }
         ws.entCount[ch] = n;
     }
-    // bin edges
-    for (int idx = tid; idx < R * k; idx += nth) {
-        const int r = idx / k, b = idx - r * k;
+    // (b) pre-scaled gradients: gs[r,t,b] = grad_out[r,t,b] / cell size   (ps_roipool_cuda.cu:134-137)
+    T* gs = static_cast<T*>(ws.gs);
+    for (int idx = tid; idx < R * nT * kk; idx += nth) {
+        const int b = idx % kk, r = idx / (nT * kk);
+        const int i = b / k, j = b - i * k;
         const T* roi = rois + (size_t)r * 4;
-        int e0, e1;
-        bin_edge<T, false>(roi[0], roi[2], b, k, H, e0, e1);
-        ws.eI0[idx] = (short)e0;
-        ws.eI1[idx] = (short)e1;
-        bin_edge<T, false>(roi[1], roi[3], b, k, W, e0, e1);
-        ws.eJ0[idx] = (short)e0;
-        ws.eJ1[idx] = (short)e1;
+        int i0, i1, j0, j1;
+        bin_edge<T, false>(roi[0], roi[2], i, k, H, i0, i1);
+        bin_edge<T, false>(roi[1], roi[3], j, k, W, j0, j1);
+        const int numel = (i1 - i0) * (j1 - j0);
+        T v = __ldg(go + idx);
+        if (numel > 0) v /= numel;
+        gs[idx] = v;
+    }
+    // (b') merged value for channel 0 of the reference map, targets summed in ascending order
+    T* gs0 = static_cast<T*>(ws.gs0);
+    for (int r = tid; r < R; r += nth) {
+        const T* roi = rois + (size_t)r * 4;
+        int i0, i1, j0, j1;
+        bin_edge<T, false>(roi[0], roi[2], 0, k, H, i0, i1);
+        bin_edge<T, false>(roi[1], roi[3], 0, k, W, j0, j1);
+        const int numel = (i1 - i0) * (j1 - j0);
+        T sum = 0;
+        for (int t = 0; t < nT; ++t) {
+            T v = __ldg(go + ((size_t)r * nT + t) * kk);
+            if (numel > 0) v /= numel;
+            sum += v;
+        }
+        gs0[r] = sum;
+    }
+    // (c) per (bin b, pixel row y): ascending list of the RoIs that can contribute, with their column range.
+    //     One warp per list; ballot compaction keeps the order deterministic.
+    const int lane = threadIdx.x & 31;
+    const int warpGlobal = tid >> 5, nWarps = nth >> 5;
+    for (int l = warpGlobal; l < kk * H; l += nWarps) {
+        const int b = l / H, y = l - b * H;
+        const int i = b / k, j = b - i * k;
+        uint2* list = ws.list + (size_t)l * R;
+        int n = 0;
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            const int r = r0 + lane;
+            bool in = false;
+            int j0 = 0, j1 = 0;
+            if (r < R) {
+                const T* roi = rois + (size_t)r * 4;
+                int e0, e1;
+                bin_edge<T, false>(roi[0], roi[2], i, k, H, e0, e1);
+                bin_edge<T, false>(roi[1], roi[3], j, k, W, j0, j1);
+                in = e0 <= y && y < e1 && j1 > j0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) list[n + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)r, (unsigned)j0 | ((unsigned)j1 << 16));
+            n += __popc(bal);
+        }
+        if (lane == 0) ws.cnt[l] = n;
     }
 }
 
+// grid: (H * ceil(W/64), nChannels), 64 threads: a block is (part of) one pixel row of one channel, a thread
+// one pixel.  For every (target, bin) pair that reads this channel the block walks the ascending list of
+// RoIs that cover this row in that bin; a lane adds the RoI's pre-scaled gradient if its column lies in the
+// RoI's column range.  Control flow is uniform, the order of additions per pixel is fixed => deterministic,
+// no atomics; every pixel is written exactly once.
+constexpr int kPsRowThreads = 64;
 template <typename T>
-__global__ void __launch_bounds__(kPoolThreads)
-psroipool_bwd_mask_kernel(PsBwdWs ws, int R, int H, int W, int k) {
-    const int NW = ws.NW;
-    const int nRow = k * H * NW, nCol = k * W * NW;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nRow + nCol; idx += gridDim.x * blockDim.x) {
-        const bool isRow = idx < nRow;
-        const int q = isRow ? idx : idx - nRow;
-        const int n = isRow ? H : W;
-        const int w = q % NW;
-        const int y = (q / NW) % n;
-        const int b = q / (NW * n);
-        const short* e0 = isRow ? ws.eI0 : ws.eJ0;
-        const short* e1 = isRow ? ws.eI1 : ws.eJ1;
-        uint32_t m = 0;
-        const int rEnd = min(R, (w + 1) * 32);
-        for (int r = w * 32; r < rEnd; ++r)
-            if (e0[r * k + b] <= y && y < e1[r * k + b]) m |= 1u << (r & 31);
-        (isRow ? ws.rowmask : ws.colmask)[q] = m;
-    }
-}
-
-// grid: (ceil(H*W / kPoolThreads), nChannels)
-template <typename T>
-__global__ void __launch_bounds__(kPoolThreads)
-psroipool_bwd_kernel(const T* __restrict__ go, PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int W, int k) {
+__global__ void __launch_bounds__(kPsRowThreads)
+psroipool_bwd_kernel(PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int W, int k, int colTiles) {
     const int ch = blockIdx.y;
     const int kk = k * k;
-    const int HW = H * W;
-    const int px = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = px < HW;
-    const int y = active ? px / W : 0;
-    const int x = active ? px - y * W : 0;
-    const int NW = ws.NW;
-
-    T acc = 0;
+    const int y = blockIdx.x / colTiles;
+    const int x = (blockIdx.x - y * colTiles) * kPsRowThreads + threadIdx.x;
+    const bool active = x < W;
+    T* dst = gin + (size_t)ch * H * W + (size_t)y * W + x;
     const int nEnt = ws.entCount[ch];
+    if (nEnt == 0) {
+        if (active) *dst = 0;
+        return;
+    }
     const uint32_t* ent = ws.ent + (size_t)ch * nT;
-    for (int en = 0; en < nEnt && active; ++en) {
+    T acc = 0;
+    for (int en = 0; en < nEnt; ++en) {
         const uint32_t pk = __ldg(ent + en);
-        const int t = pk >> 16, s = pk & 0xffff;
-        const int i = s / k, j = s - i * k;
-        const uint32_t* rm = ws.rowmask + ((size_t)i * H + y) * NW;
-        const uint32_t* cm = ws.colmask + ((size_t)j * W + x) * NW;
-        for (int w = 0; w < NW; ++w) {
-            uint32_t m = __ldg(rm + w) & __ldg(cm + w);
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const int r = w * 32 + bit;
-                const int numel = (ws.eI1[r * k + i] - ws.eI0[r * k + i]) * (ws.eJ1[r * k + j] - ws.eJ0[r * k + j]);
-                T add = __ldg(go + ((size_t)r * nT + t) * kk + s);
-                add /= numel;  // numel > 0 here (the pixel is inside the cell)
-                acc += add;
-            }
+        const int t = pk >> 16, b = pk & 0xffff;
+        const int l = b * H + y;
+        const int cnt = __ldg(ws.cnt + l);
+        const uint2* list = ws.list + (size_t)l * R;
+        const T* g;
+        size_t gstride;
+        if (t == 0xFFFF) {
+            g = static_cast<const T*>(ws.gs0);
+            gstride = 1;
+        } else {
+            g = static_cast<const T*>(ws.gs) + (size_t)t * kk + b;
+            gstride = (size_t)nT * kk;
+        }
+#pragma unroll 4
+        for (int n = 0; n < cnt; ++n) {
+            const uint2 e = __ldg(list + n);
+            const int j0 = e.y & 0xffff, j1 = e.y >> 16;
+            const T v = __ldg(g + e.x * gstride);
+            if (x >= j0 && x < j1) acc += v;
         }
     }
-    if (active) gin[(size_t)ch * HW + px] = acc;
+    if (active) *dst = acc;
 }
 
 // =================================================================================
@@ -499,35 +536,32 @@ int psroipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int nT, int 
     return D2T_OK;
 }
 
-static size_t psroipool_bwd_ws_layout(int R, int nT, int H, int W, int k, void* base, PsBwdWs* ws) {
-    const int NW = ceil_div(R > 0 ? R : 1, 32);
+static size_t psroipool_bwd_ws_layout(int R, int nT, int H, int W, int k, size_t elem, void* base, PsBwdWs* ws) {
+    const size_t Rn = R > 0 ? R : 1;
+    const size_t kk = (size_t)k * k;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
         off = align_up(off + bytes, 256);
         return o;
     };
-    const size_t e = (size_t)(R > 0 ? R : 1) * k * sizeof(short);
-    size_t o0 = take(e), o1 = take(e), o2 = take(e), o3 = take(e);
-    size_t orow = take((size_t)k * H * NW * 4), ocol = take((size_t)k * W * NW * 4);
-    size_t ocnt = take((size_t)nT * k * k * sizeof(int)), oent = take((size_t)nT * k * k * nT * sizeof(uint32_t));
+    size_t olist = take(kk * H * Rn * sizeof(uint2)), ocnt2 = take(kk * H * sizeof(int));
+    size_t ocnt = take((size_t)nT * kk * sizeof(int)), oent = take((size_t)nT * kk * nT * sizeof(uint32_t));
+    size_t ogs = take(Rn * nT * kk * elem), ogs0 = take(Rn * elem);
     if (ws) {
         char* b = static_cast<char*>(base);
-        ws->eI0 = (short*)(b + o0);
-        ws->eI1 = (short*)(b + o1);
-        ws->eJ0 = (short*)(b + o2);
-        ws->eJ1 = (short*)(b + o3);
-        ws->rowmask = (uint32_t*)(b + orow);
-        ws->colmask = (uint32_t*)(b + ocol);
+        ws->list = (uint2*)(b + olist);
+        ws->cnt = (int*)(b + ocnt2);
         ws->entCount = (int*)(b + ocnt);
         ws->ent = (uint32_t*)(b + oent);
-        ws->NW = NW;
+        ws->gs = b + ogs;
+        ws->gs0 = b + ogs0;
     }
     return off;
 }
 
-size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k) {
-    return psroipool_bwd_ws_layout(R, nT, H, W, k, nullptr, nullptr);
+size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k, int elem) {
+    return psroipool_bwd_ws_layout(R, nT, H, W, k, (size_t)elem, nullptr, nullptr);
 }
 
 template <typename T>
@@ -538,28 +572,32 @@ int psroipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int nT, int 
     D2T_REQUIRE(H < 32768 && W < 32768, "psroipool_bwd: H, W must be < 32768");
     const int nCh = nT * k * k;
     D2T_REQUIRE(nCh <= 65535, "psroipool_bwd: n_targets*r_hw^2 must be <= 65535");
+    D2T_REQUIRE((long long)R * nCh < (1ll << 31), "psroipool_bwd: grad_out too large");
+    D2T_REQUIRE(R <= 65535, "psroipool_bwd: at most 65535 RoIs per call");
     if (R == 0) {
         D2T_CUDA_TRY(cudaMemsetAsync(gin, 0, (size_t)nCh * H * W * sizeof(T), st));
         return D2T_OK;
     }
-    const size_t need = psroipool_bwd_ws_bytes(R, nT, H, W, k);
+    const size_t need = psroipool_bwd_ws_bytes(R, nT, H, W, k, (int)sizeof(T));
     if (wsp == nullptr || ws_bytes < need) {
         set_error("psroipool_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
         return D2T_ERR_WORKSPACE;
     }
     PsBwdWs ws;
-    psroipool_bwd_ws_layout(R, nT, H, W, k, wsp, &ws);
-    const int prepItems = R * k > nCh ? R * k : nCh;
-    psroipool_bwd_prep_kernel<T><<<ceil_div(prepItems, kPoolThreads), kPoolThreads, 0, st>>>(
-        rois, ws, R, nT, H, W, k, (flags & D2T_PS_CANONICAL_MAP) != 0);
+    psroipool_bwd_ws_layout(R, nT, H, W, k, sizeof(T), wsp, &ws);
+    DeviceInfo di;
+    int drc = device_info(&di);
+    if (drc) return drc;
+    const int prepItems = R * nCh;
+    int prepGrid = ceil_div(prepItems, kPoolThreads);
+    if (prepGrid > di.sm_count * 8) prepGrid = di.sm_count * 8;
+    psroipool_bwd_prep_kernel<T><<<prepGrid, kPoolThreads, 0, st>>>(go, rois, ws, R, nT, H, W, k,
+                                                                     (flags & D2T_PS_CANONICAL_MAP) != 0);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
-    const int nMask = k * (H + W) * ws.NW;
-    psroipool_bwd_mask_kernel<T><<<ceil_div(nMask, kPoolThreads), kPoolThreads, 0, st>>>(ws, R, H, W, k);
-    D2T_CUDA_TRY(cudaGetLastError());
-    note_launch();
-    dim3 grid(ceil_div(H * W, kPoolThreads), nCh);
-    psroipool_bwd_kernel<T><<<grid, kPoolThreads, 0, st>>>(go, ws, gin, R, nT, H, W, k);
+    const int colTiles = ceil_div(W, kPsRowThreads);
+    dim3 grid(H * colTiles, nCh);
+    psroipool_bwd_kernel<T><<<grid, kPsRowThreads, 0, st>>>(ws, gin, R, nT, H, W, k, colTiles);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;
