@@ -63,6 +63,8 @@ template <typename T>
 int pool_bins_launch(const T*, int32_t*, int, int, int, int, int, cudaStream_t);
 size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k, int elem);
 
+bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
+int corr_umma_fwd_launch(const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 // tuned float32 correlation (corr_tile.cu)
 bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
 bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride);
@@ -138,6 +140,15 @@ int d2t_corr_bwd_f64(const double* grad_out, const double* fm0, const double* fm
     D2T_REQUIRE((long long)B * C * H * W == 0 || (grad_fm0 && grad_fm1), "d2t_corr_bwd_f64: null output pointer");
     return corr_bwd_generic_launch<double>(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, stride,
                                            (cudaStream_t)stream);
+}
+
+// tensor-core (tcgen05, 3xTF32) forward, d_max = 8, stride 1 only; experimental, looser tolerance
+int d2t_corr_fwd_f32_tc(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
+                        void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, "d2t_corr_fwd_f32_tc");
+    if (rc) return rc;
+    D2T_REQUIRE(corr_umma_supported(B, C, H, W, d_max, stride), "d2t_corr_fwd_f32_tc: needs d_max = 8, stride = 1");
+    return corr_umma_fwd_launch(fm0, fm1, out, B, C, H, W, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // ---- ROIPool -------------------------------------------------------------------------

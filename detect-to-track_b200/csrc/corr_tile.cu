@@ -24,32 +24,12 @@
 //             (B,H,W,2d+1,2d+1) layout, dead entries (row/column 2d, out-of-image
 //             displacements: SURVEY.md F4) written as exact zeros, and streamed out as
 //             long coalesced runs.  No memset of `out`.
-#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "corr_common.cuh"
 
 namespace d2t {
-
-constexpr int kCorrThreads = 256;
-
-template <int D>
-struct FwdCfg {
-    static constexpr int TD = 2 * D;              // live column / row displacements
-    static constexpr int K1 = 2 * D + 1;          // output map side
-    static constexpr int KK = K1 * K1;            // output map size
-    static constexpr int QROWS = 128 / TD;        // query rows per tile
-    static constexpr int QCOLS = 16;              // query cols per tile
-    static constexpr int KROWS = QROWS + TD - 1;  // key rows per tile
-    static constexpr int KCOLS = QCOLS + TD - 1;  // key cols per tile
-    static constexpr int KP = (D == 8) ? 36 : 28; // key row pitch (floats): >= 16+TD, = 4 mod 8
-    static constexpr int QP = 20;                 // query row pitch (floats): 16 used, = 4 mod 8
-    static constexpr int KPATCH = KROWS * KP + 8;  // key rows >= 16 are shifted by 8 floats (bank-group skew)
-    static constexpr int CH_FLOATS = QROWS * QP + KPATCH;  // staged floats per channel
-    static constexpr int KV = (8 + TD) / 4;       // LDS.128 per thread per channel for keys
-    static constexpr int KPASS = (KROWS + 7) / 8; // staging passes over key rows (8 rows x 32 lanes each)
-    static constexpr int QPASS = (QROWS * QCOLS + kCorrThreads - 1) / kCorrThreads;
-    static constexpr int TILE_FLOATS = QROWS * QCOLS * KK;     // one tile of output / one partial slot
-    static_assert(D == 4 || D == 8, "tuned kernel covers d_max 4 and 8");
-    static_assert(KP >= 16 + TD && KP % 4 == 0, "key pitch");
-};
 
 // shared-memory offset of key-patch row r (rows >= 16 skewed by two 16-byte chunks so that rows r and
 // r+16, which one quarter-warp can touch together, fall in different bank groups)
@@ -74,13 +54,6 @@ __device__ __forceinline__ void cp_async_wait() {
 
 constexpr int kStages = 3;  // operand ring depth (cp.async groups in flight: kStages - 1)
 
-struct CorrPlan {
-    int B, C, H, W;
-    int tilesX, tilesY, T;  // tiles per image in x / y, total tiles
-    int NI;                 // channel chunks per tile
-    int G;                  // CTAs
-    int ipc;                // (tile, chunk) iterations per CTA
-};
 
 template <int D, int CK>
 __global__ void __launch_bounds__(kCorrThreads, 1)
@@ -483,24 +456,12 @@ corr_bwd_tile_kernel(const float* __restrict__ go, const float* __restrict__ xsr
 // ---- host side -------------------------------------------------------------------------------
 constexpr int kFwdCK = 8;
 
-template <int D>
-static int make_plan(int B, int C, int H, int W, int CK, CorrPlan* p) {
-    using Cfg = FwdCfg<D>;
-    DeviceInfo di;
-    int rc = device_info(&di);
-    if (rc) return rc;
-    p->B = B; p->C = C; p->H = H; p->W = W;
-    p->tilesX = ceil_div(W, Cfg::QCOLS);
-    p->tilesY = ceil_div(H, Cfg::QROWS);
-    p->T = B * p->tilesX * p->tilesY;
-    p->NI = ceil_div(C, CK);
-    const long long total = (long long)p->T * p->NI;
-    long long G = di.sm_count;
-    if (G > total) G = total;
-    p->G = (int)G;
-    p->ipc = (int)((total + G - 1) / G);
-    p->G = (int)((total + p->ipc - 1) / p->ipc);
-    return 0;
+int corr_fwd_finalize8_launch(const float* partial, float* out, const CorrPlan& p, cudaStream_t st) {
+    dim3 grid(p.T, FwdCfg<8>::QROWS);
+    corr_fwd_finalize_kernel<8><<<grid, 256, 0, st>>>(partial, out, p);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
 }
 
 bool corr_tile_supported(int B, int C, int H, int W, int d, int stride) {
@@ -514,7 +475,9 @@ template <int D>
 static size_t fwd_ws_bytes(int B, int C, int H, int W) {
     CorrPlan p;
     if (make_plan<D>(B, C, H, W, kFwdCK, &p)) return 0;
-    return (size_t)(p.G + p.T) * FwdCfg<D>::TILE_FLOATS * sizeof(float);
+    DeviceInfo di;
+    if (device_info(&di)) return 0;
+    return (size_t)(di.sm_count + p.T) * FwdCfg<D>::TILE_FLOATS * sizeof(float);  // enough for any stream-K split
 }
 
 size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d) {
@@ -555,8 +518,25 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     return D2T_OK;
 }
 
+// tensor-core forward (corr_umma.cu)
+bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
+int corr_umma_fwd_launch(const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
+
+// The tcgen05 kernel is opt-in (D2T_CORR_FWD=umma, or the d2t_corr_fwd_f32_tc entry point): at this round's
+// state it does not yet beat the FP32-pipe band kernel, so the band kernel stays the default.
+static bool use_umma_fwd() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("D2T_CORR_FWD");
+        cached = (e && strcmp(e, "umma") == 0) ? 1 : 0;
+    }
+    return cached == 1;
+}
+
 int corr_tile_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
+    if (d == 8 && use_umma_fwd() && corr_umma_supported(B, C, H, W, d, 1))
+        return corr_umma_fwd_launch(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);
     return d == 8 ? fwd_launch<8>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st)
                   : fwd_launch<4>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);
 }

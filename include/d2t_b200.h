@@ -83,6 +83,12 @@ D2T_API int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int
 D2T_API int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
                      int stride, void* ws, size_t ws_bytes, void* stream);
 
+/* Experimental tensor-core forward (tcgen05 + TMEM, 3xTF32 split; d_max = 8, stride = 1 only).  Same contract and
+ * workspace as d2t_corr_fwd_f32; values agree with it to |err| <= 4e-6 * sum_c |fm0*fm1| (looser than the FP32-pipe
+ * kernel).  No counterpart in the reference; not used by the Python mirror unless D2T_CORR_FWD=umma. */
+D2T_API int d2t_corr_fwd_f32_tc(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max,
+                        int stride, void* ws, size_t ws_bytes, void* stream);
+
 /* grad_out : (B, H, W, 2d+1, 2d+1);  grad_fm0, grad_fm1 : (B, C, H, W) */
 D2T_API size_t d2t_corr_bwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size);
 D2T_API int d2t_corr_bwd_f32(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0,

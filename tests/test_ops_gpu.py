@@ -89,6 +89,29 @@ def test_pointwise_correlation_gradients(cuda, d_max, stride, input_b, input_c, 
     assert gradcheck(pc, (fm0, fm1))
 
 
+@pytest.mark.parametrize("B,C,H,W", [(1, 96, 38, 63), (3, 40, 20, 21), (1, 16, 70, 66), (2, 2048, 38, 63)])
+def test_corr_fwd_tensor_core_variant(cuda, B, C, H, W):
+    """experimental tcgen05 / 3xTF32 forward (d2t_corr_fwd_f32_tc): stated looser tolerance
+    |err| <= 1e-5 * sum_c |fm0*fm1| (measured 4e-6, tools/umma_test.cu), dead entries exactly zero."""
+    from detect_to_track_b200 import _lib
+    d = 8
+    g = torch.Generator(device="cpu").manual_seed(77)
+    fm0 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    fm1 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    lib = _lib.lib()
+    out = torch.empty((B, H, W, 17, 17), device=cuda)
+    n = lib.d2t_corr_fwd_workspace_bytes(B, C, H, W, d, 1, 4)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=cuda)
+    rc = lib.d2t_corr_fwd_f32_tc(fm0.data_ptr(), fm1.data_ptr(), out.data_ptr(), B, C, H, W, d, 1, ws.data_ptr(), n,
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    ref = pc_mod.pointwise_correlation_forward(fm0.double(), fm1.double(), d, 1)        # float64 generic kernel
+    mag = pc_mod.pointwise_correlation_forward(fm0.double().abs(), fm1.double().abs(), d, 1)
+    err = (out.double() - ref).abs()
+    assert bool((err <= 1e-5 * mag + 1e-30).all()), float((err / (mag + 1e-30)).max())
+    assert bool((out[ref == 0] == 0).all())
+
+
 def test_corr_backward_is_deterministic(cuda):
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 64, 38, 63, 8, seed=13, dtype=np.float32))
     a = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)

@@ -33,13 +33,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
     d |= (uint64_t)1 << 46;  // version = 1 (sm_100)
     return d;
 }
-__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int mn_major) {
     uint32_t d = 0;
     d |= 1u << 4;                     // c_format = F32
     d |= 2u << 7;                     // a_format = TF32
     d |= 2u << 10;                    // b_format = TF32
-    d |= 1u << 15;                    // a_major = MN
-    d |= 1u << 16;                    // b_major = MN
+    if (mn_major) d |= (1u << 15) | (1u << 16);  // a_major, b_major = MN
     d |= (uint32_t)(N >> 3) << 17;
     d |= (uint32_t)(M >> 4) << 24;
     return d;
@@ -56,7 +55,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // A: [128][8], B: [N][8] (row-major in global), D: [128][N].  split: 0 = plain tf32, 1 = 3xTF32
-__global__ void __launch_bounds__(128) umma_kernel(const float* Ag, const float* Bg, float* Dg, int N, int ksteps, int split) {
+__global__ void __launch_bounds__(128) umma_kernel(const float* Ag, const float* Bg, float* Dg, int N, int ksteps, int split, int mn_major) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* Ah = reinterpret_cast<float*>(smem);   // 128*8 floats
     float* Al = Ah + 128 * 8;
@@ -86,7 +85,7 @@ __global__ void __launch_bounds__(128) umma_kernel(const float* Ag, const float*
             const int m = e >> 3, k = e & 7;
             const float v = Ag[(size_t)ks * 128 * 8 + e];
             const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-            const int off = (m >> 2) * 32 + k * 4 + (m & 3);
+            const int off = mn_major ? (m >> 2) * 32 + k * 4 + (m & 3) : (m >> 3) * 64 + (k >> 2) * 32 + (m & 7) * 4 + (k & 3);
             Ah[off] = split ? hi : v;
             Al[off] = v - hi;
         }
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(128) umma_kernel(const float* Ag, const float*
             const int n = e >> 3, k = e & 7;
             const float v = Bg[(size_t)ks * N * 8 + e];
             const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-            const int off = (n >> 2) * 32 + k * 4 + (n & 3);
+            const int off = mn_major ? (n >> 2) * 32 + k * 4 + (n & 3) : (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
             Bh[off] = split ? hi : v;
             Bl[off] = v - hi;
         }
@@ -104,9 +103,10 @@ __global__ void __launch_bounds__(128) umma_kernel(const float* Ag, const float*
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int n0 = 0; n0 < N; n0 += 256) {
                 const int nn = (N - n0) < 256 ? (N - n0) : 256;
-                const uint32_t idesc = make_idesc_tf32(128, nn);
-                const uint64_t dAh = make_desc(smem_u32(Ah), 128, 128), dAl = make_desc(smem_u32(Al), 128, 128);
-                const uint64_t dBh = make_desc(smem_u32(Bh + n0 * 8), 128, 128), dBl = make_desc(smem_u32(Bl + n0 * 8), 128, 128);
+                const uint32_t idesc = make_idesc_tf32(128, nn, mn_major);
+                const uint32_t sbo = mn_major ? 128 : 256, lbo = 128;
+                const uint64_t dAh = make_desc(smem_u32(Ah), sbo, lbo), dAl = make_desc(smem_u32(Al), sbo, lbo);
+                const uint64_t dBh = make_desc(smem_u32(Bh + n0 * 8), sbo, lbo), dBl = make_desc(smem_u32(Bl + n0 * 8), sbo, lbo);
                 umma_tf32(tmem_base + n0, dAh, dBh, idesc, ks > 0);
                 if (split) {
                     umma_tf32(tmem_base + n0, dAh, dBl, idesc, 1);
@@ -142,11 +142,14 @@ __global__ void __launch_bounds__(128) umma_kernel(const float* Ag, const float*
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
-int main() {
+int main(int argc, char** argv) {
     const int M = 128;
+    const int ksteps_arg = argc > 1 ? atoi(argv[1]) : 1;
+    const int mn_major = argc > 2 ? atoi(argv[2]) : 1;
+    printf("mn_major=%d\n", mn_major);
     for (int N : {256, 96, 384}) {
         for (int split = 0; split <= 1; ++split) {
-            const int ksteps = 64;  // K = 512
+            const int ksteps = ksteps_arg;
             std::vector<float> A((size_t)ksteps * M * 8), B((size_t)ksteps * N * 8);
             srand(123 + N);
             for (auto& v : A) v = (float)rand() / RAND_MAX - 0.3f;
@@ -157,7 +160,7 @@ int main() {
             CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
             const size_t smem = (size_t)(2 * 128 * 8 + 2 * N * 8) * 4;
             CK(cudaFuncSetAttribute(umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            umma_kernel<<<1, 128, smem>>>(dA, dB, dD, N, ksteps, split);
+            umma_kernel<<<1, 128, smem>>>(dA, dB, dD, N, ksteps, split, mn_major);
             CK(cudaDeviceSynchronize());
             std::vector<float> D((size_t)M * N);
             CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
@@ -175,6 +178,11 @@ int main() {
                     if (err / mag > maxrel) maxrel = err / mag;
                     if (fabs(ref) > scale) scale = fabs(ref);
                 }
+            {
+                int nz = 0; for (float v : D) nz += (v != 0.f);
+                double r00 = 0; for (int ks = 0; ks < ksteps; ++ks) for (int k = 0; k < 8; ++k) r00 += (double)A[((size_t)ks * M + 0) * 8 + k] * B[((size_t)ks * N + 0) * 8 + k];
+                printf("  nonzero %d / %d; D[0][0..3] = %g %g %g %g (ref00 %g); D[1][0]=%g D[64][5]=%g\n", nz, M * N, D[0], D[1], D[2], D[3], r00, D[N], D[(size_t)64 * N + 5]);
+            }
             printf("N=%3d split=%d K=%d: max |err| = %.3e (max|ref| %.2f), max |err|/sum|a*b| = %.3e  %s\n", N, split, ksteps * 8, maxabs,
                    scale, maxrel, maxrel < (split ? 2e-6 : 2e-3) ? "OK" : "FAIL");
             cudaFree(dA); cudaFree(dB); cudaFree(dD);
