@@ -45,6 +45,7 @@ SIGNATURES = {
     "d2t_roipool_bwd_workspace_bytes": (_c_size_t, _WS6),
     "d2t_roipool_fwd_f32": (_c_int, _POOL),
     "d2t_roipool_fwd_f64": (_c_int, _POOL),
+    "d2t_roipool_fwd_f32_exact": (_c_int, _POOL),
     "d2t_roipool_bwd_f32": (_c_int, _POOL),
     "d2t_roipool_bwd_f64": (_c_int, _POOL),
     "d2t_psroipool_fwd_workspace_bytes": (_c_size_t, _WS6),

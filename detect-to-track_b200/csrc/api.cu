@@ -52,7 +52,7 @@ int corr_fwd_generic_launch(const T*, const T*, T*, int, int, int, int, int, int
 template <typename T>
 int corr_bwd_generic_launch(const T*, const T*, const T*, T*, T*, int, int, int, int, int, int, cudaStream_t);
 template <typename T>
-int roipool_fwd_launch(const T*, const T*, T*, int, int, int, int, int, cudaStream_t);
+int roipool_fwd_launch(const T*, const T*, T*, int, int, int, int, int, cudaStream_t, bool);
 template <typename T>
 int roipool_bwd_launch(const T*, const T*, T*, int, int, int, int, int, cudaStream_t);
 template <typename T>
@@ -157,11 +157,15 @@ size_t d2t_roipool_bwd_workspace_bytes(int, int, int, int, int, int) { return 0;
 
 int d2t_roipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int r_hw, void*,
                         size_t, void* stream) {
-    return roipool_fwd_launch<float>(fm, rois, out, R, C, H, W, r_hw, (cudaStream_t)stream);
+    return roipool_fwd_launch<float>(fm, rois, out, R, C, H, W, r_hw, (cudaStream_t)stream, false);
+}
+int d2t_roipool_fwd_f32_exact(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int r_hw, void*,
+                              size_t, void* stream) {
+    return roipool_fwd_launch<float>(fm, rois, out, R, C, H, W, r_hw, (cudaStream_t)stream, true);
 }
 int d2t_roipool_fwd_f64(const double* fm, const double* rois, double* out, int R, int C, int H, int W, int r_hw, void*,
                         size_t, void* stream) {
-    return roipool_fwd_launch<double>(fm, rois, out, R, C, H, W, r_hw, (cudaStream_t)stream);
+    return roipool_fwd_launch<double>(fm, rois, out, R, C, H, W, r_hw, (cudaStream_t)stream, false);
 }
 int d2t_roipool_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int R, int C, int H, int W, int r_hw,
                         void*, size_t, void* stream) {

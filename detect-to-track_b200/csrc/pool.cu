@@ -25,6 +25,8 @@
 //                 ANDs a row mask with a column mask and visits the surviving RoIs in
 //                 ascending order: deterministic, no atomics, every pixel written
 //                 exactly once; channels nobody reads are just zero-filled.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace d2t {
@@ -243,8 +245,9 @@ psroipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __
 //   rowmask : [k][H][NW] uint32   bit r%32 of word r/32 set iff I0[r][i] <= y < I1[r][i]
 //   colmask : [k][W][NW] uint32
 struct PsBwdWs {
+    short4* edges;    // [R][k]       {I0, I1, J0, J1} of row-bin b / column-bin b
     uint2* list;      // [k*k][H][R]  per (bin b, pixel row y): ascending RoIs whose row-bin covers y and whose
-                      //              column-bin is non-empty, packed {r, J0 | J1 << 16}
+                      //              column-bin is non-empty, packed {r | J0 << 16 | J1 << 24, r * nT * k*k}
     int* cnt;         // [k*k][H]
     int* entCount;    // [nCh]        how many (target, bin) pairs read channel ch
     uint32_t* ent;    // [nCh][nT]    those pairs, ascending target: (t << 16) | bin ; t = 0xFFFF => "all targets"
@@ -252,12 +255,24 @@ struct PsBwdWs {
     void* gs0;        // [R]          sum over targets of gs[r,t,0]  (reference map: every target's bin 0 reads channel 0)
 };
 
-// One launch builds everything the gather needs; the phases are independent of each other (each
-// recomputes the bin edges it needs), so no second launch / grid barrier is required.
+// launch 1 (tiny): bin edges of every RoI, computed once
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
-psroipool_bwd_prep_kernel(const T* __restrict__ go, const T* __restrict__ rois, PsBwdWs ws, int R, int nT, int H, int W,
-                          int k, bool canonical) {
+psroipool_bwd_edges_kernel(const T* __restrict__ rois, PsBwdWs ws, int R, int H, int W, int k) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < R * k; idx += gridDim.x * blockDim.x) {
+        const int r = idx / k, b = idx - r * k;
+        const T* roi = rois + (size_t)r * 4;
+        int i0, i1, j0, j1;
+        bin_edge<T, false>(roi[0], roi[2], b, k, H, i0, i1);
+        bin_edge<T, false>(roi[1], roi[3], b, k, W, j0, j1);
+        ws.edges[idx] = make_short4((short)i0, (short)i1, (short)j0, (short)j1);
+    }
+}
+
+// launch 2: inverse channel map, pre-scaled gradients, per-(bin, row) RoI lists
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+psroipool_bwd_prep_kernel(const T* __restrict__ go, PsBwdWs ws, int R, int nT, int H, int W, int k, bool canonical) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
     const int kk = k * k;
@@ -285,30 +300,31 @@ psroipool_bwd_prep_kernel(const T* __restrict__ go, const T* __restrict__ rois, 
     for (int idx = tid; idx < R * nT * kk; idx += nth) {
         const int b = idx % kk, r = idx / (nT * kk);
         const int i = b / k, j = b - i * k;
-        const T* roi = rois + (size_t)r * 4;
-        int i0, i1, j0, j1;
-        bin_edge<T, false>(roi[0], roi[2], i, k, H, i0, i1);
-        bin_edge<T, false>(roi[1], roi[3], j, k, W, j0, j1);
-        const int numel = (i1 - i0) * (j1 - j0);
+        const short4 ei = ws.edges[r * k + i], ej = ws.edges[r * k + j];
+        const int numel = (ei.y - ei.x) * (ej.w - ej.z);
         T v = __ldg(go + idx);
         if (numel > 0) v /= numel;
         gs[idx] = v;
     }
-    // (b') merged value for channel 0 of the reference map, targets summed in ascending order
+    // (b') merged value for channel 0 of the reference map: one warp per RoI, lanes over targets, fixed-order
+    //      shuffle tree (deterministic)
     T* gs0 = static_cast<T*>(ws.gs0);
-    for (int r = tid; r < R; r += nth) {
-        const T* roi = rois + (size_t)r * 4;
-        int i0, i1, j0, j1;
-        bin_edge<T, false>(roi[0], roi[2], 0, k, H, i0, i1);
-        bin_edge<T, false>(roi[1], roi[3], 0, k, W, j0, j1);
-        const int numel = (i1 - i0) * (j1 - j0);
-        T sum = 0;
-        for (int t = 0; t < nT; ++t) {
-            T v = __ldg(go + ((size_t)r * nT + t) * kk);
-            if (numel > 0) v /= numel;
-            sum += v;
+    {
+        const int lane0 = threadIdx.x & 31;
+        const int wg = tid >> 5, nw = nth >> 5;
+        for (int r = wg; r < R; r += nw) {
+            const short4 e = ws.edges[r * k];
+            const int numel = (e.y - e.x) * (e.w - e.z);
+            T sum = 0;
+            for (int t = lane0; t < nT; t += 32) {
+                T v = __ldg(go + ((size_t)r * nT + t) * kk);
+                if (numel > 0) v /= numel;
+                sum += v;
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+            if (lane0 == 0) gs0[r] = sum;
         }
-        gs0[r] = sum;
     }
     // (c) per (bin b, pixel row y): ascending list of the RoIs that can contribute, with their column range.
     //     One warp per list; ballot compaction keeps the order deterministic.
@@ -324,66 +340,72 @@ psroipool_bwd_prep_kernel(const T* __restrict__ go, const T* __restrict__ rois, 
             bool in = false;
             int j0 = 0, j1 = 0;
             if (r < R) {
-                const T* roi = rois + (size_t)r * 4;
-                int e0, e1;
-                bin_edge<T, false>(roi[0], roi[2], i, k, H, e0, e1);
-                bin_edge<T, false>(roi[1], roi[3], j, k, W, j0, j1);
-                in = e0 <= y && y < e1 && j1 > j0;
+                const short4 ei = ws.edges[r * k + i], ej = ws.edges[r * k + j];
+                j0 = ej.z; j1 = ej.w;
+                in = ei.x <= y && y < ei.y && j1 > j0;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, in);
-            if (in) list[n + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)r, (unsigned)j0 | ((unsigned)j1 << 16));
+            if (in)
+                list[n + __popc(bal & ((1u << lane) - 1))] =
+                    make_uint2((unsigned)r | ((unsigned)j0 << 16) | ((unsigned)j1 << 24), (unsigned)(r * nT * kk));
             n += __popc(bal);
         }
         if (lane == 0) ws.cnt[l] = n;
     }
 }
 
-// grid: (H * ceil(W/64), nChannels), 64 threads: a block is (part of) one pixel row of one channel, a thread
-// one pixel.  For every (target, bin) pair that reads this channel the block walks the ascending list of
-// RoIs that cover this row in that bin; a lane adds the RoI's pre-scaled gradient if its column lies in the
-// RoI's column range.  Control flow is uniform, the order of additions per pixel is fixed => deterministic,
-// no atomics; every pixel is written exactly once.
-constexpr int kPsRowThreads = 64;
+// grid: (H * ceil(W/64), nChannels), ONE warp per block: (part of) one pixel row of one channel, a lane owns the
+// pixels x and x + 32.  For every (target, bin) pair that reads this channel the warp walks the ascending list of
+// RoIs that cover this row in that bin; a lane adds the RoI's pre-scaled gradient if its column lies in the RoI's
+// column range.  Control flow is uniform, the order of additions per pixel is fixed => deterministic, no atomics;
+// every pixel is written exactly once.
+constexpr int kPsRowSpan = 64;
 template <typename T>
-__global__ void __launch_bounds__(kPsRowThreads)
+__global__ void __launch_bounds__(32)
 psroipool_bwd_kernel(PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int W, int k, int colTiles) {
     const int ch = blockIdx.y;
     const int kk = k * k;
     const int y = blockIdx.x / colTiles;
-    const int x = (blockIdx.x - y * colTiles) * kPsRowThreads + threadIdx.x;
-    const bool active = x < W;
-    T* dst = gin + (size_t)ch * H * W + (size_t)y * W + x;
+    const int xa = (blockIdx.x - y * colTiles) * kPsRowSpan + threadIdx.x, xb = xa + 32;
+    T* dst = gin + (size_t)ch * H * W + (size_t)y * W;
     const int nEnt = ws.entCount[ch];
     if (nEnt == 0) {
-        if (active) *dst = 0;
+        if (xa < W) dst[xa] = 0;
+        if (xb < W) dst[xb] = 0;
         return;
     }
     const uint32_t* ent = ws.ent + (size_t)ch * nT;
-    T acc = 0;
+    T acca = 0, accb = 0;
     for (int en = 0; en < nEnt; ++en) {
         const uint32_t pk = __ldg(ent + en);
         const int t = pk >> 16, b = pk & 0xffff;
         const int l = b * H + y;
         const int cnt = __ldg(ws.cnt + l);
         const uint2* list = ws.list + (size_t)l * R;
-        const T* g;
-        size_t gstride;
         if (t == 0xFFFF) {
-            g = static_cast<const T*>(ws.gs0);
-            gstride = 1;
-        } else {
-            g = static_cast<const T*>(ws.gs) + (size_t)t * kk + b;
-            gstride = (size_t)nT * kk;
-        }
+            const T* g = static_cast<const T*>(ws.gs0);
 #pragma unroll 4
-        for (int n = 0; n < cnt; ++n) {
-            const uint2 e = __ldg(list + n);
-            const int j0 = e.y & 0xffff, j1 = e.y >> 16;
-            const T v = __ldg(g + e.x * gstride);
-            if (x >= j0 && x < j1) acc += v;
+            for (int n = 0; n < cnt; ++n) {
+                const uint2 e = __ldg(list + n);
+                const int j0 = (e.x >> 16) & 0xff, j1 = e.x >> 24;
+                const T v = __ldg(g + (e.x & 0xffff));
+                if (xa >= j0 && xa < j1) acca += v;
+                if (xb >= j0 && xb < j1) accb += v;
+            }
+        } else {
+            const T* g = static_cast<const T*>(ws.gs) + (size_t)t * kk + b;
+#pragma unroll 4
+            for (int n = 0; n < cnt; ++n) {
+                const uint2 e = __ldg(list + n);
+                const int j0 = (e.x >> 16) & 0xff, j1 = e.x >> 24;
+                const T v = __ldg(g + e.y);
+                if (xa >= j0 && xa < j1) acca += v;
+                if (xb >= j0 && xb < j1) accb += v;
+            }
         }
     }
-    if (active) *dst = acc;
+    if (xa < W) dst[xa] = acca;
+    if (xb < W) dst[xb] = accb;
 }
 
 // =================================================================================
@@ -418,6 +440,8 @@ __global__ void pool_bins_kernel(const T* __restrict__ rois, int32_t* __restrict
 bool roipool_fast_supported(int R, int C, int H, int W, int k);
 int roipool_fast_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int roipool_fast_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+bool roipool_prefix_supported(int R, int C, int H, int W, int k);
+int roipool_prefix_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 template <typename T>
 struct FastPath {
     static bool fwd(const T*, const T*, T*, int, int, int, int, int, cudaStream_t, int*) { return false; }
@@ -425,8 +449,18 @@ struct FastPath {
 };
 template <>
 struct FastPath<float> {
-    static bool fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t, int*) {
-        return false;  // the 1024-thread slab kernel below is faster than roipool_fast_fwd_kernel so far
+    static bool fwd(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int k, cudaStream_t st,
+                    int* rc) {
+        // default: row-prefix kernel (rounding-level differences from the reference's summation order);
+        // D2T_ROIPOOL_EXACT=1 keeps the bit-identical slab kernel below
+        static int exact = -1;
+        if (exact < 0) {
+            const char* e = getenv("D2T_ROIPOOL_EXACT");
+            exact = (e && e[0] == '1') ? 1 : 0;
+        }
+        if (exact || !roipool_prefix_supported(R, C, H, W, k)) return false;
+        *rc = roipool_prefix_fwd_launch(fm, rois, out, R, C, H, W, k, st);
+        return true;
     }
     static bool bwd(const float* go, const float* rois, float* gin, int R, int C, int H, int W, int k, cudaStream_t st,
                     int* rc) {
@@ -473,13 +507,14 @@ static int plan_slab(int R, int C, int H, int W, int k, size_t elem, size_t per_
 }
 
 template <typename T>
-int roipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int C, int H, int W, int k, cudaStream_t st) {
+int roipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int C, int H, int W, int k, cudaStream_t st,
+                       bool force_exact) {
     D2T_REQUIRE(R >= 0 && C >= 0 && H > 0 && W > 0 && k > 0 && k <= kMaxK, "roipool_fwd: bad shape R=%d C=%d H=%d W=%d r_hw=%d", R,
                 C, H, W, k);
     D2T_REQUIRE(H < 32768 && W < 32768, "roipool_fwd: H, W must be < 32768");
     if (R == 0 || C == 0) return D2T_OK;
     int frc = 0;
-    if (FastPath<T>::fwd(fm, rois, out, R, C, H, W, k, st, &frc)) return frc;
+    if (!force_exact && FastPath<T>::fwd(fm, rois, out, R, C, H, W, k, st, &frc)) return frc;
     SlabPlan p;
     int rc = plan_slab(R, C, H, W, k, sizeof(T), 0, &p);
     if (rc) return rc;
@@ -545,11 +580,13 @@ static size_t psroipool_bwd_ws_layout(int R, int nT, int H, int W, int k, size_t
         off = align_up(off + bytes, 256);
         return o;
     };
+    size_t oedge = take(Rn * k * sizeof(short4));
     size_t olist = take(kk * H * Rn * sizeof(uint2)), ocnt2 = take(kk * H * sizeof(int));
     size_t ocnt = take((size_t)nT * kk * sizeof(int)), oent = take((size_t)nT * kk * nT * sizeof(uint32_t));
     size_t ogs = take(Rn * nT * kk * elem), ogs0 = take(Rn * elem);
     if (ws) {
         char* b = static_cast<char*>(base);
+        ws->edges = (short4*)(b + oedge);
         ws->list = (uint2*)(b + olist);
         ws->cnt = (int*)(b + ocnt2);
         ws->entCount = (int*)(b + ocnt);
@@ -588,16 +625,20 @@ int psroipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int nT, int 
     DeviceInfo di;
     int drc = device_info(&di);
     if (drc) return drc;
+    D2T_REQUIRE(W <= 255, "psroipool_bwd: W must be <= 255");
+    psroipool_bwd_edges_kernel<T><<<ceil_div(R * k, kPoolThreads), kPoolThreads, 0, st>>>(rois, ws, R, H, W, k);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
     const int prepItems = R * nCh;
     int prepGrid = ceil_div(prepItems, kPoolThreads);
     if (prepGrid > di.sm_count * 8) prepGrid = di.sm_count * 8;
-    psroipool_bwd_prep_kernel<T><<<prepGrid, kPoolThreads, 0, st>>>(go, rois, ws, R, nT, H, W, k,
+    psroipool_bwd_prep_kernel<T><<<prepGrid, kPoolThreads, 0, st>>>(go, ws, R, nT, H, W, k,
                                                                      (flags & D2T_PS_CANONICAL_MAP) != 0);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
-    const int colTiles = ceil_div(W, kPsRowThreads);
+    const int colTiles = ceil_div(W, kPsRowSpan);
     dim3 grid(H * colTiles, nCh);
-    psroipool_bwd_kernel<T><<<grid, kPsRowThreads, 0, st>>>(ws, gin, R, nT, H, W, k, colTiles);
+    psroipool_bwd_kernel<T><<<grid, 32, 0, st>>>(ws, gin, R, nT, H, W, k, colTiles);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;
@@ -614,8 +655,8 @@ int pool_bins_launch(const T* rois, int32_t* edges, int R, int H, int W, int k, 
 }
 
 // explicit instantiations used by api.cu
-template int roipool_fwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
-template int roipool_fwd_launch<double>(const double*, const double*, double*, int, int, int, int, int, cudaStream_t);
+template int roipool_fwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, cudaStream_t, bool);
+template int roipool_fwd_launch<double>(const double*, const double*, double*, int, int, int, int, int, cudaStream_t, bool);
 template int roipool_bwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 template int roipool_bwd_launch<double>(const double*, const double*, double*, int, int, int, int, int, cudaStream_t);
 template int psroipool_fwd_launch<float>(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);

@@ -25,8 +25,11 @@ def _check_rois(FM_dtype, FM_device, rois: Tensor) -> None:
         raise RuntimeError("FM and rois must be on the same device")
 
 
-def roipool_forward(FM: Tensor, rois: Tensor, r_hw: int) -> Tensor:
-    """replaces `_ext.roipool_forward` (roipool.cpp:22-31)."""
+def roipool_forward(FM: Tensor, rois: Tensor, r_hw: int, exact: bool = False) -> Tensor:
+    """replaces `_ext.roipool_forward` (roipool.cpp:22-31).
+
+    exact=True (float32 only) keeps the reference's left-to-right summation order and is bit-identical to
+    its kernel; the default sums bins through per-row prefix sums (rounding-level differences, much faster)."""
     _lib.check_input(FM, "FM")
     if FM.dim() != 3:
         raise RuntimeError(f"FM must be (C, H, W); got {tuple(FM.shape)}")
@@ -37,7 +40,8 @@ def roipool_forward(FM: Tensor, rois: Tensor, r_hw: int) -> Tensor:
     lib = _lib.lib()
     with torch.cuda.device(FM.device):
         out = torch.empty((R, C, r_hw, r_hw), dtype=FM.dtype, device=FM.device)
-        rc = getattr(lib, f"d2t_roipool_fwd_{sfx}")(
+        name = "d2t_roipool_fwd_f32_exact" if (exact and sfx == "f32") else f"d2t_roipool_fwd_{sfx}"
+        rc = getattr(lib, name)(
             FM.data_ptr(), rois.data_ptr(), out.data_ptr(), R, C, H, W, r_hw, None, 0, _lib.stream_ptr(FM.device))
         _lib.check(rc, "roipool_forward")
     return out

@@ -108,6 +108,12 @@ D2T_API int d2t_roipool_fwd_f32(const float* fm, const float* rois, float* out, 
 D2T_API int d2t_roipool_fwd_f64(const double* fm, const double* rois, double* out, int R, int C, int H, int W,
                         int r_hw, void* ws, size_t ws_bytes, void* stream);
 
+/* d2t_roipool_fwd_f32 sums each bin through per-row prefix sums (rounding-level differences from the reference's
+ * left-to-right order, |err| <~ 1e-6 * row magnitude).  This variant keeps the reference's summation order and is
+ * bit-identical to roipool_cuda.cu:56-61 (several times slower). */
+D2T_API int d2t_roipool_fwd_f32_exact(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int r_hw,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* grad_out : (R, C, r_hw, r_hw);  grad_fm : (C, H, W) */
 D2T_API size_t d2t_roipool_bwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int elem_size);
 D2T_API int d2t_roipool_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int R, int C, int H, int W,
