@@ -442,6 +442,10 @@ int roipool_fast_fwd_launch(const float*, const float*, float*, int, int, int, i
 int roipool_fast_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 bool roipool_prefix_supported(int R, int C, int H, int W, int k);
 int roipool_prefix_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+// float32 [pixel][16 channel] kernels (pool_vec.cu)
+bool roipool_vec_supported(int R, int C, int H, int W, int k);
+int roipool_vec_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int roipool_vec_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 template <typename T>
 struct FastPath {
     static bool fwd(const T*, const T*, T*, int, int, int, int, int, cudaStream_t, int*) { return false; }
@@ -458,12 +462,21 @@ struct FastPath<float> {
             const char* e = getenv("D2T_ROIPOOL_EXACT");
             exact = (e && e[0] == '1') ? 1 : 0;
         }
-        if (exact || !roipool_prefix_supported(R, C, H, W, k)) return false;
+        if (exact) return false;
+        if (roipool_vec_supported(R, C, H, W, k)) {
+            *rc = roipool_vec_fwd_launch(fm, rois, out, R, C, H, W, k, st);
+            return true;
+        }
+        if (!roipool_prefix_supported(R, C, H, W, k)) return false;
         *rc = roipool_prefix_fwd_launch(fm, rois, out, R, C, H, W, k, st);
         return true;
     }
     static bool bwd(const float* go, const float* rois, float* gin, int R, int C, int H, int W, int k, cudaStream_t st,
                     int* rc) {
+        if (roipool_vec_supported(R, C, H, W, k)) {
+            *rc = roipool_vec_bwd_launch(go, rois, gin, R, C, H, W, k, st);
+            return true;
+        }
         if (!roipool_fast_supported(R, C, H, W, k)) return false;
         *rc = roipool_fast_bwd_launch(go, rois, gin, R, C, H, W, k, st);
         return true;

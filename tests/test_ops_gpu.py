@@ -179,6 +179,22 @@ def test_roipool_vs_oracle(cuda, C, H, W, k, dtype):
     close(gin, oracle.roipool_bwd(go, rois, H, W), dtype)
 
 
+@pytest.mark.parametrize("C,H,W,R", [(21, 12, 9, 700), (3, 38, 63, 5), (16, 40, 70, 33), (53, 7, 200, 64)])
+def test_roipool_vec_kernels_shapes(cuda, C, H, W, R):
+    """float32, r_hw = 7 runs the [pixel][16 channel] kernels (pool_vec.cu): channel counts that are not a multiple
+    of 4, more RoIs than one edge-table chunk (512), maps narrower than a bin row, wide maps."""
+    k = 7
+    rois = _roipool_rois(H, W, np.float32, R=R)
+    fm, go = cases.pool_inputs(C, H, W, (rois.shape[0], C, k, k), 34, np.float32)
+    want = oracle.roipool_fwd(fm, rois, k)
+    out = rp_mod.roipool_forward(dev(fm, cuda), dev(rois, cuda), k)
+    close(out, want, np.float32, scale=float(np.nanmax(np.abs(want))), equal_nan=True)
+    assert np.array_equal(np.isnan(out.cpu().numpy()), np.isnan(want))
+    gin = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
+    close(gin, oracle.roipool_bwd(go, rois, H, W), np.float32)
+    assert torch.equal(gin, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
+
+
 def test_roipool_vs_reference_kernels(cuda):
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
