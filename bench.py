@@ -200,11 +200,11 @@ def build_device_inputs(torch, dev, seed):
         fm1 = (torch.randn(B, C, H, W, generator=g).relu_() / 16).to(dev)
         go = torch.randn(B, H, W, 2 * D + 1, 2 * D + 1, generator=g).to(dev)
         inp["corr"].append((fm0, fm1, go))
-    for f in range(2 * B):
-        rois = torch.from_numpy(cases.rois_random(R, 1237 + f)).to(dev)
-        for nT in (N_CLS, N_REG):
-            inp["ps"].append((nT, torch.randn(nT * K * K, H, W, generator=g).to(dev), rois,
-                              torch.randn(R, nT, K, K, generator=g).to(dev)))
+    # R-FCN heads: 2 frames per pair, class (31 targets) and box (4 targets) score maps, batched over the frames
+    rois = torch.stack([torch.from_numpy(cases.rois_random(R, 1237 + f)) for f in range(2 * B)]).to(dev)
+    for nT in (N_CLS, N_REG):
+        inp["ps"].append((nT, torch.randn(2 * B, nT * K * K, H, W, generator=g).to(dev), rois,
+                          torch.randn(2 * B, R, nT, K, K, generator=g).to(dev)))
     for pr in range(B):
         rois = torch.from_numpy(cases.rois_random(R, 1238 + pr)).to(dev)
         inp["track"].append((torch.randn(TRACK_C, H, W, generator=g).to(dev), rois,
@@ -246,9 +246,9 @@ def run_ours(args):
                 dom["e0"].append(a); dom["e1"].append(b)
             else:
                 keep.append(pc.pointwise_correlation_backward(go, fm0, fm1, D, 1))
-        for nT, fm, rois, go in inp["ps"]:
-            keep.append(ps.ps_roipool_forward(fm, rois, nT, K))
-            keep.append(ps.ps_roipool_backward(go, rois, H, W))
+        for nT, fm, rois, go in inp["ps"]:   # all 2*B frames of the shard in one set of launches
+            keep.append(ps.ps_roipool_forward_batched(fm, rois, nT, K))
+            keep.append(ps.ps_roipool_backward_batched(go, rois, H, W))
         for fm, rois, go in inp["track"]:
             keep.append(rp.roipool_forward(fm, rois, K))
             keep.append(rp.roipool_backward(go, rois, H, W))

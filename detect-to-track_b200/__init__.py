@@ -8,12 +8,12 @@ include/d2t_b200.h.  No Triton, no CPU fallback.
 """
 from .pointwise_correlation import PointwiseCorrelation, PointwiseCorrelationFunction
 from .roipool import ROIPool, ROIPoolFunction
-from .ps_roipool import PSROIPool, PSROIPoolFunction
+from .ps_roipool import PSROIPool, PSROIPoolFunction, PSROIPoolBatched, PSROIPoolBatchedFunction
 from .models import RFCN, CorrelationTracker
 
 __all__ = [
     "PointwiseCorrelation", "PointwiseCorrelationFunction",
     "ROIPool", "ROIPoolFunction",
-    "PSROIPool", "PSROIPoolFunction",
+    "PSROIPool", "PSROIPoolFunction", "PSROIPoolBatched", "PSROIPoolBatchedFunction",
     "RFCN", "CorrelationTracker",
 ]

@@ -28,6 +28,7 @@ _CORR_FWD = [_P, _P, _P] + [_c_int] * 6 + [_P, _c_size_t, _P]
 _CORR_BWD = [_P] * 5 + [_c_int] * 6 + [_P, _c_size_t, _P]
 _POOL = [_P, _P, _P] + [_c_int] * 5 + [_P, _c_size_t, _P]
 _PSPOOL = [_P, _P, _P] + [_c_int] * 6 + [_P, _c_size_t, _P]
+_PSPOOL_B = [_P, _P, _P] + [_c_int] * 7 + [_P, _c_size_t, _P]
 _WS6 = [_c_int] * 6
 _WS7 = [_c_int] * 7
 SIGNATURES = {
@@ -54,6 +55,10 @@ SIGNATURES = {
     "d2t_psroipool_fwd_f64": (_c_int, _PSPOOL),
     "d2t_psroipool_bwd_f32": (_c_int, _PSPOOL),
     "d2t_psroipool_bwd_f64": (_c_int, _PSPOOL),
+    "d2t_psroipool_fwd_batched_workspace_bytes": (_c_size_t, _WS7),
+    "d2t_psroipool_bwd_batched_workspace_bytes": (_c_size_t, _WS7),
+    "d2t_psroipool_fwd_batched_f32": (_c_int, _PSPOOL_B),
+    "d2t_psroipool_bwd_batched_f32": (_c_int, _PSPOOL_B),
     "d2t_pool_bins_f32": (_c_int, [_P, _P] + [_c_int] * 5 + [_P]),
     "d2t_pool_bins_f64": (_c_int, [_P, _P] + [_c_int] * 5 + [_P]),
 }

@@ -1,0 +1,379 @@
+// pool_ps.cu -- float32 PSROIPool forward/backward over a BATCH of frames (N >= 1), channel-owner CTAs.  sm_100a.
+//
+// The per-output kernels in pool.cu put the target index on the lanes, so every load instruction touches 32
+// different channel planes (32 L1 wavefronts per LDG) and a call is a handful of small latency-bound launches:
+// 20 + 90 us per frame for the R-FCN class head (31 targets, 300 RoIs), 16 frames per training step on one GPU.
+// Here one launch covers all frames and a CTA owns one (frame, channel) plane:
+//
+//   forward   the CTA copies its plane into shared memory (coalesced), finds the (target, bin) pairs that read this
+//             channel -- the reference map (t+1)*(i*k+j) is many-to-one, SURVEY.md F6 -- and lets a lane take one
+//             RoI: bin edges come from a packed table, the bin is summed rows-then-columns out of shared memory in
+//             the reference's order (bit-identical results, ps_roipool_cuda.cu:60-69).
+//   backward  row-owner difference arrays, no atomics (reference: atomicAdd per bin pixel, ps_roipool_cuda.cu:124-139):
+//               1. edges    packed bin edges of every (frame, RoI, bin index), plus a bin-major copy
+//               2. scale    Vt[n][b][t][r] = grad_out[n][r][t][b] / cell size      (r fastest: coalesced later)
+//               3. rowlists for every (frame, bin row i, pixel row y): the RoIs whose bin row i contains y, ascending
+//                           (the bin geometry is shared by all targets and all bin columns: 7 x H lists per frame)
+//               4. main     CTA = (frame, channel), a THREAD owns a pixel row of the plane.  For each (target, bin)
+//                           pair that reads the channel, in ascending bin order, the thread walks its row list and
+//                           applies  D[y][J0] += v, D[y][J1] -= v  (v, J0, J1 of the RoI staged in shared memory);
+//                           an inclusive scan along x then turns D into the gradient row, written out coalesced.
+//                           One owner per row, fixed order => bitwise reproducible; every pixel written once,
+//                           channels nobody reads are zero-filled.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace d2t {
+
+constexpr int kPsbThreads = 256;
+constexpr int kPsbFwdThreads = 128;
+
+__device__ __forceinline__ uint32_t psb_pack_edges(const float* __restrict__ roi, int b, int k, int H, int W) {
+    int i0, i1, j0, j1;
+    bin_edge<float, false>(roi[0], roi[2], b, k, H, i0, i1);
+    bin_edge<float, false>(roi[1], roi[3], b, k, W, j0, j1);
+    return (uint32_t)i0 | ((uint32_t)i1 << 8) | ((uint32_t)j0 << 16) | ((uint32_t)j1 << 24);
+}
+
+// edges[(n*R + r)*k + b] = I0 | I1<<8 | J0<<16 | J1<<24 of bin index b (row edges from H, column edges from W);
+// edgesT[(n*k + b)*R + r] = the same word, bin-major (optional)
+__global__ void __launch_bounds__(256)
+psb_edges_kernel(const float* __restrict__ rois, uint32_t* __restrict__ edges, uint32_t* __restrict__ edgesT, int N,
+                 int R, int k, int H, int W) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * R * k; idx += gridDim.x * blockDim.x) {
+        const int nr = idx / k, b = idx - nr * k;
+        const uint32_t e = psb_pack_edges(rois + (size_t)nr * 4, b, k, H, W);
+        edges[idx] = e;
+        if (edgesT) {
+            const int n = nr / R, r = nr - n * R;
+            edgesT[((size_t)n * k + b) * R + r] = e;
+        }
+    }
+}
+
+// Users of channel ch, ascending bin index, into shared memory: us[u] = t << 16 | b.  Returns the count (uniform).
+// Reference map: ch = (t+1)*b.  ch == 0 <=> b == 0 for EVERY target: reported as one merged user with t = 0xFFFF.
+__device__ __forceinline__ int psb_users(int ch, int nT, int kk, bool canonical, uint32_t* us, int* cnt) {
+    if (canonical) {
+        if (threadIdx.x == 0) {
+            const int t = ch / kk;
+            us[0] = ((uint32_t)t << 16) | (uint32_t)(ch - t * kk);
+        }
+        __syncthreads();
+        return 1;
+    }
+    if (ch == 0) {
+        if (threadIdx.x == 0) us[0] = 0xFFFF0000u;
+        __syncthreads();
+        return 1;
+    }
+    // thread b tests bin b; ordered compaction with warp ballots (kk <= blockDim.x is guaranteed by the host)
+    const int b = threadIdx.x;
+    bool is = false;
+    int t = 0;
+    if (b >= 1 && b < kk && ch % b == 0) {
+        t = ch / b - 1;
+        is = t < nT;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, is);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) cnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+    const int nw = (kk + 31) >> 5;
+    for (int w = 0; w < nw; ++w) {
+        const int c = cnt[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    if (is) us[base + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)t << 16) | (uint32_t)b;
+    __syncthreads();
+    return total;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// forward
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPsbFwdThreads)
+psb_fwd_kernel(const float* __restrict__ fm, const uint32_t* __restrict__ edges, float* __restrict__ out, int R, int nT,
+               int H, int W, int k, int canonical) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* plane = reinterpret_cast<float*>(smem_raw);           // [H*W]
+    uint32_t* us = reinterpret_cast<uint32_t*>(plane + H * W);   // [kk]
+    int* cnt = reinterpret_cast<int*>(us + k * k);               // [8]
+    const int kk = k * k;
+    const int nCh = nT * kk;
+    const int ch = blockIdx.x, n = blockIdx.y;
+    const int HW = H * W;
+    const int nU = psb_users(ch, nT, kk, canonical != 0, us, cnt);
+    if (nU == 0) return;
+    const float* src = fm + ((size_t)n * nCh + ch) * HW;
+    for (int idx = threadIdx.x; idx < HW; idx += kPsbFwdThreads) plane[idx] = __ldg(src + idx);
+    __syncthreads();
+    const uint32_t* ed = edges + (size_t)n * R * k;
+    float* o = out + (size_t)n * R * nCh;
+    for (int idx = threadIdx.x; idx < nU * R; idx += kPsbFwdThreads) {
+        const int u = idx / R, r = idx - u * R;
+        const uint32_t pk = us[u];
+        const int t = pk >> 16, b = pk & 0xffff;
+        const int i = b / k, j = b - i * k;
+        const uint32_t ei = __ldg(ed + r * k + i), ej = __ldg(ed + r * k + j);
+        const int i0 = ei & 255, i1 = (ei >> 8) & 255, j0 = (ej >> 16) & 255, j1 = ej >> 24;
+        float acc = 0.f;
+        for (int pi = i0; pi < i1; ++pi) {
+            const float* row = plane + pi * W;
+            for (int pj = j0; pj < j1; ++pj) acc += row[pj];
+        }
+        const int numel = (i1 - i0) * (j1 - j0);
+        if (numel > 0) acc /= numel;
+        if (t == 0xFFFF) {  // channel 0 of the reference map: bin 0 of every target reads it
+            for (int tt = 0; tt < nT; ++tt) o[((size_t)r * nT + tt) * kk] = acc;
+        } else {
+            o[((size_t)r * nT + t) * kk + b] = acc;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// backward 2: Vt[((n*kk + b)*nT + t)*R + r] = grad_out[((n*R + r)*nT + t)*kk + b] / cell size
+// ----------------------------------------------------------------------------------------------------
+// grid (ceil(R/32), nT, N), 64 threads: a 32-RoI x kk tile goes through shared memory
+__global__ void __launch_bounds__(64)
+psb_scale_kernel(const float* __restrict__ go, const uint32_t* __restrict__ edges, float* __restrict__ vt, int R, int nT,
+                 int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);  // [32][kk | 1]
+    const int kk = k * k;
+    const int pitch = kk | 1;
+    const int r0 = blockIdx.x * 32, t = blockIdx.y, n = blockIdx.z;
+    const int nr = min(32, R - r0);
+    for (int e = threadIdx.x; e < nr * kk; e += 64) {
+        const int rr = e / kk, b = e - rr * kk;
+        const int i = b / k, j = b - i * k;
+        const int r = r0 + rr;
+        const uint32_t* ed = edges + ((size_t)n * R + r) * k;
+        const uint32_t ei = __ldg(ed + i), ej = __ldg(ed + j);
+        const int numel = ((int)((ei >> 8) & 255) - (int)(ei & 255)) * ((int)(ej >> 24) - (int)((ej >> 16) & 255));
+        float v = __ldg(go + (((size_t)n * R + r) * nT + t) * kk + b);
+        if (numel > 0) v /= numel;  // ps_roipool_cuda.cu:134-137
+        tile[rr * pitch + b] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < nr)
+        for (int b = warp; b < kk; b += 2) vt[(((size_t)n * kk + b) * nT + t) * R + r0 + lane] = tile[lane * pitch + b];
+}
+
+// ----------------------------------------------------------------------------------------------------
+// backward 3: row lists.  One warp per (frame n, bin row i, pixel row y)
+// ----------------------------------------------------------------------------------------------------
+// rowlist[((n*k + i)*R + e)*H + y] = e-th RoI (ascending) whose bin row i contains pixel row y   (y fastest: the row
+// threads of the main kernel read entry e of their lists with one coalesced load);  rowcnt[(n*k + i)*H + y] = length
+__global__ void __launch_bounds__(kPsbThreads)
+psb_rowlists_kernel(const uint32_t* __restrict__ edgesT, uint16_t* __restrict__ rowlist, int* __restrict__ rowcnt, int N,
+                    int R, int H, int k) {
+    const int lane = threadIdx.x & 31;
+    const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int l = warpGlobal; l < N * k * H; l += nWarps) {
+        const int ni = l / H, y = l - ni * H;  // ni = n*k + i
+        const uint32_t* ed = edgesT + (size_t)ni * R;
+        uint16_t* list = rowlist + (size_t)ni * R * H + y;
+        int cnt = 0;
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            const int r = r0 + lane;
+            bool in = false;
+            if (r < R) {
+                const uint32_t e = __ldg(ed + r);
+                in = (int)(e & 255) <= y && y < (int)((e >> 8) & 255);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) list[(size_t)(cnt + __popc(bal & ((1u << lane) - 1u))) * H] = (uint16_t)r;
+            cnt += __popc(bal);
+        }
+        if (lane == 0) rowcnt[l] = cnt;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// backward 4: main.  grid (nCh, N): CTA = (channel, frame), 64 threads, a thread owns pixel rows
+// ----------------------------------------------------------------------------------------------------
+constexpr int kPsbRowThreads = 64;
+__global__ void __launch_bounds__(kPsbRowThreads)
+psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlist, const int* __restrict__ rowcnt,
+               const uint32_t* __restrict__ edgesT, float* __restrict__ gin, int R, int nT, int H, int W, int k,
+               int canonical) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int kk = k * k;
+    const int pitch = (W + 1) | 1;  // odd: rows land in different banks
+    float* D = reinterpret_cast<float*>(smem_raw);                 // [H][pitch]
+    float* vS = D + H * pitch;                                     // [R]
+    uint32_t* jS = reinterpret_cast<uint32_t*>(vS + R);            // [R]  packed edges of the user's bin column
+    uint32_t* us = jS + R;                                         // [kk]
+    int* cnt = reinterpret_cast<int*>(us + kk);                    // [8]
+    const int nCh = nT * kk;
+    const int ch = blockIdx.x, n = blockIdx.y;
+    const int HW = H * W;
+    float* dst = gin + ((size_t)n * nCh + ch) * HW;
+    const int nU = psb_users(ch, nT, kk, canonical != 0, us, cnt);
+    if (nU == 0) {
+        for (int px = threadIdx.x; px < HW; px += kPsbRowThreads) dst[px] = 0.f;
+        return;
+    }
+    for (int idx = threadIdx.x; idx < H * pitch; idx += kPsbRowThreads) D[idx] = 0.f;
+    // thread -> row map: warp 0 takes even rows, warp 1 odd rows (both warps busy when H < 64)
+    const int yFirst = (threadIdx.x & 31) * 2 + (threadIdx.x >> 5);
+    for (int u = 0; u < nU; ++u) {
+        const uint32_t pk = us[u];
+        const int t = pk >> 16, b = pk & 0xffff;
+        const int i = b / k, j = b - i * k;
+        __syncthreads();  // the previous user's vS / jS are no longer read (first time: D is zeroed)
+        for (int r = threadIdx.x; r < R; r += kPsbRowThreads) {
+            float v;
+            if (t == 0xFFFF) {  // merged channel 0: sum over targets, ascending (fixed order)
+                v = 0.f;
+                for (int tt = 0; tt < nT; ++tt) v += __ldg(vt + (((size_t)n * kk) * nT + tt) * R + r);
+            } else {
+                v = __ldg(vt + (((size_t)n * kk + b) * nT + t) * R + r);
+            }
+            vS[r] = v;
+            jS[r] = __ldg(edgesT + ((size_t)n * k + j) * R + r);
+        }
+        __syncthreads();
+        const uint16_t* lists = rowlist + ((size_t)n * k + i) * R * H;
+        const int* cnts = rowcnt + ((size_t)n * k + i) * H;
+        for (int y = yFirst; y < H; y += kPsbRowThreads) {
+            float* row = D + y * pitch;
+            const int c = __ldg(cnts + y);
+            for (int e = 0; e < c; ++e) {
+                const int r = __ldg(lists + (size_t)e * H + y);
+                const float v = vS[r];
+                const uint32_t ej = jS[r];
+                const int j0 = (ej >> 16) & 255, j1 = ej >> 24;
+                if (j1 > j0) {  // an empty bin column receives nothing (and (a + v) - v need not give a back)
+                    row[j0] += v;
+                    row[j1] -= v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int y = yFirst; y < H; y += kPsbRowThreads) {  // inclusive scan along x
+        float* row = D + y * pitch;
+        float acc = 0.f;
+        for (int x = 0; x < W; ++x) {
+            acc += row[x];
+            row[x] = acc;
+        }
+    }
+    __syncthreads();
+    for (int px = threadIdx.x; px < HW; px += kPsbRowThreads) {
+        const int y = px / W, x = px - y * W;
+        dst[px] = D[y * pitch + x];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------
+struct PsbLayout {
+    size_t edgesOff, edgesTOff, vtOff, listOff, cntOff, total;
+};
+static PsbLayout psb_layout(int N, int R, int nT, int H, int W, int k, bool bwd) {
+    (void)W;
+    PsbLayout L;
+    size_t off = 0;
+    L.edgesOff = off;
+    off += align_up((size_t)N * R * k * sizeof(uint32_t), 256);
+    L.edgesTOff = off;
+    if (bwd) off += align_up((size_t)N * R * k * sizeof(uint32_t), 256);
+    L.vtOff = off;
+    if (bwd) off += align_up((size_t)N * k * k * nT * R * sizeof(float), 256);
+    L.listOff = off;
+    if (bwd) off += align_up((size_t)N * k * R * H * sizeof(uint16_t), 256);
+    L.cntOff = off;
+    if (bwd) off += align_up((size_t)N * k * H * sizeof(int), 256);
+    L.total = off;
+    return L;
+}
+
+bool psb_supported(int N, int R, int nT, int H, int W, int k) {
+    if (N <= 0 || R <= 0 || nT <= 0 || k <= 0 || H <= 0 || W <= 0) return false;
+    if (H > 255 || W > 255 || R >= 65534 || k * k > kPsbFwdThreads || nT >= 0xFFFF || N > 65535) return false;
+    if ((long long)nT * k * k > 0x7fffffffLL / 4) return false;
+    static int off = -1;
+    if (off < 0) {
+        const char* e = getenv("D2T_PSROI_BATCHED");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    if (off) return false;
+    DeviceInfo di;
+    if (device_info(&di)) return false;
+    const size_t fwdSmem = (size_t)H * W * 4 + (size_t)k * k * 4 + 64;
+    const size_t bwdSmem = (size_t)H * ((W + 1) | 1) * 4 + (size_t)R * 8 + (size_t)k * k * 4 + 64;
+    const size_t cap = (size_t)di.max_smem_optin;
+    return fwdSmem <= cap && bwdSmem <= cap;
+}
+
+size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd) { return psb_layout(N, R, nT, H, W, k, bwd).total; }
+
+static int psb_edges_launch(const float* rois, uint32_t* edges, uint32_t* edgesT, int N, int R, int k, int H, int W,
+                            cudaStream_t st) {
+    const int total = N * R * k;
+    psb_edges_kernel<<<ceil_div(total, 256), 256, 0, st>>>(rois, edges, edgesT, N, R, k, H, W);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
+int psb_fwd_launch(const float* fm, const float* rois, float* out, int N, int R, int nT, int H, int W, int k, int flags,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
+    const PsbLayout L = psb_layout(N, R, nT, H, W, k, false);
+    if (!ws || ws_bytes < L.total) {
+        set_error("psroipool_fwd (batched): workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
+        return D2T_ERR_WORKSPACE;
+    }
+    uint32_t* edges = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + L.edgesOff);
+    int rc = psb_edges_launch(rois, edges, nullptr, N, R, k, H, W, st);
+    if (rc) return rc;
+    const size_t smem = (size_t)H * W * 4 + (size_t)k * k * 4 + 64;
+    D2T_CUDA_TRY(cudaFuncSetAttribute(psb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    psb_fwd_kernel<<<dim3(nT * k * k, N), kPsbFwdThreads, smem, st>>>(fm, edges, out, R, nT, H, W, k,
+                                                                     (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
+int psb_bwd_launch(const float* go, const float* rois, float* gin, int N, int R, int nT, int H, int W, int k, int flags,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
+    const PsbLayout L = psb_layout(N, R, nT, H, W, k, true);
+    if (!ws || ws_bytes < L.total) {
+        set_error("psroipool_bwd (batched): workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
+        return D2T_ERR_WORKSPACE;
+    }
+    char* base = static_cast<char*>(ws);
+    uint32_t* edges = reinterpret_cast<uint32_t*>(base + L.edgesOff);
+    uint32_t* edgesT = reinterpret_cast<uint32_t*>(base + L.edgesTOff);
+    float* vt = reinterpret_cast<float*>(base + L.vtOff);
+    uint16_t* rowlist = reinterpret_cast<uint16_t*>(base + L.listOff);
+    int* rowcnt = reinterpret_cast<int*>(base + L.cntOff);
+    const bool canonical = (flags & D2T_PS_CANONICAL_MAP) != 0;
+    const int kk = k * k;
+    int rc = psb_edges_launch(rois, edges, edgesT, N, R, k, H, W, st);
+    if (rc) return rc;
+    psb_scale_kernel<<<dim3(ceil_div(R, 32), nT, N), 64, (size_t)32 * (kk | 1) * 4, st>>>(go, edges, vt, R, nT, k);
+    D2T_CUDA_TRY(cudaGetLastError());
+    const int lists = N * k * H;
+    psb_rowlists_kernel<<<ceil_div(lists, kPsbThreads / 32), kPsbThreads, 0, st>>>(edgesT, rowlist, rowcnt, N, R, H, k);
+    D2T_CUDA_TRY(cudaGetLastError());
+    const size_t smem = (size_t)H * ((W + 1) | 1) * 4 + (size_t)R * 8 + (size_t)kk * 4 + 64;
+    D2T_CUDA_TRY(cudaFuncSetAttribute(psb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    psb_bwd_kernel<<<dim3(nT * kk, N), kPsbRowThreads, smem, st>>>(vt, rowlist, rowcnt, edgesT, gin, R, nT, H, W, k,
+                                                                  canonical ? 1 : 0);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch(3);
+    return D2T_OK;
+}
+
+}  // namespace d2t

@@ -30,9 +30,11 @@ def ps_roipool_forward(FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, cano
     lib = _lib.lib()
     with torch.cuda.device(FM.device):
         out = torch.empty((R, n_targets, r_hw, r_hw), dtype=FM.dtype, device=FM.device)
+        nbytes = lib.d2t_psroipool_fwd_workspace_bytes(R, n_targets, H, W, r_hw, FM.element_size())
+        ws, ws_ptr, ws_n = _lib.workspace(nbytes, FM.device)
         rc = getattr(lib, f"d2t_psroipool_fwd_{sfx}")(
             FM.data_ptr(), rois.data_ptr(), out.data_ptr(), R, n_targets, H, W, r_hw,
-            _CANONICAL if canonical_map else 0, None, 0, _lib.stream_ptr(FM.device))
+            _CANONICAL if canonical_map else 0, ws_ptr, ws_n, _lib.stream_ptr(FM.device))
         _lib.check(rc, "ps_roipool_forward")
     return out
 
@@ -57,6 +59,77 @@ def ps_roipool_backward(grad_out: Tensor, rois: Tensor, fm_h: int, fm_w: int, ca
             _CANONICAL if canonical_map else 0, ws_ptr, ws_n, _lib.stream_ptr(grad_out.device))
         _lib.check(rc, "ps_roipool_backward")
     return grad_FM
+
+
+def _check_batched(x: Tensor, rois: Tensor, what: str) -> None:
+    _lib.check_input(x, what)
+    _lib.check_input(rois, "rois")
+    if x.dtype != torch.float32:
+        raise RuntimeError("the batched PSROIPool is float32 only")
+    if rois.dtype != x.dtype or rois.device != x.device:
+        raise RuntimeError("rois must have the dtype and device of the feature map")
+    if rois.dim() != 3 or rois.size(2) != 4 or rois.size(0) != x.size(0):
+        raise RuntimeError(f"rois must be (N, |R|, 4) with N = {x.size(0)}; got {tuple(rois.shape)}")
+
+
+def ps_roipool_forward_batched(FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
+    """N frames in one set of launches: FM (N, n_targets*r_hw^2, H, W), rois (N, |R|, 4) ->
+    (N, |R|, n_targets, r_hw, r_hw).  Bit-identical to N calls of `ps_roipool_forward`.  Extension: the reference
+    pools one frame per call (rfcn.py:36-41)."""
+    if FM.dim() != 4:
+        raise RuntimeError(f"FM must be (N, n_targets*r_hw^2, H, W); got {tuple(FM.shape)}")
+    _check_batched(FM, rois, "FM")
+    N, C, H, W = FM.shape
+    if C != n_targets * r_hw ** 2:
+        raise ValueError(f"expected {n_targets * r_hw ** 2} feature map channels, recieved feature map of shape {tuple(FM.shape)}")
+    R = rois.size(1)
+    lib = _lib.lib()
+    with torch.cuda.device(FM.device):
+        out = torch.empty((N, R, n_targets, r_hw, r_hw), dtype=FM.dtype, device=FM.device)
+        nbytes = lib.d2t_psroipool_fwd_batched_workspace_bytes(N, R, n_targets, H, W, r_hw, 4)
+        ws, ws_ptr, ws_n = _lib.workspace(nbytes, FM.device)
+        rc = lib.d2t_psroipool_fwd_batched_f32(
+            FM.data_ptr(), rois.data_ptr(), out.data_ptr(), N, R, n_targets, H, W, r_hw,
+            _CANONICAL if canonical_map else 0, ws_ptr, ws_n, _lib.stream_ptr(FM.device))
+        _lib.check(rc, "ps_roipool_forward_batched")
+    return out
+
+
+def ps_roipool_backward_batched(grad_out: Tensor, rois: Tensor, fm_h: int, fm_w: int, canonical_map: bool = False) -> Tensor:
+    """grad_out (N, |R|, n_targets, r_hw, r_hw), rois (N, |R|, 4) -> grad_FM (N, n_targets*r_hw^2, H, W)."""
+    if grad_out.dim() != 5 or grad_out.size(3) != grad_out.size(4):
+        raise RuntimeError(f"grad_out must be (N, |R|, n_targets, r_hw, r_hw); got {tuple(grad_out.shape)}")
+    _check_batched(grad_out, rois, "gradOut")
+    N, R, n_targets, r_hw, _ = grad_out.shape
+    if rois.size(1) != R:
+        raise RuntimeError(f"grad_out has {R} RoIs per frame but rois has {rois.size(1)}")
+    lib = _lib.lib()
+    with torch.cuda.device(grad_out.device):
+        grad_FM = torch.empty((N, n_targets * r_hw * r_hw, fm_h, fm_w), dtype=grad_out.dtype, device=grad_out.device)
+        nbytes = lib.d2t_psroipool_bwd_batched_workspace_bytes(N, R, n_targets, fm_h, fm_w, r_hw, 4)
+        ws, ws_ptr, ws_n = _lib.workspace(nbytes, grad_out.device)
+        rc = lib.d2t_psroipool_bwd_batched_f32(
+            grad_out.data_ptr(), rois.data_ptr(), grad_FM.data_ptr(), N, R, n_targets, fm_h, fm_w, r_hw,
+            _CANONICAL if canonical_map else 0, ws_ptr, ws_n, _lib.stream_ptr(grad_out.device))
+        _lib.check(rc, "ps_roipool_backward_batched")
+    return grad_FM
+
+
+class PSROIPoolBatchedFunction(Function):
+    """PSROIPoolFunction over a leading frame dimension (one set of kernel launches for all frames)."""
+
+    @staticmethod
+    def forward(ctx, FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
+        ctx.save_for_backward(rois)
+        ctx.fm_h, ctx.fm_w = FM.shape[-2:]
+        ctx.canonical_map = canonical_map
+        return ps_roipool_forward_batched(FM, rois, n_targets, r_hw, canonical_map)
+
+    @staticmethod
+    def backward(ctx: object, grad_out: Tensor) -> Tuple[Tensor, None, None, None, None]:
+        rois, = ctx.saved_tensors
+        grad_FM = ps_roipool_backward_batched(grad_out.contiguous(), rois, ctx.fm_h, ctx.fm_w, ctx.canonical_map)
+        return grad_FM, None, None, None, None
 
 
 class PSROIPoolFunction(Function):
@@ -135,3 +208,19 @@ class PSROIPool(Module):
         if self.canonical_map:
             return PSROIPoolFunction.apply(FM, rois, self.n_targets, self.r_hw, True)
         return PSROIPoolFunction.apply(FM, rois, self.n_targets, self.r_hw)
+
+
+class PSROIPoolBatched(Module):
+    """PSROIPool over a batch of frames: FM (N, n_targets*r_hw^2, H, W), rois (N, |R|, 4) ->
+    (N, |R|, n_targets, r_hw, r_hw).  Same attributes as `PSROIPool`; float32 only."""
+
+    def __init__(self, n_targets: int, r_hw: int, canonical_map: bool = False) -> None:
+        super().__init__()
+        self.n_targets = n_targets
+        self.r_hw = r_hw
+        self.canonical_map = canonical_map
+
+    def forward(self, FM: Tensor, rois: Tensor) -> Tensor:
+        if self.canonical_map:
+            return PSROIPoolBatchedFunction.apply(FM, rois, self.n_targets, self.r_hw, True)
+        return PSROIPoolBatchedFunction.apply(FM, rois, self.n_targets, self.r_hw)

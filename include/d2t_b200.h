@@ -140,6 +140,19 @@ D2T_API int d2t_psroipool_bwd_f32(const float* grad_out, const float* rois, floa
 D2T_API int d2t_psroipool_bwd_f64(const double* grad_out, const double* rois, double* grad_fm, int R, int n_targets,
                           int H, int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- PSROIPool over a batch of frames (float32) ---------------------------
+ * Extension: the reference pools one frame per call (rfcn.py:36-41, called per frame from trainer.py:208-209).
+ * fm : (N, n_targets*r_hw^2, H, W);  rois : (N, R, 4);  out / grad_out : (N, R, n_targets, r_hw, r_hw);
+ * grad_fm : (N, n_targets*r_hw^2, H, W).  Frame n uses rois[n].  Results are bit-identical to N single-frame calls;
+ * one set of launches covers all frames (a CTA owns one (frame, channel) plane).
+ */
+D2T_API size_t d2t_psroipool_fwd_batched_workspace_bytes(int N, int R, int n_targets, int H, int W, int r_hw, int elem_size);
+D2T_API int d2t_psroipool_fwd_batched_f32(const float* fm, const float* rois, float* out, int N, int R, int n_targets,
+                          int H, int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
+D2T_API size_t d2t_psroipool_bwd_batched_workspace_bytes(int N, int R, int n_targets, int H, int W, int r_hw, int elem_size);
+D2T_API int d2t_psroipool_bwd_batched_f32(const float* grad_out, const float* rois, float* grad_fm, int N, int R,
+                          int n_targets, int H, int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- integer bin edges (parity instrumentation) ----------------------------
  * edges : (R, r_hw, 4) int32 = (I0, I1, J0, J1) of row-bin / column-bin b,
  * computed on the device by the same code the pooling kernels use.

@@ -317,6 +317,59 @@ def test_psroipool_full_size_cls_head(cuda):
     assert int((gin.abs().sum(dim=(1, 2)) > 0).sum()) == 608
 
 
+@pytest.mark.parametrize("canonical", [False, True])
+@pytest.mark.parametrize("N,nT,H,W,k,R", [(3, 4, 38, 63, 7, 50), (2, 31, 38, 63, 7, 300), (4, 2, 11, 10, 6, 9), (1, 5, 20, 21, 3, 700)])
+def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
+    """the batched entry points (one set of launches for N frames) give bit-identical results to N single-frame
+    calls, and both match the oracle (R = 700 on a 20x21 map: long row lists, many RoIs per pixel)."""
+    rng = np.random.default_rng(36)
+    rois = np.stack([np.concatenate([cases.rois_edge_cases(H, W), cases.rois_random(R, 40 + n), cases.ROIS_OOB.astype(np.float32)])
+                     for n in range(N)]).astype(np.float32)
+    Rt = rois.shape[1]
+    fm = rng.standard_normal((N, nT * k * k, H, W)).astype(np.float32)
+    go = rng.standard_normal((N, Rt, nT, k, k)).astype(np.float32)
+    out = ps_mod.ps_roipool_forward_batched(dev(fm, cuda), dev(rois, cuda), nT, k, canonical)
+    gin = ps_mod.ps_roipool_backward_batched(dev(go, cuda), dev(rois, cuda), H, W, canonical)
+    assert torch.equal(gin, ps_mod.ps_roipool_backward_batched(dev(go, cuda), dev(rois, cuda), H, W, canonical))
+    for n in range(N):
+        o1 = ps_mod.ps_roipool_forward(dev(fm[n], cuda), dev(rois[n], cuda), nT, k, canonical)
+        g1 = ps_mod.ps_roipool_backward(dev(go[n], cuda), dev(rois[n], cuda), H, W, canonical)
+        assert torch.equal(out[n], o1) and torch.equal(gin[n], g1)
+        np.testing.assert_array_equal(out[n].cpu().numpy(), oracle.psroipool_fwd(fm[n], rois[n], nT, k, canonical))
+        close(gin[n], oracle.psroipool_bwd(go[n], rois[n], H, W, canonical), np.float32)
+
+
+def test_psroipool_batched_module_autograd(cuda):
+    N, nT, H, W, k, R = 2, 4, 12, 13, 7, 20
+    g = torch.Generator(device="cpu").manual_seed(5)
+    fm = torch.randn(N, nT * k * k, H, W, generator=g).to(cuda).requires_grad_(True)
+    rois = torch.stack([dev(cases.rois_random(R, 50 + n), cuda) for n in range(N)])
+    out = d2t.PSROIPoolBatched(nT, k)(fm, rois)
+    w = torch.randn(out.shape, generator=g).to(cuda)
+    (out * w).sum().backward()
+    fm2 = fm.detach().clone().requires_grad_(True)
+    outs = torch.stack([d2t.PSROIPool(nT, k)(fm2[n], rois[n]) for n in range(N)])
+    (outs * w).sum().backward()
+    assert torch.equal(out, outs) and torch.equal(fm.grad, fm2.grad)
+    with pytest.raises(ValueError):
+        d2t.PSROIPoolBatched(nT, k)(fm[:, :-1].contiguous(), rois)
+
+
+def test_psroipool_legacy_kernels_still_match(cuda, monkeypatch):
+    """a NULL workspace keeps the per-output kernels of pool.cu (the float64 path): same results."""
+    from detect_to_track_b200 import _lib
+    nT, H, W, k = 4, 38, 63, 7
+    rois = _roipool_rois(H, W, np.float32, R=60)
+    fm, go = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 37, np.float32)
+    tf, tr, tg = dev(fm, cuda), dev(rois, cuda), dev(go, cuda)
+    lib = _lib.lib()
+    out = torch.empty((rois.shape[0], nT, k, k), device=cuda)
+    rc = lib.d2t_psroipool_fwd_f32(tf.data_ptr(), tr.data_ptr(), out.data_ptr(), rois.shape[0], nT, H, W, k, 0, None, 0,
+                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    assert torch.equal(out, ps_mod.ps_roipool_forward(tf, tr, nT, k))
+
+
 # ------------------------------------------------------------------ error behaviour + autograd wiring
 def test_errors_match_reference(cuda):
     fm = torch.rand(1, 2, 8, 8, device=cuda)
