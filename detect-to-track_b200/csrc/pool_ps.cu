@@ -138,31 +138,44 @@ psb_fwd_kernel(const float* __restrict__ fm, const uint32_t* __restrict__ edges,
 // ----------------------------------------------------------------------------------------------------
 // backward 2: Vt[((n*kk + b)*nT + t)*R + r] = grad_out[((n*R + r)*nT + t)*kk + b] / cell size
 // ----------------------------------------------------------------------------------------------------
-// grid (ceil(R/32), nT, N), 64 threads: a 32-RoI x kk tile goes through shared memory
-__global__ void __launch_bounds__(64)
+// grid (ceil(R/32), nT, N), 128 threads: a 32-RoI x kk tile goes through shared memory
+constexpr int kPsbScaleThreads = 128;
+__global__ void __launch_bounds__(kPsbScaleThreads)
 psb_scale_kernel(const float* __restrict__ go, const uint32_t* __restrict__ edges, float* __restrict__ vt, int R, int nT,
                  int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* tile = reinterpret_cast<float*>(smem_raw);  // [32][kk | 1]
     const int kk = k * k;
     const int pitch = kk | 1;
+    float* tile = reinterpret_cast<float*>(smem_raw);                 // [32][kk | 1]
+    short* hS = reinterpret_cast<short*>(tile + 32 * pitch);          // [32][k] bin heights
+    short* wS = hS + 32 * k;                                          // [32][k] bin widths
+    unsigned char* bi = reinterpret_cast<unsigned char*>(wS + 32 * k);  // [kk] bin row of bin b
     const int r0 = blockIdx.x * 32, t = blockIdx.y, n = blockIdx.z;
     const int nr = min(32, R - r0);
-    for (int e = threadIdx.x; e < nr * kk; e += 64) {
-        const int rr = e / kk, b = e - rr * kk;
-        const int i = b / k, j = b - i * k;
-        const int r = r0 + rr;
-        const uint32_t* ed = edges + ((size_t)n * R + r) * k;
-        const uint32_t ei = __ldg(ed + i), ej = __ldg(ed + j);
-        const int numel = ((int)((ei >> 8) & 255) - (int)(ei & 255)) * ((int)(ej >> 24) - (int)((ej >> 16) & 255));
-        float v = __ldg(go + (((size_t)n * R + r) * nT + t) * kk + b);
-        if (numel > 0) v /= numel;  // ps_roipool_cuda.cu:134-137
-        tile[rr * pitch + b] = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NWARP = kPsbScaleThreads / 32;
+    for (int e = threadIdx.x; e < nr * k; e += kPsbScaleThreads) {
+        const uint32_t w = __ldg(edges + ((size_t)n * R + r0) * k + e);
+        hS[e] = (short)((int)((w >> 8) & 255) - (int)(w & 255));
+        wS[e] = (short)((int)(w >> 24) - (int)((w >> 16) & 255));
+    }
+    for (int b = threadIdx.x; b < kk; b += kPsbScaleThreads) bi[b] = (unsigned char)(b / k);
+    __syncthreads();
+    // a warp takes whole RoIs: its lanes read the RoI's kk gradients as one contiguous run
+    for (int rr = warp; rr < nr; rr += NWARP) {
+        const float* src = go + (((size_t)n * R + r0 + rr) * nT + t) * kk;
+        for (int b = lane; b < kk; b += 32) {
+            const int i = bi[b], j = b - i * k;
+            const int numel = (int)hS[rr * k + i] * (int)wS[rr * k + j];
+            float v = __ldg(src + b);
+            if (numel > 0) v /= numel;  // ps_roipool_cuda.cu:134-137
+            tile[rr * pitch + b] = v;
+        }
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane < nr)
-        for (int b = warp; b < kk; b += 2) vt[(((size_t)n * kk + b) * nT + t) * R + r0 + lane] = tile[lane * pitch + b];
+        for (int b = warp; b < kk; b += NWARP)
+            vt[(((size_t)n * kk + b) * nT + t) * R + r0 + lane] = tile[lane * pitch + b];
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -207,9 +220,8 @@ psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlis
     const int kk = k * k;
     const int pitch = (W + 1) | 1;  // odd: rows land in different banks
     float* D = reinterpret_cast<float*>(smem_raw);                 // [H][pitch]
-    float* vS = D + H * pitch;                                     // [R]
-    uint32_t* jS = reinterpret_cast<uint32_t*>(vS + R);            // [R]  packed edges of the user's bin column
-    uint32_t* us = jS + R;                                         // [kk]
+    uint2* vj = reinterpret_cast<uint2*>(D + ((H * pitch + 1) & ~1));  // [R] {value bits, packed edges of the user's bin column}
+    uint32_t* us = reinterpret_cast<uint32_t*>(vj + R);            // [kk]
     int* cnt = reinterpret_cast<int*>(us + kk);                    // [8]
     const int nCh = nT * kk;
     const int ch = blockIdx.x, n = blockIdx.y;
@@ -227,7 +239,7 @@ psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlis
         const uint32_t pk = us[u];
         const int t = pk >> 16, b = pk & 0xffff;
         const int i = b / k, j = b - i * k;
-        __syncthreads();  // the previous user's vS / jS are no longer read (first time: D is zeroed)
+        __syncthreads();  // the previous user's values are no longer read (first time: D is zeroed)
         for (int r = threadIdx.x; r < R; r += kPsbRowThreads) {
             float v;
             if (t == 0xFFFF) {  // merged channel 0: sum over targets, ascending (fixed order)
@@ -236,8 +248,7 @@ psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlis
             } else {
                 v = __ldg(vt + (((size_t)n * kk + b) * nT + t) * R + r);
             }
-            vS[r] = v;
-            jS[r] = __ldg(edgesT + ((size_t)n * k + j) * R + r);
+            vj[r] = make_uint2(__float_as_uint(v), __ldg(edgesT + ((size_t)n * k + j) * R + r));
         }
         __syncthreads();
         const uint16_t* lists = rowlist + ((size_t)n * k + i) * R * H;
@@ -245,14 +256,22 @@ psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlis
         for (int y = yFirst; y < H; y += kPsbRowThreads) {
             float* row = D + y * pitch;
             const int c = __ldg(cnts + y);
-            for (int e = 0; e < c; ++e) {
-                const int r = __ldg(lists + (size_t)e * H + y);
-                const float v = vS[r];
-                const uint32_t ej = jS[r];
-                const int j0 = (ej >> 16) & 255, j1 = ej >> 24;
-                if (j1 > j0) {  // an empty bin column receives nothing (and (a + v) - v need not give a back)
-                    row[j0] += v;
-                    row[j1] -= v;
+            const uint16_t* lp = lists + y;
+            for (int e = 0; e < c; e += 4) {  // four entries in flight: list loads, then value loads, then the updates
+                int r[4];
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) r[s4] = (e + s4 < c) ? (int)__ldg(lp + (e + s4) * H) : -1;
+                uint2 q[4];
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) q[s4] = r[s4] >= 0 ? vj[r[s4]] : make_uint2(0u, 0u);
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int j0 = (q[s4].y >> 16) & 255, j1 = q[s4].y >> 24;
+                    if (j1 > j0) {  // an empty bin column receives nothing (and (a + v) - v need not give a back)
+                        const float v = __uint_as_float(q[s4].x);
+                        row[j0] += v;
+                        row[j1] -= v;
+                    }
                 }
             }
         }
@@ -261,15 +280,17 @@ psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlis
     for (int y = yFirst; y < H; y += kPsbRowThreads) {  // inclusive scan along x
         float* row = D + y * pitch;
         float acc = 0.f;
+#pragma unroll 4
         for (int x = 0; x < W; ++x) {
             acc += row[x];
             row[x] = acc;
         }
     }
     __syncthreads();
-    for (int px = threadIdx.x; px < HW; px += kPsbRowThreads) {
-        const int y = px / W, x = px - y * W;
-        dst[px] = D[y * pitch + x];
+    for (int x0 = 0; x0 < W; x0 += kPsbRowThreads) {  // thread = column: conflict-free reads, coalesced stores
+        const int x = x0 + threadIdx.x;
+        if (x < W)
+            for (int y = 0; y < H; ++y) dst[y * W + x] = D[y * pitch + x];
     }
 }
 
@@ -310,7 +331,7 @@ bool psb_supported(int N, int R, int nT, int H, int W, int k) {
     DeviceInfo di;
     if (device_info(&di)) return false;
     const size_t fwdSmem = (size_t)H * W * 4 + (size_t)k * k * 4 + 64;
-    const size_t bwdSmem = (size_t)H * ((W + 1) | 1) * 4 + (size_t)R * 8 + (size_t)k * k * 4 + 64;
+    const size_t bwdSmem = (size_t)H * ((W + 1) | 1) * 4 + 8 + (size_t)R * 8 + (size_t)k * k * 4 + 64;
     const size_t cap = (size_t)di.max_smem_optin;
     return fwdSmem <= cap && bwdSmem <= cap;
 }
@@ -362,12 +383,13 @@ int psb_bwd_launch(const float* go, const float* rois, float* gin, int N, int R,
     const int kk = k * k;
     int rc = psb_edges_launch(rois, edges, edgesT, N, R, k, H, W, st);
     if (rc) return rc;
-    psb_scale_kernel<<<dim3(ceil_div(R, 32), nT, N), 64, (size_t)32 * (kk | 1) * 4, st>>>(go, edges, vt, R, nT, k);
+    psb_scale_kernel<<<dim3(ceil_div(R, 32), nT, N), kPsbScaleThreads, (size_t)32 * (kk | 1) * 4 + (size_t)64 * k * 2 + kk + 16, st>>>(
+        go, edges, vt, R, nT, k);
     D2T_CUDA_TRY(cudaGetLastError());
     const int lists = N * k * H;
     psb_rowlists_kernel<<<ceil_div(lists, kPsbThreads / 32), kPsbThreads, 0, st>>>(edgesT, rowlist, rowcnt, N, R, H, k);
     D2T_CUDA_TRY(cudaGetLastError());
-    const size_t smem = (size_t)H * ((W + 1) | 1) * 4 + (size_t)R * 8 + (size_t)kk * 4 + 64;
+    const size_t smem = (size_t)H * ((W + 1) | 1) * 4 + 8 + (size_t)R * 8 + (size_t)kk * 4 + 64;
     D2T_CUDA_TRY(cudaFuncSetAttribute(psb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     psb_bwd_kernel<<<dim3(nT * kk, N), kPsbRowThreads, smem, st>>>(vt, rowlist, rowcnt, edgesT, gin, R, nT, H, W, k,
                                                                   canonical ? 1 : 0);
