@@ -70,6 +70,10 @@ int psb_bwd_launch(const float*, const float*, float*, int, int, int, int, int, 
 
 bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
 int corr_umma_fwd_launch(const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
+bool corr_umma_bwd_supported(int B, int C, int H, int W, int d, int stride);
+size_t corr_umma_bwd_ws_bytes(int B, int C, int H, int W);
+int corr_umma_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, void*, size_t,
+                         cudaStream_t);
 // tuned float32 correlation (corr_tile.cu)
 bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
 bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride);
@@ -154,6 +158,19 @@ int d2t_corr_fwd_f32_tc(const float* fm0, const float* fm1, float* out, int B, i
     if (rc) return rc;
     D2T_REQUIRE(corr_umma_supported(B, C, H, W, d_max, stride), "d2t_corr_fwd_f32_tc: needs d_max = 8, stride = 1");
     return corr_umma_fwd_launch(fm0, fm1, out, B, C, H, W, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// tensor-core (tcgen05, 3xTF32) backward, d_max = 8, stride 1 only; looser tolerance (see d2t_b200.h)
+size_t d2t_corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int d_max, int stride) {
+    return corr_umma_bwd_supported(B, C, H, W, d_max, stride) ? corr_umma_bwd_ws_bytes(B, C, H, W) : 0;
+}
+int d2t_corr_bwd_f32_tc(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0, float* grad_fm1, int B,
+                        int C, int H, int W, int d_max, int stride, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_corr(grad_out, fm0, fm1, B, C, H, W, d_max, stride, "d2t_corr_bwd_f32_tc");
+    if (rc) return rc;
+    D2T_REQUIRE((long long)B * C * H * W == 0 || (grad_fm0 && grad_fm1), "d2t_corr_bwd_f32_tc: null output pointer");
+    D2T_REQUIRE(corr_umma_bwd_supported(B, C, H, W, d_max, stride), "d2t_corr_bwd_f32_tc: needs d_max = 8, stride = 1");
+    return corr_umma_bwd_launch(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // ---- ROIPool -------------------------------------------------------------------------

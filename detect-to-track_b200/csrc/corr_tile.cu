@@ -52,6 +52,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+constexpr bool kCorrBwdDefaultUmma = false;  // default backward family when D2T_CORR_BWD is unset
 constexpr int kStages = 3;  // operand ring depth (cp.async groups in flight: kStages - 1)
 
 
@@ -497,7 +498,25 @@ size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d) {
 bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride) {
     return corr_tile_supported(B, C, H, W, d, stride);
 }
-size_t corr_tile_bwd_ws_bytes(int, int, int, int, int) { return 0; }
+
+// tensor-core backward (corr_umma_bwd.cu)
+bool corr_umma_bwd_supported(int B, int C, int H, int W, int d, int stride);
+size_t corr_umma_bwd_ws_bytes(int B, int C, int H, int W);
+int corr_umma_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, void*, size_t,
+                         cudaStream_t);
+
+// D2T_CORR_BWD = umma | simt selects the backward kernel family (read per call, so a test can flip it); see DESIGN.md
+// for the measurements behind the default.
+static bool use_umma_bwd(int B, int C, int H, int W, int d) {
+    if (!corr_umma_bwd_supported(B, C, H, W, d, 1)) return false;
+    const char* e = getenv("D2T_CORR_BWD");
+    if (e && strcmp(e, "umma") == 0) return true;
+    if (e && strcmp(e, "simt") == 0) return false;
+    return kCorrBwdDefaultUmma;
+}
+size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d) {
+    return use_umma_bwd(B, C, H, W, d) ? corr_umma_bwd_ws_bytes(B, C, H, W) : 0;
+}
 
 template <int D>
 static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, void* ws,
@@ -582,7 +601,9 @@ static int bwd_launch(const float* go, const float* fm0, const float* fm1, float
 }
 
 int corr_tile_bwd_launch(const float* go, const float* fm0, const float* fm1, float* g0, float* g1, int B, int C,
-                         int H, int W, int d, void*, size_t, cudaStream_t st) {
+                         int H, int W, int d, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (use_umma_bwd(B, C, H, W, d) && ws != nullptr && ws_bytes >= corr_umma_bwd_ws_bytes(B, C, H, W))
+        return corr_umma_bwd_launch(go, fm0, fm1, g0, g1, B, C, H, W, ws, ws_bytes, st);
     return d == 8 ? bwd_launch<8>(go, fm0, fm1, g0, g1, B, C, H, W, st)
                   : bwd_launch<4>(go, fm0, fm1, g0, g1, B, C, H, W, st);
 }

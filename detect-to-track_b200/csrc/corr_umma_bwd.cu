@@ -1,0 +1,382 @@
+// corr_umma_bwd.cu -- PointwiseCorrelation backward on the 5th-generation tensor cores (tcgen05 + TMEM), d_max = 8.
+//
+// Both gradients are the banded apply of corr_tile.cu,
+//     OUT[c, pos] = sum_{si,sj in [0,16)} G[pos, si, sj] * X[c, pos + (si,sj) - OFF]
+//   grad_FM0: X = FM1, OFF = 8, G[pos,si,sj] = gradOut[pos, si, sj]                                 (reference
+//   grad_FM1: X = FM0, OFF = 7, G[pos,si,sj] = gradOut[pos + (si,sj) - 7, 15 - si, 15 - sj]         pointwise_correlation_cuda.cu:145-172)
+// which for one tile of 8x16 positions is a GEMM over the tile's 23x31 halo patch of X:
+//     D[m = position (128)][n = channel] = sum_{k = patch element} S[m][k] * X[n][k],
+//     S[(qrow,qcol)][(r,x)] = G[(qrow,qcol), r - qrow, x - qcol]  inside the 16x16 band, 0 outside.
+// K runs over POSITIONS, which are contiguous in an NCHW plane, so X is K-major as it lies in memory: one patch row
+// (31 keys + 1 zero pad = 32 tf32 = 128 bytes) is exactly one row of the K-major SWIZZLE_128B operand layout.  S is
+// built on the fly from gradOut (L2-resident).  FP32 inputs are split 3xTF32 (hi*hi + hi*lo + lo*hi, hi rounded to
+// nearest) -- measured |err| <= 9e-7 * sum|a||b| (tools/umma_sw128_test.cu); the dense tile does ~2.8x the band's MACs.
+// Against the FP32-pipe band kernel (corr_tile.cu: 128 FFMA + 10 shared-memory accesses per thread and channel, bound by
+// the FMA and shared-memory pipes together) this moves the contraction to the tensor pipe and leaves the CUDA cores
+// only the operand staging.
+//
+//   work item  (image b, block of 256 channels, tile): M = 128, N = 256 accumulators = 256 TMEM columns; K walks the
+//              tile's live patch rows (rows outside the image are skipped, not multiplied).  Items are numbered with
+//              the tile fastest, so CTAs running together share an image and a channel block in L2.
+//   chunk      one patch row: A = S[128][32], B = X[256][32], each as hi and lo (96 KB per stage, 2 stages);
+//              4 k-steps x 3 MMAs (128x256x8, kind::tf32) per chunk.
+//   warps 0-7  producers: lane = key column.  Warp w stages channels 32w..32w+31 of B (one coalesced 124-byte LDG and
+//              two conflict-free 128-byte-row STS per channel) and query row w of A.  Loads run two chunks ahead in
+//              registers, across item boundaries.  After the last chunk of an item they read the accumulators
+//              (tcgen05.ld) and store D[m][n] -> grad[b][n][position].
+//   warp 0     additionally issues the MMAs (one lane) once the stage's `full` barrier completes; tcgen05.commit ->
+//              `empty` barrier of the stage / `accum_full` of the item.  (A ninth warp would cap the kernel at 168
+//              registers per thread -- allocation is per 4 warps -- and spill the prefetch registers.)
+//   grad_FM1   needs gradOut transposed (the queries whose window contains a key): corr_bwd_flip_kernel writes
+//              GT[b,p,si,sj] = gradOut[b, p + (si,sj) - 7, 15 - si, 15 - sj] (0 outside the image) into the workspace
+//              once per call (42 MB of traffic at B = 8), so that both gradients use the same staging code.
+#include <stdlib.h>
+#include <string.h>
+
+#include "corr_common.cuh"
+
+namespace d2t {
+
+namespace {
+
+constexpr int XD = 8;                     // d_max
+constexpr int XTD = 16;                   // live displacements per axis
+constexpr int XK1 = 17, XKK = 289;        // gradOut map side / size
+constexpr int XM = 128;                   // positions per tile = UMMA M
+constexpr int XN = 256;                   // channels per item = UMMA N = TMEM columns
+constexpr int XQROWS = 8, XQCOLS = 16;
+constexpr int XROWS = XQROWS + XTD - 1;   // 23 patch rows
+constexpr int XPROD_WARPS = 8;
+constexpr int XTHREADS = XPROD_WARPS * 32;
+constexpr int XA_BYTES = XM * 128;        // one A operand (hi or lo) of a chunk
+constexpr int XB_BYTES = XN * 128;        // one B operand (hi or lo) of a chunk
+constexpr int XSTAGE_BYTES = 2 * XA_BYTES + 2 * XB_BYTES;
+constexpr int XSTAGES = 2;
+constexpr int XNA = XQCOLS, XNB = XN / XPROD_WARPS;  // A / B elements a producer thread stages per chunk
+constexpr int XFLIP_PITCH = 290;          // shared-memory pitch of one gradOut map in the flip kernel
+
+struct XPlan {
+    int B, C, H, W;
+    int tilesX, tilesY, nCb, nItems;
+    int off;          // 8 (grad_FM0) or 7 (grad_FM1)
+    int gMap, gRow;   // floats per position / per row displacement of the G source (289/17 or 256/16)
+};
+
+__device__ __forceinline__ uint32_t x_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void x_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(x_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void x_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
+            x_smem(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void x_mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(x_smem(bar)) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): rows of 128 bytes,
+// 8-row atoms 1024 bytes apart (SBO); the start address may point 32*ks bytes into the row to select a k-step.
+__device__ __forceinline__ uint64_t x_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+constexpr uint32_t kXIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(XN >> 3) << 17) | ((uint32_t)(XM >> 4) << 24);
+__device__ __forceinline__ void x_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kXIdesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void x_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(x_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void x_sts(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float x_ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// round-to-nearest split: hi keeps 10 explicit mantissa bits (tf32), lo = v - hi is exact in fp32 and |lo| <= 2^-11 |v|
+__device__ __forceinline__ float x_tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+// walks the (item, live patch row) sequence of one CTA
+struct XCursor {
+    int item, r, rLo, rHi;
+    int b, cb, i0, j0;
+    __device__ __forceinline__ bool valid(const XPlan& p) const { return item < p.nItems; }
+    __device__ __forceinline__ void decode(const XPlan& p) {
+        if (item >= p.nItems) return;
+        const int tpi = p.tilesX * p.tilesY;
+        const int t = item % tpi;
+        const int rest = item / tpi;
+        cb = rest % p.nCb;
+        b = rest / p.nCb;
+        i0 = (t / p.tilesX) * XQROWS;
+        j0 = (t % p.tilesX) * XQCOLS;
+        const int nq = min(XQROWS, p.H - i0);           // live query rows of the tile
+        rLo = max(0, p.off - i0);                         // first patch row inside the image
+        rHi = min(min(XROWS, p.H + p.off - i0), nq + XTD - 1);  // one past the last row that is in the image and in a band
+        r = rLo;
+    }
+    __device__ __forceinline__ void start(const XPlan& p) { item = blockIdx.x; decode(p); }
+    __device__ __forceinline__ bool last() const { return r == rHi - 1; }
+    __device__ __forceinline__ void advance(const XPlan& p) {
+        if (++r >= rHi) { item += gridDim.x; decode(p); }
+    }
+};
+
+__global__ void __launch_bounds__(XTHREADS, 1)
+corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ xsrc, float* __restrict__ gout, XPlan p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[XSTAGES], bar_empty[XSTAGES], bar_acc_full, bar_acc_empty;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.H, W = p.W, C = p.C;
+    const size_t plane = (size_t)H * W;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(x_smem(&tmem_base_s)), "r"((uint32_t)XN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < XSTAGES; ++s) {
+            x_mbar_init(&bar_full[s], XPROD_WARPS);
+            x_mbar_init(&bar_empty[s], 1);
+        }
+        x_mbar_init(&bar_acc_full, 1);
+        x_mbar_init(&bar_acc_empty, XPROD_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    {
+        // ================================ producers / MMA issue / epilogue =================================
+        const uint32_t smemBase = x_smem(smem);
+        XCursor ld, st;
+        ld.start(p);
+        st.start(p);
+        uint32_t k = 0, t = 0;  // chunks stored, items finished
+
+        // chunk at cursor c -> registers: v[0..31] = B (channel 32*warp + j, key column lane), v[32..47] = A (query
+        // (warp, j), key column lane)
+        auto load = [&](float (&v)[XNB + XNA], const XCursor& c) {
+            const int gi = c.i0 - p.off + c.r, gj = c.j0 - p.off + lane;
+            const int c0 = c.cb * XN + warp * XNB;
+            const bool bok = lane < XQCOLS + XTD - 1 && gj >= 0 && gj < W;
+            const float* bp = xsrc + ((size_t)c.b * C + c0) * plane + (size_t)gi * W + gj;
+            const int nch = C - c0;
+#pragma unroll
+            for (int j = 0; j < XNB; ++j) v[j] = (bok && j < nch) ? x_ldg_stream(bp + (size_t)j * plane) : 0.f;
+            const int si = c.r - warp;  // row displacement of query row `warp` for this patch row (warp-uniform)
+            const bool aok = si >= 0 && si < XTD && c.i0 + warp < H;
+            const float* ap = gsrc + (((size_t)c.b * H + c.i0 + warp) * W + c.j0) * p.gMap + si * p.gRow + lane;
+#pragma unroll
+            for (int j = 0; j < XNA; ++j) {
+                const int sj = lane - j;
+                v[XNB + j] = (aok && sj >= 0 && sj < XTD && c.j0 + j < W) ? __ldg(ap + (size_t)j * p.gMap - j) : 0.f;
+            }
+        };
+        // registers -> (hi, lo) -> stage s.  Row `row` of an operand lives at (row>>3)*1024 + (row&7)*128, and its 16-byte
+        // chunks are XOR-swizzled with row&7: byte offset of key column `lane` = (4*lane) ^ ((row&7) << 4).
+        auto store = [&](const float (&v)[XNB + XNA], int s) {
+            const uint32_t stg = smemBase + (uint32_t)s * XSTAGE_BYTES;
+            const uint32_t aHi = stg + warp * (XNA * 128);
+            const uint32_t bHi = stg + 2 * XA_BYTES + warp * (XNB * 128);
+#pragma unroll
+            for (int j = 0; j < XNA; ++j) {
+                const float hi = x_tf32_rn(v[XNB + j]);
+                const uint32_t o = (j >> 3) * 1024 + (j & 7) * 128 + ((4 * lane) ^ ((j & 7) << 4));
+                x_sts(aHi + o, hi);
+                x_sts(aHi + XA_BYTES + o, v[XNB + j] - hi);
+            }
+#pragma unroll
+            for (int j = 0; j < XNB; ++j) {
+                const float hi = x_tf32_rn(v[j]);
+                const uint32_t o = (j >> 3) * 1024 + (j & 7) * 128 + ((4 * lane) ^ ((j & 7) << 4));
+                x_sts(bHi + o, hi);
+                x_sts(bHi + XB_BYTES + o, v[j] - hi);
+            }
+        };
+        // warp 0: all eight warps have staged chunk k -> issue its 12 MMAs
+        auto issue = [&](const XCursor& c, int s) {
+            if (c.r == c.rLo) x_mbar_wait(&bar_acc_empty, (t & 1u) ^ 1u);  // previous item's accumulators are drained
+            x_mbar_wait(&bar_full[s], (k >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t aHi = smemBase + (uint32_t)s * XSTAGE_BYTES, aLo = aHi + XA_BYTES;
+                const uint32_t bHi = aHi + 2 * XA_BYTES, bLo = bHi + XB_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte row
+                    x_mma(tmem_base, x_desc(aHi + ko), x_desc(bHi + ko), (c.r == c.rLo && ks == 0) ? 0u : 1u);
+                    x_mma(tmem_base, x_desc(aHi + ko), x_desc(bLo + ko), 1u);
+                    x_mma(tmem_base, x_desc(aLo + ko), x_desc(bHi + ko), 1u);
+                }
+                x_commit(&bar_empty[s]);
+                if (c.last()) x_commit(&bar_acc_full);
+            }
+            __syncwarp();
+        };
+        // accumulators of the finished item -> grad[b][c][position]
+        auto epilogue = [&](const XCursor& c) {
+            x_mbar_wait(&bar_acc_full, t & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int quarter = warp & 3, half = warp >> 2;
+            const int m = quarter * 32 + lane;
+            const int gi = c.i0 + (m >> 4), gj = c.j0 + (m & 15);
+            const bool pok = gi < H && gj < W;
+            const int cbase = c.cb * XN + half * (XN / 2);
+            float* dst = gout + ((size_t)c.b * C + cbase) * plane + (size_t)gi * W + gj;
+#pragma unroll 1
+            for (int q = 0; q < XN / 2 / 16; ++q) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (XN / 2) + q * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int nch = C - (cbase + q * 16);
+#pragma unroll
+                for (int x = 0; x < 16; ++x)
+                    if (pok && x < nch) dst[(size_t)(q * 16 + x) * plane] = __uint_as_float(r[x]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) x_mbar_arrive(&bar_acc_empty);
+            ++t;
+        };
+        auto step = [&](float (&v)[XNB + XNA]) {
+            const int s = (int)(k & 1u);
+            x_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);  // the MMAs that read this stage two chunks ago are done
+            store(v, s);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) x_mbar_arrive(&bar_full[s]);
+            if (warp == 0) issue(st, s);
+            ++k;
+            if (ld.valid(p)) {
+                load(v, ld);
+                ld.advance(p);
+            }
+            if (st.last()) epilogue(st);
+            st.advance(p);
+        };
+
+        float va[XNB + XNA], vb[XNB + XNA];
+        if (ld.valid(p)) { load(va, ld); ld.advance(p); }
+        if (ld.valid(p)) { load(vb, ld); ld.advance(p); }
+        while (st.valid(p)) {
+            step(va);
+            if (!st.valid(p)) break;
+            step(vb);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)XN));
+    }
+}
+
+// GT[b, p, si, sj] = gradOut[b, p + (si,sj) - 7, 15 - si, 15 - sj] if that query is inside the image, else 0.
+// One CTA per (b, query row xi): the row's W maps are staged in shared memory, then scattered to the <= 16 key rows
+// pi = xi + 7 - si they contribute to (64-byte runs).  xi runs over [-7, H + 7] so that out-of-image rows are zeroed.
+__global__ void __launch_bounds__(256)
+corr_bwd_flip_kernel(const float* __restrict__ go, float* __restrict__ gt, int B, int H, int W) {
+    extern __shared__ float fs[];
+    const int b = blockIdx.x / (H + 2 * (XD - 1) + 1);
+    const int xi = blockIdx.x % (H + 2 * (XD - 1) + 1) - (XD - 1);
+    const bool rowIn = xi >= 0 && xi < H;
+    if (rowIn) {
+        const float* src = go + ((size_t)b * H + xi) * W * XKK;
+        for (int e = threadIdx.x; e < W * XKK; e += blockDim.x) fs[(e / XKK) * XFLIP_PITCH + e % XKK] = src[e];
+    }
+    __syncthreads();
+    const int total = XTD * W * XTD;  // (si, pj, sj)
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int sj = e & 15, pj = (e >> 4) % W, si = (e >> 4) / W;
+        const int pi = xi + (XD - 1) - si;
+        if (pi < 0 || pi >= H) continue;
+        const int xj = pj + sj - (XD - 1);
+        float v = 0.f;
+        if (rowIn && xj >= 0 && xj < W) v = fs[xj * XFLIP_PITCH + (XTD - 1 - si) * XK1 + (XTD - 1 - sj)];
+        gt[((((size_t)b * H + pi) * W + pj) * XTD + si) * XTD + sj] = v;
+    }
+}
+
+}  // namespace
+
+bool corr_umma_bwd_supported(int B, int C, int H, int W, int d, int stride) {
+    if (stride != 1 || d != XD) return false;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return false;
+    if ((long long)B * C * H * W >= (1ll << 31)) return false;
+    if ((long long)B * H * W * XKK >= (1ll << 31)) return false;
+    if ((size_t)W * XFLIP_PITCH * sizeof(float) > 200 * 1024) return false;  // flip kernel stages one gradOut row
+    return true;
+}
+
+size_t corr_umma_bwd_ws_bytes(int B, int C, int H, int W) {
+    (void)C;
+    return (size_t)B * H * W * XTD * XTD * sizeof(float);
+}
+
+int corr_umma_bwd_launch(const float* go, const float* fm0, const float* fm1, float* g0, float* g1, int B, int C, int H,
+                         int W, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t need = corr_umma_bwd_ws_bytes(B, C, H, W);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("corr_bwd(umma): workspace too small (%zu < %zu)", ws_bytes, need);
+        return D2T_ERR_WORKSPACE;
+    }
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    float* gt = static_cast<float*>(ws);
+
+    XPlan p;
+    p.B = B; p.C = C; p.H = H; p.W = W;
+    p.tilesX = ceil_div(W, XQCOLS);
+    p.tilesY = ceil_div(H, XQROWS);
+    p.nCb = ceil_div(C, XN);
+    p.nItems = B * p.nCb * p.tilesX * p.tilesY;
+    const int grid = p.nItems < di.sm_count ? p.nItems : di.sm_count;
+    const size_t smem = (size_t)XSTAGES * XSTAGE_BYTES + 1024;
+    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    const size_t fsmem = (size_t)W * XFLIP_PITCH * sizeof(float);
+    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    corr_bwd_flip_kernel<<<B * (H + 2 * (XD - 1) + 1), 256, fsmem, st>>>(go, gt, B, H, W);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+
+    p.off = XD; p.gMap = XKK; p.gRow = XK1;              // grad_FM0: G = gradOut, X = FM1
+    corr_bwd_umma_kernel<<<grid, XTHREADS, smem, st>>>(go, fm1, g0, p);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    p.off = XD - 1; p.gMap = XTD * XTD; p.gRow = XTD;    // grad_FM1: G = flipped gradOut, X = FM0
+    corr_bwd_umma_kernel<<<grid, XTHREADS, smem, st>>>(gt, fm0, g1, p);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
+}  // namespace d2t

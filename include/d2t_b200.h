@@ -98,6 +98,16 @@ D2T_API int d2t_corr_bwd_f64(const double* grad_out, const double* fm0, const do
                      double* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,
                      size_t ws_bytes, void* stream);
 
+/* Tensor-core backward (tcgen05 + TMEM, 3xTF32 split with a round-to-nearest hi part; d_max = 8, stride = 1 only).
+ * Same contract as d2t_corr_bwd_f32 with its own workspace size (a flipped copy of grad_out, B*H*W*256 floats).  Each
+ * gradient element agrees with the exact sum to |err| <= 2e-6 * sum |grad_out * fm| over its 256 terms (measured 9e-7,
+ * tools/umma_sw128_test.cu) -- looser than the FP32-pipe kernel, inside rtol 1e-4 of the result's scale.  Bitwise
+ * reproducible run to run (no atomics).  d2t_corr_bwd_f32 dispatches here when D2T_CORR_BWD=umma. */
+D2T_API size_t d2t_corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int d_max, int stride);
+D2T_API int d2t_corr_bwd_f32_tc(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0,
+                        float* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,
+                        size_t ws_bytes, void* stream);
+
 /* ---- ROIPool (average pooling) ------------------------------
  * fm   : (C, H, W);  rois : (R, 4) same dtype;  out : (R, C, r_hw, r_hw)
  * Empty bins give 0/0 = NaN like the reference (F7).

@@ -112,6 +112,53 @@ def test_corr_fwd_tensor_core_variant(cuda, B, C, H, W):
     assert bool((out[ref == 0] == 0).all())
 
 
+@pytest.mark.parametrize("B,C,H,W", [(1, 96, 38, 63), (3, 40, 20, 21), (1, 16, 70, 66), (2, 300, 9, 17), (2, 2048, 38, 63)])
+def test_corr_bwd_tensor_core_variant(cuda, B, C, H, W):
+    """tcgen05 / 3xTF32 backward (d2t_corr_bwd_f32_tc).  Stated tolerance: |err| <= 2e-6 * sum |grad_out * fm| over the
+    element's terms (measured 9e-7, tools/umma_sw128_test.cu); checked against the float64 generic kernel, with the
+    magnitude sum obtained from the same kernel on absolute values.  Also bitwise reproducible."""
+    from detect_to_track_b200 import _lib
+    d = 8
+    g = torch.Generator(device="cpu").manual_seed(78)
+    fm0 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    fm1 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    go = torch.randn(B, H, W, 17, 17, generator=g).to(cuda)
+    lib = _lib.lib()
+    n = lib.d2t_corr_bwd_tc_workspace_bytes(B, C, H, W, d, 1)
+    assert n == B * H * W * 256 * 4
+    ws = torch.empty(n, dtype=torch.uint8, device=cuda)
+
+    def run():
+        g0, g1 = torch.full_like(fm0, float("nan")), torch.full_like(fm1, float("nan"))
+        rc = lib.d2t_corr_bwd_f32_tc(go.data_ptr(), fm0.data_ptr(), fm1.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, C, H, W,
+                                     d, 1, ws.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        return g0, g1
+
+    g0, g1 = run()
+    r0, r1 = pc_mod.pointwise_correlation_backward(go.double(), fm0.double(), fm1.double(), d, 1)
+    m0, m1 = pc_mod.pointwise_correlation_backward(go.double().abs(), fm0.double().abs(), fm1.double().abs(), d, 1)
+    for got, ref, mag in ((g0, r0, m0), (g1, r1, m1)):
+        err = (got.double() - ref).abs()
+        assert bool((err <= 2e-6 * mag + 1e-30).all()), float((err / (mag + 1e-30)).max())
+    # the op-level tolerance of the FP32 path (rtol 1e-4 at the result's scale) holds as well
+    close(g0, r0.cpu().numpy(), np.float32)
+    close(g1, r1.cpu().numpy(), np.float32)
+    h0, h1 = run()
+    assert torch.equal(g0, h0) and torch.equal(g1, h1)
+
+
+def test_corr_bwd_dispatch_env(cuda, monkeypatch):
+    """D2T_CORR_BWD selects the kernel family behind d2t_corr_bwd_f32; both agree within the FP32 tolerance."""
+    fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 72, 38, 63, 8, seed=15, dtype=np.float32))
+    monkeypatch.setenv("D2T_CORR_BWD", "simt")
+    a = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
+    monkeypatch.setenv("D2T_CORR_BWD", "umma")
+    b = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
+    close(b[0], a[0].cpu().numpy(), np.float32)
+    close(b[1], a[1].cpu().numpy(), np.float32)
+
+
 def test_corr_backward_is_deterministic(cuda):
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 64, 38, 63, 8, seed=13, dtype=np.float32))
     a = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
