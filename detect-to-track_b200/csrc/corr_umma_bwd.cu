@@ -24,9 +24,11 @@
 //              two conflict-free 128-byte-row STS per channel) and query row w of A.  Loads run two chunks ahead in
 //              registers, across item boundaries.  After the last chunk of an item they read the accumulators
 //              (tcgen05.ld) and store D[m][n] -> grad[b][n][position].
-//   warp 0     additionally issues the MMAs (one lane) once the stage's `full` barrier completes; tcgen05.commit ->
-//              `empty` barrier of the stage / `accum_full` of the item.  (A ninth warp would cap the kernel at 168
-//              registers per thread -- allocation is per 4 warps -- and spill the prefetch registers.)
+//   warp 8     issues the MMAs (one lane) once the stage's `full` barrier completes; tcgen05.commit -> `empty` barrier
+//              of the stage / `accum_full` of the item.  It must be a warp of its own: tcgen05.mma issue blocks while
+//              the tensor core's queue is full, and a producer warp that blocks there serialises staging and MMAs
+//              (measured: stage + MMA + handshake times added up exactly).  Registers are allocated per 4 warps, so the
+//              third warpgroup (warps 8-11) hands its registers to the producers with setmaxnreg (40 / 224).
 //   grad_FM1   needs gradOut transposed (the queries whose window contains a key): corr_bwd_flip_kernel writes
 //              GT[b,p,si,sj] = gradOut[b, p + (si,sj) - 7, 15 - si, 15 - sj] (0 outside the image) into the workspace
 //              once per call (42 MB of traffic at B = 8), so that both gradients use the same staging code.
@@ -47,7 +49,7 @@ constexpr int XN = 256;                   // channels per item = UMMA N = TMEM c
 constexpr int XQROWS = 8, XQCOLS = 16;
 constexpr int XROWS = XQROWS + XTD - 1;   // 23 patch rows
 constexpr int XPROD_WARPS = 8;
-constexpr int XTHREADS = XPROD_WARPS * 32;
+constexpr int XTHREADS = (XPROD_WARPS + 4) * 32;  // + one warpgroup: MMA issuer warp and three idle warps
 constexpr int XA_BYTES = XM * 128;        // one A operand (hi or lo) of a chunk
 constexpr int XB_BYTES = XN * 128;        // one B operand (hi or lo) of a chunk
 constexpr int XSTAGE_BYTES = 2 * XA_BYTES + 2 * XB_BYTES;
@@ -58,8 +60,7 @@ constexpr int XFLIP_PITCH = 290;          // shared-memory pitch of one gradOut 
 struct XPlan {
     int B, C, H, W;
     int tilesX, tilesY, nCb, nItems;
-    int off;          // 8 (grad_FM0) or 7 (grad_FM1)
-    int gMap, gRow;   // floats per position / per row displacement of the G source (289/17 or 256/16)
+    int dbg;  // experiment switches (D2T_UMMA_DBG; results are wrong when set): 1 = no staging stores, 2 = no MMAs, 4 = no loads
 };
 
 __device__ __forceinline__ uint32_t x_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,20 +102,23 @@ __device__ __forceinline__ void x_commit(uint64_t* bar) {
 __device__ __forceinline__ void x_sts(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ float x_ldg_stream(const float* p) {
+__device__ __forceinline__ float x_ldg_stream(uint64_t addr) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(addr));
     return v;
 }
 // round-to-nearest split: hi keeps 10 explicit mantissa bits (tf32), lo = v - hi is exact in fp32 and |lo| <= 2^-11 |v|
 __device__ __forceinline__ float x_tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+template <int V>
+struct XInt { static constexpr int value = V; };
 
 // walks the (item, live patch row) sequence of one CTA
 struct XCursor {
     int item, r, rLo, rHi;
     int b, cb, i0, j0;
     __device__ __forceinline__ bool valid(const XPlan& p) const { return item < p.nItems; }
-    __device__ __forceinline__ void decode(const XPlan& p) {
+    __device__ __forceinline__ void decode(const XPlan& p, int off) {
         if (item >= p.nItems) return;
         const int tpi = p.tilesX * p.tilesY;
         const int t = item % tpi;
@@ -124,19 +128,24 @@ struct XCursor {
         i0 = (t / p.tilesX) * XQROWS;
         j0 = (t % p.tilesX) * XQCOLS;
         const int nq = min(XQROWS, p.H - i0);           // live query rows of the tile
-        rLo = max(0, p.off - i0);                         // first patch row inside the image
-        rHi = min(min(XROWS, p.H + p.off - i0), nq + XTD - 1);  // one past the last row that is in the image and in a band
+        rLo = max(0, off - i0);                           // first patch row inside the image
+        rHi = min(min(XROWS, p.H + off - i0), nq + XTD - 1);  // one past the last row that is in the image and in a band
         r = rLo;
     }
-    __device__ __forceinline__ void start(const XPlan& p) { item = blockIdx.x; decode(p); }
+    __device__ __forceinline__ void start(const XPlan& p, int off) { item = blockIdx.x; decode(p, off); }
     __device__ __forceinline__ bool last() const { return r == rHi - 1; }
-    __device__ __forceinline__ void advance(const XPlan& p) {
-        if (++r >= rHi) { item += gridDim.x; decode(p); }
+    __device__ __forceinline__ void advance(const XPlan& p, int off) {
+        if (++r >= rHi) { item += gridDim.x; decode(p, off); }
     }
 };
 
+// MODE 0: grad_FM0 (G = gradOut, 17x17 maps, OFF = 8).  MODE 1: grad_FM1 (G = flipped gradOut, 16x16 maps, OFF = 7).
+template <int MODE>
 __global__ void __launch_bounds__(XTHREADS, 1)
 corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ xsrc, float* __restrict__ gout, XPlan p) {
+    constexpr int OFF = MODE == 0 ? XD : XD - 1;
+    constexpr int GMAP = MODE == 0 ? XKK : XTD * XTD;
+    constexpr int GROW = MODE == 0 ? XK1 : XTD;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bar_full[XSTAGES], bar_empty[XSTAGES], bar_acc_full, bar_acc_empty;
@@ -145,6 +154,7 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, C = p.C;
     const size_t plane = (size_t)H * W;
+    const uint64_t planeBytes = (uint64_t)plane * sizeof(float);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(x_smem(&tmem_base_s)), "r"((uint32_t)XN));
@@ -163,132 +173,187 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    const uint32_t smemBase = x_smem(smem);
 
-    {
-        // ================================ producers / MMA issue / epilogue =================================
-        const uint32_t smemBase = x_smem(smem);
-        XCursor ld, st;
-        ld.start(p);
-        st.start(p);
-        uint32_t k = 0, t = 0;  // chunks stored, items finished
+    // Row `row` of an operand lives at (row>>3)*1024 + (row&7)*128 and its 16-byte chunks are XOR-swizzled with row&7, so
+    // key column `lane` of a row with row&7 == t sits at byte (4*lane) ^ (t << 4).  This warp's rows start at a multiple
+    // of 8, so eight per-thread base addresses (stage 0) cover everything else with compile-time offsets.
+    uint32_t stsA[8], stsB[8];
+#pragma unroll
+    for (int t8 = 0; t8 < 8; ++t8) {
+        const uint32_t x = (uint32_t)((4 * lane) ^ (t8 << 4)) + t8 * 128;
+        stsA[t8] = smemBase + warp * (XNA * 128) + x;
+        stsB[t8] = smemBase + 2 * XA_BYTES + warp * (XNB * 128) + x;
+    }
+    // A element j of this lane is inside the band iff 0 <= lane - j < 16
+    uint32_t amask = 0;
+#pragma unroll
+    for (int j = 0; j < XNA; ++j) amask |= (lane - j >= 0 && lane - j < XTD) ? (1u << j) : 0u;
 
-        // chunk at cursor c -> registers: v[0..31] = B (channel 32*warp + j, key column lane), v[32..47] = A (query
-        // (warp, j), key column lane)
-        auto load = [&](float (&v)[XNB + XNA], const XCursor& c) {
-            const int gi = c.i0 - p.off + c.r, gj = c.j0 - p.off + lane;
-            const int c0 = c.cb * XN + warp * XNB;
-            const bool bok = lane < XQCOLS + XTD - 1 && gj >= 0 && gj < W;
-            const float* bp = xsrc + ((size_t)c.b * C + c0) * plane + (size_t)gi * W + gj;
-            const int nch = C - c0;
+    if (warp >= XPROD_WARPS) {
+        // ================================ MMA issuer (warp 8; warps 9-11 only donate registers) ================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::);
+        if (warp == XPROD_WARPS) {
+            XCursor c;
+            c.start(p, OFF);
+            uint32_t k = 0, t = 0;
+            while (c.valid(p)) {
+                const uint32_t s = k & 1u;
+                const bool first = c.r == c.rLo, last = c.last();
+                if (first) x_mbar_wait(&bar_acc_empty, (t & 1u) ^ 1u);  // previous item's accumulators are drained
+                x_mbar_wait(&bar_full[s], (k >> 1) & 1u);                // all eight producer warps have staged chunk k
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t aHi = smemBase + s * XSTAGE_BYTES, aLo = aHi + XA_BYTES;
+                    const uint32_t bHi = aHi + 2 * XA_BYTES, bLo = bHi + XB_BYTES;
 #pragma unroll
-            for (int j = 0; j < XNB; ++j) v[j] = (bok && j < nch) ? x_ldg_stream(bp + (size_t)j * plane) : 0.f;
-            const int si = c.r - warp;  // row displacement of query row `warp` for this patch row (warp-uniform)
-            const bool aok = si >= 0 && si < XTD && c.i0 + warp < H;
-            const float* ap = gsrc + (((size_t)c.b * H + c.i0 + warp) * W + c.j0) * p.gMap + si * p.gRow + lane;
-#pragma unroll
-            for (int j = 0; j < XNA; ++j) {
-                const int sj = lane - j;
-                v[XNB + j] = (aok && sj >= 0 && sj < XTD && c.j0 + j < W) ? __ldg(ap + (size_t)j * p.gMap - j) : 0.f;
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (p.dbg & 2) break;
+                        const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte row
+                        x_mma(tmem_base, x_desc(aHi + ko), x_desc(bHi + ko), (first && ks == 0) ? 0u : 1u);
+                        x_mma(tmem_base, x_desc(aHi + ko), x_desc(bLo + ko), 1u);
+                        x_mma(tmem_base, x_desc(aLo + ko), x_desc(bHi + ko), 1u);
+                    }
+                    x_commit(&bar_empty[s]);
+                    if (last) x_commit(&bar_acc_full);
+                }
+                __syncwarp();
+                if (last) ++t;
+                ++k;
+                c.advance(p, OFF);
             }
-        };
-        // registers -> (hi, lo) -> stage s.  Row `row` of an operand lives at (row>>3)*1024 + (row&7)*128, and its 16-byte
-        // chunks are XOR-swizzled with row&7: byte offset of key column `lane` = (4*lane) ^ ((row&7) << 4).
-        auto store = [&](const float (&v)[XNB + XNA], int s) {
-            const uint32_t stg = smemBase + (uint32_t)s * XSTAGE_BYTES;
-            const uint32_t aHi = stg + warp * (XNA * 128);
-            const uint32_t bHi = stg + 2 * XA_BYTES + warp * (XNB * 128);
+        }
+    } else {
+    // ================================ producers / epilogue (warps 0-7) =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n" ::);
+    XCursor ld, st;
+    ld.start(p, OFF);
+    st.start(p, OFF);
+    uint32_t k = 0, t = 0;  // chunks stored, items finished
+
+    // chunk at cursor c -> registers: v[0..31] = B (channel 32*warp + j, key column lane), v[32..47] = A (query
+    // (warp, j), key column lane)
+    auto load = [&](float (&v)[XNB + XNA], const XCursor& c) {
+        const int gi = c.i0 - OFF + c.r, gj = c.j0 - OFF + lane;
+        const int c0 = c.cb * XN + warp * XNB;
+        const bool bok = lane < XQCOLS + XTD - 1 && gj >= 0 && gj < W;
+        const int nch = C - c0;
+        // byte addresses, advanced one plane per channel (kept as integers so that the compiler does not fall back to
+        // element-index arithmetic: 2 instructions per load instead of 4)
+        uint64_t ba = (uint64_t)(xsrc + ((size_t)c.b * C + c0) * plane + (size_t)gi * W + gj);
+        if (p.dbg & 4) {
 #pragma unroll
-            for (int j = 0; j < XNA; ++j) {
-                const float hi = x_tf32_rn(v[XNB + j]);
-                const uint32_t o = (j >> 3) * 1024 + (j & 7) * 128 + ((4 * lane) ^ ((j & 7) << 4));
-                x_sts(aHi + o, hi);
-                x_sts(aHi + XA_BYTES + o, v[XNB + j] - hi);
-            }
+            for (int j = 0; j < XNB + XNA; ++j) v[j] = 0.f;
+            return;
+        }
+        if (bok && nch >= XNB) {
 #pragma unroll
             for (int j = 0; j < XNB; ++j) {
-                const float hi = x_tf32_rn(v[j]);
-                const uint32_t o = (j >> 3) * 1024 + (j & 7) * 128 + ((4 * lane) ^ ((j & 7) << 4));
-                x_sts(bHi + o, hi);
-                x_sts(bHi + XB_BYTES + o, v[j] - hi);
+                v[j] = x_ldg_stream(ba);
+                ba += planeBytes;
             }
-        };
-        // warp 0: all eight warps have staged chunk k -> issue its 12 MMAs
-        auto issue = [&](const XCursor& c, int s) {
-            if (c.r == c.rLo) x_mbar_wait(&bar_acc_empty, (t & 1u) ^ 1u);  // previous item's accumulators are drained
-            x_mbar_wait(&bar_full[s], (k >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t aHi = smemBase + (uint32_t)s * XSTAGE_BYTES, aLo = aHi + XA_BYTES;
-                const uint32_t bHi = aHi + 2 * XA_BYTES, bLo = bHi + XB_BYTES;
+        } else {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte row
-                    x_mma(tmem_base, x_desc(aHi + ko), x_desc(bHi + ko), (c.r == c.rLo && ks == 0) ? 0u : 1u);
-                    x_mma(tmem_base, x_desc(aHi + ko), x_desc(bLo + ko), 1u);
-                    x_mma(tmem_base, x_desc(aLo + ko), x_desc(bHi + ko), 1u);
-                }
-                x_commit(&bar_empty[s]);
-                if (c.last()) x_commit(&bar_acc_full);
+            for (int j = 0; j < XNB; ++j) {
+                v[j] = (bok && j < nch) ? x_ldg_stream(ba) : 0.f;
+                ba += planeBytes;
             }
-            __syncwarp();
-        };
-        // accumulators of the finished item -> grad[b][c][position]
-        auto epilogue = [&](const XCursor& c) {
-            x_mbar_wait(&bar_acc_full, t & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int quarter = warp & 3, half = warp >> 2;
-            const int m = quarter * 32 + lane;
-            const int gi = c.i0 + (m >> 4), gj = c.j0 + (m & 15);
-            const bool pok = gi < H && gj < W;
-            const int cbase = c.cb * XN + half * (XN / 2);
-            float* dst = gout + ((size_t)c.b * C + cbase) * plane + (size_t)gi * W + gj;
-#pragma unroll 1
-            for (int q = 0; q < XN / 2 / 16; ++q) {
-                uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (XN / 2) + q * 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-                    "%15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int nch = C - (cbase + q * 16);
-#pragma unroll
-                for (int x = 0; x < 16; ++x)
-                    if (pok && x < nch) dst[(size_t)(q * 16 + x) * plane] = __uint_as_float(r[x]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) x_mbar_arrive(&bar_acc_empty);
-            ++t;
-        };
-        auto step = [&](float (&v)[XNB + XNA]) {
-            const int s = (int)(k & 1u);
-            x_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);  // the MMAs that read this stage two chunks ago are done
-            store(v, s);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) x_mbar_arrive(&bar_full[s]);
-            if (warp == 0) issue(st, s);
-            ++k;
-            if (ld.valid(p)) {
-                load(v, ld);
-                ld.advance(p);
-            }
-            if (st.last()) epilogue(st);
-            st.advance(p);
-        };
-
-        float va[XNB + XNA], vb[XNB + XNA];
-        if (ld.valid(p)) { load(va, ld); ld.advance(p); }
-        if (ld.valid(p)) { load(vb, ld); ld.advance(p); }
-        while (st.valid(p)) {
-            step(va);
-            if (!st.valid(p)) break;
-            step(vb);
         }
+        const int si = c.r - warp;  // row displacement of query row `warp` for this patch row (warp-uniform)
+        uint32_t m = 0;
+        if (si >= 0 && si < XTD && c.i0 + warp < H) {
+            const int nc = W - c.j0;
+            m = nc < XQCOLS ? (amask & ((1u << nc) - 1u)) : amask;
+        }
+        const float* ap = gsrc + (((size_t)c.b * H + c.i0 + warp) * W + c.j0) * GMAP + si * GROW + lane;
+#pragma unroll
+        for (int j = 0; j < XNA; ++j) v[XNB + j] = ((m >> j) & 1u) ? __ldg(ap + j * (GMAP - 1)) : 0.f;
+    };
+    // registers -> (hi, lo) -> stage S
+    auto store = [&](const float (&v)[XNB + XNA], auto S) {
+        constexpr uint32_t so = decltype(S)::value * XSTAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < XNA; ++j) {
+            const float hi = x_tf32_rn(v[XNB + j]);
+            const uint32_t ad = stsA[j & 7] + so + (j >> 3) * 1024;
+            x_sts(ad, hi);
+            x_sts(ad + XA_BYTES, v[XNB + j] - hi);
+        }
+#pragma unroll
+        for (int j = 0; j < XNB; ++j) {
+            const float hi = x_tf32_rn(v[j]);
+            const uint32_t ad = stsB[j & 7] + so + (j >> 3) * 1024;
+            x_sts(ad, hi);
+            x_sts(ad + XB_BYTES, v[j] - hi);
+        }
+    };
+    // accumulators of the finished item -> grad[b][c][position]
+    auto epilogue = [&](const XCursor& c) {
+        x_mbar_wait(&bar_acc_full, t & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3, half = warp >> 2;
+        const int m = quarter * 32 + lane;
+        const int gi = c.i0 + (m >> 4), gj = c.j0 + (m & 15);
+        const bool pok = gi < H && gj < W;
+        const int cbase = c.cb * XN + half * (XN / 2);
+        float* dst = gout + ((size_t)c.b * C + cbase) * plane + (size_t)gi * W + gj;
+#pragma unroll 1
+        for (int q = 0; q < XN / 2 / 16; ++q) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (XN / 2) + q * 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                "%15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int nch = C - (cbase + q * 16);
+            if (pok) {
+                if (nch >= 16) {
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) {
+                        *dst = __uint_as_float(r[x]);
+                        dst += plane;
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 16; ++x)
+                        if (x < nch) dst[(size_t)x * plane] = __uint_as_float(r[x]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) x_mbar_arrive(&bar_acc_empty);
+        ++t;
+    };
+    auto step = [&](float (&v)[XNB + XNA], auto S) {
+        constexpr int s = decltype(S)::value;
+        x_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);  // the MMAs that read this stage two chunks ago are done
+        if (!(p.dbg & 1)) store(v, S);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) x_mbar_arrive(&bar_full[s]);
+        ++k;
+        if (ld.valid(p)) {
+            load(v, ld);
+            ld.advance(p, OFF);
+        }
+        if (st.last()) epilogue(st);
+        st.advance(p, OFF);
+    };
+
+    // chunk k always uses stage k & 1, so the two register sets are tied to one stage each
+    float va[XNB + XNA], vb[XNB + XNA];
+    if (ld.valid(p)) { load(va, ld); ld.advance(p, OFF); }
+    if (ld.valid(p)) { load(vb, ld); ld.advance(p, OFF); }
+    while (st.valid(p)) {
+        step(va, XInt<0>{});
+        if (!st.valid(p)) break;
+        step(vb, XInt<1>{});
     }
+    }  // producers
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -358,9 +423,12 @@ int corr_umma_bwd_launch(const float* go, const float* fm0, const float* fm1, fl
     p.tilesY = ceil_div(H, XQROWS);
     p.nCb = ceil_div(C, XN);
     p.nItems = B * p.nCb * p.tilesX * p.tilesY;
+    p.dbg = 0;
+    if (const char* e = getenv("D2T_UMMA_DBG")) p.dbg = atoi(e);
     const int grid = p.nItems < di.sm_count ? p.nItems : di.sm_count;
     const size_t smem = (size_t)XSTAGES * XSTAGE_BYTES + 1024;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     const size_t fsmem = (size_t)W * XFLIP_PITCH * sizeof(float);
     D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
@@ -368,12 +436,10 @@ int corr_umma_bwd_launch(const float* go, const float* fm0, const float* fm1, fl
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
 
-    p.off = XD; p.gMap = XKK; p.gRow = XK1;              // grad_FM0: G = gradOut, X = FM1
-    corr_bwd_umma_kernel<<<grid, XTHREADS, smem, st>>>(go, fm1, g0, p);
+    corr_bwd_umma_kernel<0><<<grid, XTHREADS, smem, st>>>(go, fm1, g0, p);   // grad_FM0: G = gradOut, X = FM1
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
-    p.off = XD - 1; p.gMap = XTD * XTD; p.gRow = XTD;    // grad_FM1: G = flipped gradOut, X = FM0
-    corr_bwd_umma_kernel<<<grid, XTHREADS, smem, st>>>(gt, fm0, g1, p);
+    corr_bwd_umma_kernel<1><<<grid, XTHREADS, smem, st>>>(gt, fm0, g1, p);   // grad_FM1: G = flipped gradOut, X = FM0
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;
