@@ -52,7 +52,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-constexpr bool kCorrBwdDefaultUmma = false;  // default backward family when D2T_CORR_BWD is unset
+constexpr int kCorrBwdUmmaMinItems = 80;  // tensor-core backward by default from this many work items
 constexpr int kStages = 3;  // operand ring depth (cp.async groups in flight: kStages - 1)
 
 
@@ -512,7 +512,11 @@ static bool use_umma_bwd(int B, int C, int H, int W, int d) {
     const char* e = getenv("D2T_CORR_BWD");
     if (e && strcmp(e, "umma") == 0) return true;
     if (e && strcmp(e, "simt") == 0) return false;
-    return kCorrBwdDefaultUmma;
+    // default: the tensor-core kernel once there are enough (tile, 256-channel block) work items to fill the SMs.
+    // Measured on B200 (38x63, d=8; profiles/r1_time_ops_v4.txt): B=8 c3/c4/c5 253/386/620 us against 437/861/1729 us for
+    // the FP32-pipe kernel; B=1: c4 112 vs 142, c5 185 vs 236, but c3 (40 items) 112 vs 95.
+    const long long items = (long long)B * ceil_div(C, 256) * ceil_div(H, 8) * ceil_div(W, 16);
+    return items >= kCorrBwdUmmaMinItems;
 }
 size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d) {
     return use_umma_bwd(B, C, H, W, d) ? corr_umma_bwd_ws_bytes(B, C, H, W) : 0;

@@ -55,6 +55,7 @@ constexpr int XB_BYTES = XN * 128;        // one B operand (hi or lo) of a chunk
 constexpr int XSTAGE_BYTES = 2 * XA_BYTES + 2 * XB_BYTES;
 constexpr int XSTAGES = 2;
 constexpr int XNA = XQCOLS, XNB = XN / XPROD_WARPS;  // A / B elements a producer thread stages per chunk
+constexpr int XFLIP_THREADS = 512;
 constexpr int XFLIP_PITCH = 290;          // shared-memory pitch of one gradOut map in the flip kernel
 
 struct XPlan {
@@ -344,7 +345,8 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
         st.advance(p, OFF);
     };
 
-    // chunk k always uses stage k & 1, so the two register sets are tied to one stage each
+    // chunk k always uses stage k & 1, so the two register sets are tied to one stage each.  (A third set, loads three
+    // chunks ahead, was measured slower: the loads are bound by L1 throughput, not latency.)
     float va[XNB + XNA], vb[XNB + XNA];
     if (ld.valid(p)) { load(va, ld); ld.advance(p, OFF); }
     if (ld.valid(p)) { load(vb, ld); ld.advance(p, OFF); }
@@ -366,26 +368,38 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
 // GT[b, p, si, sj] = gradOut[b, p + (si,sj) - 7, 15 - si, 15 - sj] if that query is inside the image, else 0.
 // One CTA per (b, query row xi): the row's W maps are staged in shared memory, then scattered to the <= 16 key rows
 // pi = xi + 7 - si they contribute to (64-byte runs).  xi runs over [-7, H + 7] so that out-of-image rows are zeroed.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(XFLIP_THREADS)
 corr_bwd_flip_kernel(const float* __restrict__ go, float* __restrict__ gt, int B, int H, int W) {
     extern __shared__ float fs[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x / (H + 2 * (XD - 1) + 1);
     const int xi = blockIdx.x % (H + 2 * (XD - 1) + 1) - (XD - 1);
     const bool rowIn = xi >= 0 && xi < H;
-    if (rowIn) {
+    if (rowIn) {  // warp per map: 289 contiguous floats -> fs[xj][0..288]
         const float* src = go + ((size_t)b * H + xi) * W * XKK;
-        for (int e = threadIdx.x; e < W * XKK; e += blockDim.x) fs[(e / XKK) * XFLIP_PITCH + e % XKK] = src[e];
+        for (int xj = warp; xj < W; xj += XFLIP_THREADS / 32) {
+            const float* m = src + (size_t)xj * XKK;
+            float* d = fs + xj * XFLIP_PITCH;
+#pragma unroll
+            for (int u = 0; u < (XKK + 31) / 32; ++u) {
+                const int e = lane + 32 * u;
+                if (e < XKK) d[e] = __ldg(m + e);
+            }
+        }
     }
     __syncthreads();
-    const int total = XTD * W * XTD;  // (si, pj, sj)
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int sj = e & 15, pj = (e >> 4) % W, si = (e >> 4) / W;
+    for (int si = 0; si < XTD; ++si) {
         const int pi = xi + (XD - 1) - si;
         if (pi < 0 || pi >= H) continue;
-        const int xj = pj + sj - (XD - 1);
-        float v = 0.f;
-        if (rowIn && xj >= 0 && xj < W) v = fs[xj * XFLIP_PITCH + (XTD - 1 - si) * XK1 + (XTD - 1 - sj)];
-        gt[((((size_t)b * H + pi) * W + pj) * XTD + si) * XTD + sj] = v;
+        float* dst = gt + (((size_t)b * H + pi) * W * XTD + si) * XTD;   // + pj * 256 + sj
+        const float* srow = fs + (XTD - 1 - si) * XK1 + (XTD - 1);
+        for (int e = threadIdx.x; e < W * XTD; e += XFLIP_THREADS) {
+            const int pj = e >> 4, sj = e & 15;
+            const int xj = pj + sj - (XD - 1);
+            float v = 0.f;
+            if (rowIn && xj >= 0 && xj < W) v = srow[xj * XFLIP_PITCH - sj];
+            dst[(size_t)pj * (XTD * XTD) + sj] = v;
+        }
     }
 }
 
@@ -432,7 +446,7 @@ int corr_umma_bwd_launch(const float* go, const float* fm0, const float* fm1, fl
 
     const size_t fsmem = (size_t)W * XFLIP_PITCH * sizeof(float);
     D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    corr_bwd_flip_kernel<<<B * (H + 2 * (XD - 1) + 1), 256, fsmem, st>>>(go, gt, B, H, W);
+    corr_bwd_flip_kernel<<<B * (H + 2 * (XD - 1) + 1), XFLIP_THREADS, fsmem, st>>>(go, gt, B, H, W);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
 
