@@ -393,10 +393,30 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
     h2d = sum(t.numel() * t.element_size() for it in host for v in it.values() for t in v)
     loss_host = torch.zeros(1).pin_memory()
 
-    def one_step():
-        total = torch.zeros((), device=dev)
-        for it in host:
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def upload(it):
+        """pair -> device on the copy stream (pinned host memory, asynchronous); returns (tensors, ready-event)"""
+        with torch.cuda.stream(copy_stream):
             d = {k: [t.to(dev, non_blocking=True) for t in v] for k, v in it.items()}
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        return d, ready
+
+    def one_step():
+        # the upload of pair n+1 runs on the copy stream while pair n is computed (what a data loader with a
+        # prefetch depth of one does); every byte still crosses PCIe inside the timed region
+        main = torch.cuda.current_stream(dev)
+        total = torch.zeros((), device=dev)
+        nxt = upload(host[0])
+        for n in range(len(host)):
+            d, ready = nxt
+            if n + 1 < len(host):
+                nxt = upload(host[n + 1])
+            main.wait_event(ready)
+            for v in d.values():
+                for t in v:
+                    t.record_stream(main)
             for k in ("c3", "c4", "c5", "reg", "cls_map", "reg_map"):
                 for t in d[k]:
                     t.requires_grad_(True)
@@ -410,7 +430,7 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
             loss.backward()
             total = total + loss.detach()
         loss_host.copy_(total.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
         return float(loss_host[0])
 
     one_step()

@@ -205,7 +205,7 @@ roipool_vec_fwd_kernel(const float* __restrict__ fm, const float* __restrict__ r
 // ----------------------------------------------------------------------------------------------------
 // backward
 // ----------------------------------------------------------------------------------------------------
-// smem: D[H][rowPitch] | gstage[2][RG][16][SP] | edges[RCH][K] | simple[RCH] | cover[2][H][RG] | counter[2]
+// smem: D[H][rowPitch] | gstage[2][RG][KK][16] | edges[RCH][K] | simple[RCH] | cover[2][H][RG] | off[2][RG][32] | counter[2]
 //
 // Work unit = (RoI group, pixel row).  Within a group every pixel row is claimed by exactly one warp (dynamic queue),
 // which applies the group's RoIs to that row in ascending RoI order; groups are separated by one CTA barrier.  So each
@@ -226,27 +226,21 @@ roipool_vec_bwd_kernel(const float* __restrict__ go, const float* __restrict__ r
     uint32_t* edgeS = reinterpret_cast<uint32_t*>(gS + 2 * GSZ);                 // [kVecRChunk][K]
     unsigned char* simpleS = reinterpret_cast<unsigned char*>(edgeS + kVecRChunk * K);  // [kVecRChunk]
     unsigned char* coverS = simpleS + kVecRChunk;                                // [2][H][RG], 8-byte aligned rows
-    int* counter = reinterpret_cast<int*>(coverS + (size_t)2 * ((H * RG + 15) / 16 * 16));
+    uint32_t* offS = reinterpret_cast<uint32_t*>(coverS + (size_t)2 * ((H * RG + 15) / 16 * 16));  // [2][RG][32]
+    int* counter = reinterpret_cast<int*>(offS + 2 * RG * 32);
+    constexpr int NITEM = 4;  // (RoI, quad, bin) staging items per thread and group: the host guarantees 4 * threads >= RG * 4 * KK
 
     const int NT = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int c0 = blockIdx.x * CB;
     const int cb = min(CB, C - c0);
     const int HW = H * W;
-    const int nRun = cb * KK;  // floats of grad_out per RoI for this slab (contiguous in global memory)
     const int coverBuf = (H * RG + 15) / 16 * 16;
 
     for (int idx = tid; idx < H * rowPitch / 4; idx += NT) st4(D + idx * 4, make_float4(0.f, 0.f, 0.f, 0.f));
 
-    // staging map: element e of a RoI's run -> offset inside the RoI's stage block; up to 2 elements per thread
-    // (the host guarantees 2 * NT >= 16 * KK)
-    const int e0 = tid, e1 = tid + NT;
-    const int so0 = (e0 / KK) * SP + e0 % KK, so1 = (e1 / KK) * SP + e1 % KK;
-    const bool has0 = e0 < nRun, has1 = e1 < nRun;
-
     const int j = lane >> 2, q = lane & 3;
     const bool jact = j < K;
-    const int jc = jact ? j : K - 1;
 
     for (int rc0 = 0; rc0 < R; rc0 += kVecRChunk) {  // RoI chunks: one edge table each (a single chunk for R <= 512)
         const int nrc = min(kVecRChunk, R - rc0);
@@ -268,27 +262,56 @@ roipool_vec_bwd_kernel(const float* __restrict__ go, const float* __restrict__ r
             simpleS[rr] = simple ? 1 : 0;
         }
 
-        float pre0[RG], pre1[RG];
+        // ---- staging of grad_out, pre-scaled and transposed ------------------------------------------------------
+        // An item is (RoI rr of the group, channel quad qq, bin): 4 coalesced loads (lanes = consecutive bins of one
+        // channel), scaled by 1 / (bin rows x bin columns) (0 for an empty bin), one STS.128 into
+        //   gS[buf][rr][bin][slot], slot = qq ^ (j & 3)   (16-byte slots; j = bin column)
+        // so that lane (j, q) of the update loop reads its four channels of bin (i, j) with ONE conflict-free LDS.128
+        // and needs no edge arithmetic or reciprocal per pixel row.
+        int itRR[NITEM], itBin[NITEM], itQ[NITEM];
+#pragma unroll
+        for (int n = 0; n < NITEM; ++n) {
+            const int it = tid + n * NT;
+            itRR[n] = it / (4 * KK);
+            const int rem = it - itRR[n] * (4 * KK);
+            itQ[n] = rem / KK;
+            itBin[n] = rem - itQ[n] * KK;
+            if (itRR[n] >= RG) itRR[n] = -1;
+        }
+        float4 pre[NITEM];
         auto prefetch = [&](int grp) {
             const int r0 = rc0 + grp * RG;
 #pragma unroll
-            for (int rr = 0; rr < RG; ++rr) {
-                const bool ok = grp * RG + rr < nrc;
-                const float* src = go + ((size_t)(ok ? r0 + rr : rc0) * C + c0) * KK;
-                pre0[rr] = (ok && has0) ? __ldg(src + e0) : 0.f;
-                pre1[rr] = (ok && has1) ? __ldg(src + e1) : 0.f;
+            for (int n = 0; n < NITEM; ++n) {
+                const int rr = itRR[n];
+                const bool ok = rr >= 0 && grp * RG + rr < nrc;
+                const int ch = 4 * itQ[n];
+                const float* src = go + ((size_t)(ok ? r0 + rr : rc0) * C + c0 + ch) * KK + itBin[n];
+                pre[n].x = (ok && ch + 0 < cb) ? __ldg(src) : 0.f;
+                pre[n].y = (ok && ch + 1 < cb) ? __ldg(src + KK) : 0.f;
+                pre[n].z = (ok && ch + 2 < cb) ? __ldg(src + 2 * KK) : 0.f;
+                pre[n].w = (ok && ch + 3 < cb) ? __ldg(src + 3 * KK) : 0.f;
             }
         };
-        // stage the prefetched grad_out of group `grp` and build its row cover masks:
-        // cover[y][rr] bit i set <=> bin row i of RoI rr contains pixel row y
+        // stage the prefetched grad_out of group `grp`; build its row cover masks
+        // (cover[y][rr] bit i set <=> bin row i of RoI rr contains pixel row y) and its per-lane update offsets
         auto commit = [&](int grp, int buf) {
             float* g = gS + buf * GSZ;
-#pragma unroll
-            for (int rr = 0; rr < RG; ++rr) {
-                if (has0) g[rr * kVecSlots * SP + so0] = pre0[rr];
-                if (has1) g[rr * kVecSlots * SP + so1] = pre1[rr];
-            }
             const int nr = min(RG, nrc - grp * RG);
+#pragma unroll
+            for (int n = 0; n < NITEM; ++n) {
+                const int rr = itRR[n];
+                if (rr < 0 || rr >= nr) continue;
+                const int bi = itBin[n] / K, bj = itBin[n] - bi * K;
+                const uint32_t* ed = edgeS + (grp * RG + rr) * K;
+                const uint32_t ei = ed[bi], ej = ed[bj];
+                const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
+                const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
+                const float inv = (hI > 0 && wJ > 0) ? rcp_approx((float)(hI * wJ)) : 0.f;
+                float4 v = pre[n];
+                v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+                st4(g + ((rr * KK + itBin[n]) * 4 + (itQ[n] ^ (bj & 3))) * 4, v);
+            }
             for (int idx = tid; idx < H * RG; idx += NT) {
                 const int y = idx / RG, rr = idx - y * RG;
                 unsigned m = 0;
@@ -303,19 +326,34 @@ roipool_vec_bwd_kernel(const float* __restrict__ go, const float* __restrict__ r
                 }
                 coverS[buf * coverBuf + idx] = (unsigned char)m;
             }
+            // per (RoI, lane): byte offsets inside a D row of the lane's two updates (+t at J0_j, -t at J1_j), bit 31 = simple
+            for (int idx = tid; idx < RG * 32; idx += NT) {
+                const int rr = idx >> 5, ln = idx & 31;
+                uint32_t w = 0;
+                if (rr < nr) {
+                    const int jj = min(ln >> 2, K - 1), qq = ln & 3;
+                    const uint32_t ej = edgeS[(grp * RG + rr) * K + jj];
+                    const int J0 = (ej >> 16) & 255, J1 = ej >> 24;
+                    w = (uint32_t)(vec_pix_off(J0, qq) * 4) | ((uint32_t)(vec_pix_off(J1, qq) * 4) << 14) |
+                        (simpleS[grp * RG + rr] ? 0x80000000u : 0u);
+                }
+                offS[buf * RG * 32 + idx] = w;
+            }
             if (tid == 0) counter[buf] = 0;
         };
 
         const int nGroups = (nrc + RG - 1) / RG;
         prefetch(0);
         commit(0, 0);
+        const int laneG = jact ? (j * 4 + (q ^ (j & 3))) * 4 : 0;  // float offset of this lane's slot inside a bin row
 
         for (int grp = 0; grp < nGroups; ++grp) {
             const int buf = grp & 1;
-            __syncthreads();  // stage / cover / counter of `buf` complete; everyone is done with group grp-1
+            __syncthreads();  // stage / cover / offsets / counter of `buf` complete; everyone is done with group grp-1
             if (grp + 1 < nGroups) prefetch(grp + 1);
-            const float* gB = gS + buf * GSZ;
+            const float* gB = gS + buf * GSZ + laneG;
             const unsigned char* cov = coverS + buf * coverBuf;
+            const uint32_t* offB = offS + buf * RG * 32 + lane;
             while (true) {
                 int task = 0;
                 if (lane == 0) task = atomicAdd(&counter[buf], 1);
@@ -326,38 +364,24 @@ roipool_vec_bwd_kernel(const float* __restrict__ go, const float* __restrict__ r
                 const int cRow = H >> 1, U2 = 2 * (H - 1 - cRow);
                 const int y = task < U2 ? ((task & 1) ? cRow + 1 + (task >> 1) : cRow - (task >> 1))
                                         : cRow - (U2 >> 1) - (task - U2);
-                const unsigned long long masks = *reinterpret_cast<const unsigned long long*>(cov + y * RG);
-                if (masks == 0ull) continue;
-                float* row = D + y * rowPitch;
-#pragma unroll 1
-                for (int rr = 0; rr < RG; ++rr) {
+                unsigned long long masks = *reinterpret_cast<const unsigned long long*>(cov + y * RG);
+                char* row = reinterpret_cast<char*>(D + y * rowPitch);
+                while (masks != 0ull) {  // RoIs of the group that cover this row, in ascending order
+                    const int rr = (__ffsll((long long)masks) - 1) >> 3;
                     unsigned cover = (unsigned)(masks >> (8 * rr)) & 0xffu;
-                    if (cover == 0) continue;
-                    const int rl = grp * RG + rr;  // RoI index inside the chunk
-                    const uint32_t* ed = edgeS + rl * K;
-                    const uint32_t ej = ed[jc];
-                    const int J0 = (ej >> 16) & 255, J1 = ej >> 24;
-                    const int wj = J1 - J0;
-                    const bool simple = simpleS[rl] != 0;
-                    const float* gR = gB + rr * kVecSlots * SP + (4 * q) * SP + j;
+                    masks &= ~(0xffull << (8 * rr));
+                    const uint32_t w = offB[rr * 32];
+                    const float* gR = gB + rr * (KK * 16);
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    while (cover) {
+                    while (cover) {  // bin rows containing y (1, or 2 where floor/ceil edges overlap)
                         const int i = __ffs(cover) - 1;
                         cover &= cover - 1;
-                        const uint32_t ei = ed[i];
-                        const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
-                        if (jact && wj > 0) {
-                            const float inv = rcp_approx((float)(hI * wj));
-                            const float* g = gR + i * K;
-                            t.x = fmaf(g[0], inv, t.x);
-                            t.y = fmaf(g[SP], inv, t.y);
-                            t.z = fmaf(g[2 * SP], inv, t.z);
-                            t.w = fmaf(g[3 * SP], inv, t.w);
-                        }
+                        const float4 v = ld4(gR + i * (K * 16));
+                        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
                     }
-                    float* pA = row + vec_pix_off(J0, q);
-                    float* pB = row + vec_pix_off(J1, q);
-                    if (simple) {
+                    float* pA = reinterpret_cast<float*>(row + (w & 0x3fffu));
+                    float* pB = reinterpret_cast<float*>(row + ((w >> 14) & 0x3fffu));
+                    if (w & 0x80000000u) {
                         if (jact) {
                             float4 a = ld4(pA);
                             a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
@@ -447,7 +471,8 @@ static size_t vec_fwd_smem(int H, int W, int k) {
 static size_t vec_bwd_smem(int H, int W, int k) {
     const int SP = vec_stage_pitch(k * k);
     return (size_t)H * vec_row_pitch(W) * sizeof(float) + (size_t)2 * kVecBwdRG * kVecSlots * SP * sizeof(float) +
-           (size_t)kVecRChunk * k * sizeof(uint32_t) + kVecRChunk + (size_t)2 * ((H * kVecBwdRG + 15) / 16 * 16) + 16;
+           (size_t)kVecRChunk * k * sizeof(uint32_t) + kVecRChunk + (size_t)2 * ((H * kVecBwdRG + 15) / 16 * 16) +
+           (size_t)2 * kVecBwdRG * 32 * sizeof(uint32_t) + 16;
 }
 static int vec_bwd_warps(int H) {
     const int rowsPerWarp = ceil_div(H, kVecBwdMaxWarps);
@@ -468,7 +493,7 @@ bool roipool_vec_supported(int R, int C, int H, int W, int k) {
     // backward staging map: two elements per thread must cover a RoI's 16*k*k floats
     int nw = vec_bwd_warps(H);
     if (nw < 13) nw = 13;
-    return 2 * nw * 32 >= kVecSlots * k * k;
+    return 4 * nw * 32 >= kVecBwdRG * 4 * k * k;  // backward staging: 4 items per thread cover a group
 }
 
 int roipool_vec_fwd_launch(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int k,
@@ -494,7 +519,7 @@ int roipool_vec_bwd_launch(const float* go, const float* rois, float* gin, int R
     const int CB = vec_pick_cb(C, di.sm_count);
     const size_t smem = vec_bwd_smem(H, W, k);
     int nw = vec_bwd_warps(H);
-    if (nw < 13) nw = 13;  // staging needs 2 * threads >= 16 * 49
+    if (nw < 13) nw = 13;  // staging needs 4 * threads >= 8 * 4 * 49
     auto kern = roipool_vec_bwd_kernel<7>;
     D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ceil_div(C, CB), nw * 32, smem, st>>>(go, rois, gin, R, C, H, W, CB);
