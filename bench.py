@@ -232,26 +232,31 @@ def run_ours(args):
 
     inp = build_device_inputs(torch, dev, 1234 + rank)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    dom = {"e0": [], "e1": []}  # events around the dominant kernel pair (corr bwd, c5)
+    dom = {}  # CUDA events around the kernels reported in `roofline` / `roofline_other`
+
+    def timed(key, record, fn):
+        if not record:
+            return fn()
+        a, b = ev(), ev()
+        a.record()
+        r = fn()
+        b.record()
+        dom.setdefault(key, []).append((a, b))
+        return r
 
     def step(record_dom=False):
         keep = []
         for idx, (fm0, fm1, go) in enumerate(inp["corr"]):
-            keep.append(pc.pointwise_correlation_forward(fm0, fm1, D, 1))
-            if record_dom and idx == 2:
-                a, b = ev(), ev()
-                a.record()
-                keep.append(pc.pointwise_correlation_backward(go, fm0, fm1, D, 1))
-                b.record()
-                dom["e0"].append(a); dom["e1"].append(b)
-            else:
-                keep.append(pc.pointwise_correlation_backward(go, fm0, fm1, D, 1))
+            rec = record_dom and idx == 2                      # c5: C = 2048
+            keep.append(timed("corr_fwd", rec, lambda: pc.pointwise_correlation_forward(fm0, fm1, D, 1)))
+            keep.append(timed("corr_bwd", rec, lambda: pc.pointwise_correlation_backward(go, fm0, fm1, D, 1)))
         for nT, fm, rois, go in inp["ps"]:   # all 2*B frames of the shard in one set of launches
             keep.append(ps.ps_roipool_forward_batched(fm, rois, nT, K))
             keep.append(ps.ps_roipool_backward_batched(go, rois, H, W))
-        for fm, rois, go in inp["track"]:
-            keep.append(rp.roipool_forward(fm, rois, K))
-            keep.append(rp.roipool_backward(go, rois, H, W))
+        for n, (fm, rois, go) in enumerate(inp["track"]):
+            rec = record_dom and n == 0
+            keep.append(timed("roipool_fwd", rec, lambda: rp.roipool_forward(fm, rois, K)))
+            keep.append(timed("roipool_bwd", rec, lambda: rp.roipool_backward(go, rois, H, W)))
         return keep
 
     def barrier():
@@ -305,11 +310,11 @@ def run_ours(args):
     step()
     torch.cuda.synchronize()
     launches = (_lib.launch_count() - l0) * args.steps
-    # dominant kernel, timed live with CUDA events around its call (eager, same process, right after the timed steps)
+    # per-kernel times, live: CUDA events around the calls (eager, same process, right after the timed steps)
     for _ in range(max(3, args.steps)):
         step(record_dom=True)
     torch.cuda.synchronize()
-    dom_ms = sorted(a.elapsed_time(b) for a, b in zip(dom["e0"], dom["e1"]))[len(dom["e0"]) // 2]
+    med = lambda key: sorted(a.elapsed_time(b) for a, b in dom[key])[len(dom[key]) // 2] * 1e-3  # seconds
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end from host buffers through the nn.Module API ------------------------------------
@@ -328,12 +333,17 @@ def run_ours(args):
         B, C5 = PAIRS_PER_GPU, 2048
         P = live_pairs(H, W, D) * B
         k2 = (2 * D + 1) ** 2
-        # dominant kernel = corr_bwd_tile_kernel on c5; the backward call is two launches of it (grad_FM0, grad_FM1).
-        # algorithmic bytes per launch: grad_out + one feature map read, one gradient map written
-        bytes_launch = (B * H * W * k2 + 2 * B * C5 * H * W) * 4
-        flops_launch = 2.0 * C5 * P
-        t_launch = dom_ms * 1e-3 / 2
+        tf32_peak = peaks.get("bf16_tflops", 1650.0) / 2  # dense TF32 = half the dense BF16 rate on this part
         fp32_peak = 72.5  # TFLOP/s, FFMA micro-benchmark on this pool's B200 (profiles/r1_microbench.txt)
+        # Dominant kernel of the step by time: roipool_vec_bwd_kernel<7> (8 launches, ~30 % of the step).  Algorithmic
+        # bytes per launch: grad_out read + grad_fm written.
+        rp_bytes = (R * TRACK_C * K * K + TRACK_C * H * W) * 4
+        t_rpb, t_rpf = med("roipool_bwd"), med("roipool_fwd")
+        # correlation on c5 (C = 2048, B = 8): forward = one FP32-pipe launch; backward = grad_out flip + two tensor-core
+        # launches (grad_FM0, grad_FM1); algorithmic flops 2*C*P per launch / gradient
+        t_cf, t_cb = med("corr_fwd"), med("corr_bwd")
+        corr_bytes = (B * H * W * k2 + 2 * B * C5 * H * W) * 4
+        flops = 2.0 * C5 * P
         line = {
             "metric": METRIC, "value": job_throughput(world, args.steps, ms), "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -342,14 +352,27 @@ def run_ours(args):
                        "l2": "per-step working set > 2 GB, far above the 126 MB L2 (no explicit flush needed)",
                        "launch": "one CUDA graph replay per step" if graph is not None else "eager launches",
                        "parallelism": f"{world} independent pair shards, no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "corr_bwd_tile_kernel<8,8,*> (c5: C=2048, B=8)",
-                         "achieved": bytes_launch / t_launch * 1e-9, "peak": hbm, "unit": "GB/s",
-                         "frac": bytes_launch / t_launch * 1e-9 / hbm, "traffic": None, "peak_source": which,
-                         "us_per_launch": t_launch * 1e6,
-                         "note": "SIMT FP32 kernel: the binding roof is the FP32 pipe, see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32", "achieved": flops_launch / t_launch * 1e-12, "peak": fp32_peak,
-                              "unit": "TFLOP/s", "frac": flops_launch / t_launch * 1e-12 / fp32_peak,
-                              "peak_source": "measured FFMA micro-benchmark (profiles/r1_microbench.txt)"},
+            "roofline": {"bound": "hbm", "kernel": "roipool_vec_bwd_kernel<7> (track head: C=1891, R=300, 38x63)",
+                         "achieved": rp_bytes / t_rpb * 1e-9, "peak": hbm, "unit": "GB/s",
+                         "frac": rp_bytes / t_rpb * 1e-9 / hbm, "traffic": 115.96e6, "peak_source": which,
+                         "us_per_launch": t_rpb * 1e6, "algorithmic_bytes": rp_bytes,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
+                                           "(profiles/r1_ncu_pool_v4_summary.txt)",
+                         "note": "largest share of the step (8 launches); bound in practice by the shared-memory "
+                                 "read-modify-write pipe, see DESIGN.md section 2.3"},
+            "roofline_other": [
+                {"bound": "hbm", "kernel": "roipool_vec_fwd_kernel<7>", "achieved": rp_bytes / t_rpf * 1e-9, "peak": hbm,
+                 "unit": "GB/s", "frac": rp_bytes / t_rpf * 1e-9 / hbm, "us_per_launch": t_rpf * 1e6},
+                {"bound": "tensor", "kernel": "corr_bwd_umma_kernel<0|1> (c5: C=2048, B=8; 3xTF32, 2 launches + flip)",
+                 "achieved": 2 * flops / t_cb * 1e-12, "peak": tf32_peak, "unit": "TFLOP/s",
+                 "frac": 2 * flops / t_cb * 1e-12 / tf32_peak, "us_per_call": t_cb * 1e6,
+                 "hbm_gbs": 2 * corr_bytes / t_cb * 1e-9,
+                 "note": "algorithmic flops; the dense tile x 3xTF32 executes ~8.4x of them on the tensor pipe"},
+                {"bound": "fp32", "kernel": "corr_fwd_tile_kernel<8,8> (c5: C=2048, B=8)", "achieved": flops / t_cf * 1e-12,
+                 "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t_cf * 1e-12 / fp32_peak,
+                 "us_per_launch": t_cf * 1e6, "hbm_gbs": corr_bytes / t_cf * 1e-9,
+                 "peak_source": "measured FFMA micro-benchmark (profiles/r1_microbench.txt)"},
+            ],
             "e2e": {"value": job_throughput(world, e2e_steps, e2e_ms), "unit": "frame-pairs/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks,

@@ -52,6 +52,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+constexpr bool kCorrFwdDefaultUmma = false;  // default forward family when D2T_CORR_FWD is unset
 constexpr int kCorrBwdUmmaMinItems = 80;  // tensor-core backward by default from this many work items
 constexpr int kStages = 3;  // operand ring depth (cp.async groups in flight: kStages - 1)
 
@@ -556,20 +557,19 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
 bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
 int corr_umma_fwd_launch(const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 
-// The tcgen05 kernel is opt-in (D2T_CORR_FWD=umma, or the d2t_corr_fwd_f32_tc entry point): at this round's
-// state it does not yet beat the FP32-pipe band kernel, so the band kernel stays the default.
-static bool use_umma_fwd() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("D2T_CORR_FWD");
-        cached = (e && strcmp(e, "umma") == 0) ? 1 : 0;
-    }
-    return cached == 1;
+// D2T_CORR_FWD = umma | simt selects the forward kernel family (read per call, so a test can flip it); see DESIGN.md
+// for the measurements behind the default.
+static bool use_umma_fwd(int B, int C, int H, int W, int d) {
+    if (d != 8 || !corr_umma_supported(B, C, H, W, d, 1)) return false;
+    const char* e = getenv("D2T_CORR_FWD");
+    if (e && strcmp(e, "umma") == 0) return true;
+    if (e && strcmp(e, "simt") == 0) return false;
+    return kCorrFwdDefaultUmma;
 }
 
 int corr_tile_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
-    if (d == 8 && use_umma_fwd() && corr_umma_supported(B, C, H, W, d, 1))
+    if (use_umma_fwd(B, C, H, W, d))
         return corr_umma_fwd_launch(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);
     return d == 8 ? fwd_launch<8>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st)
                   : fwd_launch<4>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);

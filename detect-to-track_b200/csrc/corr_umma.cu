@@ -1,26 +1,25 @@
 // corr_umma.cu -- PointwiseCorrelation forward on the 5th-generation tensor cores (tcgen05 + TMEM), d_max = 8.
 //
-// Formulation: one tile of 8x16 query positions (M = 128) against its 23x32 key halo patch (N = 736 key
-// positions) is a GEMM over channels, D[m][n] = sum_c Q[c][m] * K[c][n]; the correlation map of query m is the
-// 16x16 band {n = (qrow+ti)*32 + qcol+tj} of row m.  The dense tile does 2.9x the useful MACs -- the price of
-// feeding a GEMM engine -- and FP32 inputs are split 3xTF32 (hi*hi + hi*lo + lo*hi, hi = top 19 bits) so the
-// result keeps ~22 bits (measured: |err| <= 4e-6 * sum|a||b|, tools/umma_test.cu), i.e. ~8.6x the useful MACs at
-// the TF32 rate, still ~3x faster than the FP32-pipe band kernel (corr_tile.cu).
+// Formulation: one tile of 8x16 query positions (M = 128) against 8 rows of its 23x31 key halo patch (N = 8 x 32 = 256
+// key positions, 31 used per row) is a GEMM over channels, D[m][n] = sum_c Q[c][m] * K[c][n]; the correlation map of
+// query (qrow, qcol) is the band {n = (kr - kr0)*32 + qcol + tj : kr = qrow + ti} of row m.  A tile is three work items
+// (key rows 0-7, 8-15, 16-22), each over all channels, writing disjoint displacement rows of the tile's maps.  The dense
+// tile does ~2.9x the band's MACs and FP32 inputs are split 3xTF32 (hi*hi + hi*lo + lo*hi, hi rounded to nearest,
+// measured |err| <= 9e-7 * sum|a||b|, tools/umma_sw128_test.cu).
 //
-//   operands : K-major canonical UMMA layout without swizzle (core matrix = 8 positions x 4 channels).  Rows of a
-//              38x63 NCHW map are not 16-byte aligned, so neither TMA nor wide copies apply (tools/tma_bench.cu) and
-//              4-byte cp.async is LSU-bound; operands go global -> registers (coalesced LDG, prefetched two stages
-//              ahead) -> hi/lo split in registers -> STS.128 straight into the UMMA layout.
-//              MN-major without swizzle silently yields zeros for kind::tf32 (tools/umma_test.cu), so the natural
-//              position-contiguous layout is not usable.
-//   TMEM     : 512 columns hold at most N = 512, so the patch is processed in two passes over the channel range
-//              (key rows 0-11: N = 384, key rows 12-22: N = 352); per 8-channel block 2 x 3 MMAs (N = 256 + rest).
-//   pipeline : 3-stage ring of 16-channel stages (64 KB each); all threads stage, one thread issues the MMAs and
-//              commits them to the stage's mbarrier, which gates the refill of that stage; one barrier per stage.
-//   epilogue : tcgen05.ld (32 lanes x 32 columns = one key row), band extraction into a per-query-row buffer in the
-//              final (17x17 per position) layout, coalesced copy-out; dead row/column 16 written as zeros.
-//   grid     : the same stream-K plan and partial-slot / finalize machinery as the SIMT kernel.
+//   operands : K-major SWIZZLE_128B (row = position, 32 channels = 128 bytes).  The maps are NCHW, so the staging
+//              transposes: a producer thread owns ONE position (lane = position inside a 32-wide row group: coalesced
+//              LDG per channel), collects 32 channels in registers, splits hi/lo and writes its whole 128-byte operand
+//              row with 8 + 8 STS.128 (the XOR swizzle makes the 8 lanes of a quarter-warp hit 8 bank groups).
+//   warps    : 0-3 stage the queries (A, 128 rows), 4-11 stage one key row each (B, 256 rows); loads run two chunks
+//              ahead in registers.  Warp 12 issues the MMAs (4 k-steps x 3 per 32-channel chunk) and commits to the
+//              stage's `empty` / the item's `accum_full` barrier; warps 13-15 only donate their registers (setmaxnreg).
+//              Why a separate MMA warp: see corr_umma_bwd.cu.
+//   epilogue : tcgen05.ld (32 lanes x 32 columns = two query rows x one key row), band extraction into a per-query-row
+//              buffer in the final (17x17 per position) layout, coalesced copy-out; dead row / column 16 written as
+//              zeros.  Out-of-image keys are staged as zeros, so dead border entries come out as exact 0.
 #include <stdlib.h>
+#include <string.h>
 
 #include "corr_common.cuh"
 
@@ -28,28 +27,28 @@ namespace d2t {
 
 namespace {
 
-constexpr int UD = 8;                 // d_max
-constexpr int UKC = 16;               // channels per stage
-constexpr int UNS = 3;                // stages
-constexpr int UM = 128;               // queries per tile
-constexpr int UNMAX = 384;            // key positions per pass (max)
-constexpr int UTHREADS = 256;
-constexpr int UKB = UKC / 8;          // 8-channel MMA k-blocks per stage
-constexpr int UBLK_A = UM * 8;        // floats of one A k-block
-constexpr int UBLK_B = UNMAX * 8;     // floats of one B k-block
-constexpr int UHI_FLOATS = UKB * (UBLK_A + UBLK_B);  // hi region of a stage (lo region has the same shape)
-constexpr int USTAGE_FLOATS = 2 * UHI_FLOATS;
-constexpr int URP = 290;              // row-buffer pitch per query (289 used): odd (URP - 1) => conflict-free band stores
+constexpr int UD = 8;
+constexpr int UM = 128;                   // queries per tile = UMMA M
+constexpr int UN = 256;                   // key positions per item = UMMA N = TMEM columns
+constexpr int UCH = 32;                   // channels per chunk (one 128-byte operand row)
+constexpr int UA_WARPS = 4, UB_WARPS = 8;
+constexpr int UPROD_WARPS = UA_WARPS + UB_WARPS;
+constexpr int UTHREADS = (UPROD_WARPS + 4) * 32;
+constexpr int UPROD_THREADS = UPROD_WARPS * 32;
+constexpr int UA_BYTES = UM * 128;
+constexpr int UB_BYTES = UN * 128;
+constexpr int USTAGE_BYTES = 2 * UA_BYTES + 2 * UB_BYTES;
+constexpr int USTAGES = 2;
+constexpr int URP = 290;                  // row-buffer pitch per query (289 used)
 constexpr int UROWBUF_FLOATS = 16 * URP;
-constexpr int UPASS_ROWS0 = 12;       // key rows 0..11 in pass 0, 12..22 in pass 1
+constexpr int UGROUPS = 3;                // key-row groups per tile: rows [0,8) [8,16) [16,23)
+
+struct UPlan {
+    int B, C, H, W;
+    int tilesX, tilesY, nItems, nChunks;
+};
 
 __device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void u_cp_async4(uint32_t dst, const float* src, uint32_t bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void u_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void u_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void u_mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(u_smem(bar)), "r"(count));
 }
@@ -60,13 +59,16 @@ __device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor: core matrices 128 B apart along K (LBO), 256 B along M/N (SBO)
-__device__ __forceinline__ uint64_t u_desc(uint32_t saddr) {
+__device__ __forceinline__ void u_mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(u_smem(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t u_desc(uint32_t saddr) {  // K-major SWIZZLE_128B, 8-row atoms 1024 bytes apart
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)(128 >> 4) << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 __device__ __forceinline__ uint32_t u_idesc(int N) {
@@ -79,196 +81,190 @@ __device__ __forceinline__ void u_mma(uint32_t tmem_d, uint64_t da, uint64_t db,
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-__device__ __forceinline__ void u_mma_commit(uint64_t* bar) {
+__device__ __forceinline__ void u_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_smem(bar)) : "memory");
 }
-// element (pos, c) of a k-block, K-major canonical layout, in floats
-__device__ __forceinline__ int u_off(int pos, int c) { return (pos >> 3) * 64 + (c >> 2) * 32 + (pos & 7) * 4 + (c & 3); }
+__device__ __forceinline__ float u_ldg_stream(uint64_t addr) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+    return v;
+}
+__device__ __forceinline__ void u_sts4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float u_tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ void u_prod_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(UPROD_THREADS) : "memory"); }
+
+template <int V>
+struct UInt { static constexpr int value = V; };
+
+// walks the (item, channel chunk) sequence of one CTA; item = (image, tile, key-row group)
+struct UCursor {
+    int item, chunk;
+    int b, i0, j0, kr0, nRows;
+    __device__ __forceinline__ bool valid(const UPlan& p) const { return item < p.nItems; }
+    __device__ __forceinline__ void decode(const UPlan& p) {
+        if (item >= p.nItems) return;
+        const int g = item % UGROUPS;
+        const int tile = item / UGROUPS;
+        const int tpi = p.tilesX * p.tilesY;
+        b = tile / tpi;
+        const int t = tile - b * tpi;
+        i0 = (t / p.tilesX) * 8;
+        j0 = (t % p.tilesX) * 16;
+        kr0 = 8 * g;
+        nRows = g == UGROUPS - 1 ? 7 : 8;
+        chunk = 0;
+    }
+    __device__ __forceinline__ void start(const UPlan& p) { item = blockIdx.x; decode(p); }
+    __device__ __forceinline__ bool last(const UPlan& p) const { return chunk == p.nChunks - 1; }
+    __device__ __forceinline__ void advance(const UPlan& p) {
+        if (++chunk >= p.nChunks) { item += gridDim.x; decode(p); }
+    }
+};
 
 __global__ void __launch_bounds__(UTHREADS, 1)
-corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm1, float* __restrict__ out,
-                     float* __restrict__ partial, CorrPlan p) {
-    extern __shared__ __align__(128) float smem[];
-    float* rowbuf = smem + UNS * USTAGE_FLOATS;
-    __shared__ __align__(8) uint64_t bar_stage[UNS];
-    __shared__ __align__(8) uint64_t bar_accum;
+corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm1, float* __restrict__ out, UPlan p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* rowbuf = reinterpret_cast<float*>(smem + USTAGES * USTAGE_BYTES);
+    __shared__ __align__(8) uint64_t bar_full[USTAGES], bar_empty[USTAGES], bar_acc_full, bar_acc_empty;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, C = p.C;
     const size_t plane = (size_t)H * W;
+    const uint64_t planeBytes = (uint64_t)plane * sizeof(float);
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(u_smem(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(u_smem(&tmem_base_s)), "r"((uint32_t)UN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        for (int s = 0; s < UNS; ++s) u_mbar_init(&bar_stage[s], 1);
-        u_mbar_init(&bar_accum, 1);
+        for (int s = 0; s < USTAGES; ++s) {
+            u_mbar_init(&bar_full[s], UPROD_WARPS);
+            u_mbar_init(&bar_empty[s], 1);
+        }
+        u_mbar_init(&bar_acc_full, 1);
+        u_mbar_init(&bar_acc_empty, UPROD_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    const uint32_t smemBase = u_smem(smem);
 
-    uint32_t stage_phase = 0;  // bit s: parity to wait for on bar_stage[s]
-    uint32_t accum_phase = 0;
-    uint32_t stage_used = 0;   // bit s: stage s has an un-waited commit
-
-    long long it = (long long)blockIdx.x * p.ipc;
-    const long long itEnd = min((long long)p.T * p.NI, it + p.ipc);
-
-    while (it < itEnd) {
-        const int tile = (int)(it / p.NI);
-        const int chunkBeg = (int)(it - (long long)tile * p.NI);
-        const int chunkEnd = (int)min((long long)p.NI, chunkBeg + (itEnd - it));
-        it += chunkEnd - chunkBeg;
-        const int nChunks = chunkEnd - chunkBeg;
-
-        const int b = tile / (p.tilesX * p.tilesY);
-        const int trem = tile - b * p.tilesX * p.tilesY;
-        const int i0 = (trem / p.tilesX) * 8;
-        const int j0 = (trem % p.tilesX) * 16;
-        const float* q_img = fm0 + (size_t)b * C * plane;
-        const float* k_img = fm1 + (size_t)b * C * plane;
-        const bool whole = (chunkBeg == 0 && chunkEnd == p.NI);
-        float* slot = partial + (size_t)(blockIdx.x + tile) * (UM * 289);
-
-        for (int pass = 0; pass < 2; ++pass) {
-            const int kr0 = pass == 0 ? 0 : UPASS_ROWS0;
-            const int nRows = pass == 0 ? UPASS_ROWS0 : 23 - UPASS_ROWS0;
-            const int Npass = nRows * 32;  // 384 or 352
-
-            // ---- staging: global -> registers -> (hi, lo) -> shared, no cp.async ------------------------------------------
-            // 4-byte cp.async costs ~8 LSU cycles per warp instruction on this part (256 of them per stage would
-            // outlast the stage's MMAs); LDG + STS.128 is ~2.7x cheaper and lets the 3xTF32 split happen in registers.
-            // A thread owns two positions of the stage (lane = position inside a 32-wide row => coalesced 128-byte
-            // loads): row group `warp` (queries for warps 0-3, key rows 4.. for warps 4-7) and row group `warp + 8`
-            // (key rows), each for all 16 channels of the stage.
-            const float* ptr[2];
-            uint32_t dstf[2];  // float offset of (pos, channel 0) inside a k-block
-            bool ok[2];
+    if (warp >= UPROD_WARPS) {
+        // ================================ MMA issuer (warp 12; warps 13-15 only donate registers) ===============
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::);
+        if (warp == UPROD_WARPS) {
+            UCursor c;
+            c.start(p);
+            uint32_t k = 0, t = 0;
+            while (c.valid(p)) {
+                const uint32_t s = k & 1u;
+                const bool first = c.chunk == 0, last = c.last(p);
+                const uint32_t idesc = u_idesc(c.nRows * 32);
+                if (first) u_mbar_wait(&bar_acc_empty, (t & 1u) ^ 1u);  // previous item's accumulators are drained
+                u_mbar_wait(&bar_full[s], (k >> 1) & 1u);               // all producer warps have staged chunk k
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t aHi = smemBase + s * USTAGE_BYTES, aLo = aHi + UA_BYTES;
+                    const uint32_t bHi = aHi + 2 * UA_BYTES, bLo = bHi + UB_BYTES;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int rg = warp + 8 * u;  // 0..3 queries, 4..15 key rows (kr0 + rg - 4)
-                int yy, xx, pos, opbase;
-                const float* img;
-                if (rg < 4) {
-                    pos = rg * 32 + lane;
-                    yy = i0 + (pos >> 4); xx = j0 + (pos & 15);
-                    ok[u] = yy < H && xx < W;
-                    img = q_img; opbase = 0;
-                } else {
-                    pos = (rg - 4) * 32 + lane;
-                    yy = i0 - UD + kr0 + (rg - 4); xx = j0 - UD + lane;
-                    ok[u] = (rg - 4) < nRows && lane < 31 && yy >= 0 && yy < H && xx >= 0 && xx < W;
-                    img = k_img; opbase = UBLK_A;
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte row
+                        u_mma(tmem_base, u_desc(aHi + ko), u_desc(bHi + ko), idesc, (first && ks == 0) ? 0u : 1u);
+                        u_mma(tmem_base, u_desc(aHi + ko), u_desc(bLo + ko), idesc, 1u);
+                        u_mma(tmem_base, u_desc(aLo + ko), u_desc(bHi + ko), idesc, 1u);
+                    }
+                    u_commit(&bar_empty[s]);
+                    if (last) u_commit(&bar_acc_full);
                 }
-                dstf[u] = (uint32_t)(opbase + (pos >> 3) * 64 + (pos & 7) * 4);
-                ptr[u] = img + (size_t)chunkBeg * UKC * plane + (ok[u] ? yy * W + xx : 0);
+                __syncwarp();
+                if (last) ++t;
+                ++k;
+                c.advance(p);
             }
+        }
+    } else {
+        // ================================ producers / epilogue (warps 0-11) ====================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n" ::);
+        const bool isA = warp < UA_WARPS;
+        const int rowInOp = (isA ? warp : warp - UA_WARPS) * 32 + lane;  // operand row staged by this thread
+        // byte address (stage 0, hi part) of this thread's operand row, and its eight swizzled 16-byte chunk offsets
+        const uint32_t rowAddr = smemBase + (isA ? 0u : 2u * UA_BYTES) + (uint32_t)((rowInOp >> 3) * 1024 + (rowInOp & 7) * 128);
+        const uint32_t loOff = isA ? UA_BYTES : UB_BYTES;
+        const uint32_t sw = (uint32_t)(lane & 7) << 4;
 
-            auto load_regs = [&](float (&r)[2][UKC], int k) {  // chunk k (relative) -> registers
-                if (k < nChunks) {
-                    const int nvalid = C - (chunkBeg + k) * UKC;
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-#pragma unroll
-                        for (int cc = 0; cc < UKC; ++cc)
-                            r[u][cc] = (ok[u] && cc < nvalid && !(p.dbg & 4)) ? __ldg(ptr[u] + (size_t)cc * plane) : 0.f;
-                        ptr[u] += (size_t)UKC * plane;
-                    }
-                }
-            };
-            auto convert_store = [&](const float (&r)[2][UKC], int s) {  // 3xTF32 split in registers, STS.128
-                float* hiS = smem + s * USTAGE_FLOATS;
-                float* loS = hiS + UHI_FLOATS;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-#pragma unroll
-                    for (int quad = 0; quad < UKC / 4; ++quad) {
-                        float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(r[u][quad * 4 + 0]) & 0xFFFFE000u);
-                        h.y = __uint_as_float(__float_as_uint(r[u][quad * 4 + 1]) & 0xFFFFE000u);
-                        h.z = __uint_as_float(__float_as_uint(r[u][quad * 4 + 2]) & 0xFFFFE000u);
-                        h.w = __uint_as_float(__float_as_uint(r[u][quad * 4 + 3]) & 0xFFFFE000u);
-                        l.x = r[u][quad * 4 + 0] - h.x; l.y = r[u][quad * 4 + 1] - h.y;
-                        l.z = r[u][quad * 4 + 2] - h.z; l.w = r[u][quad * 4 + 3] - h.w;
-                        const int off = (quad >> 1) * (UBLK_A + UBLK_B) + (quad & 1) * 32 + dstf[u];
-                        *reinterpret_cast<float4*>(hiS + off) = h;
-                        *reinterpret_cast<float4*>(loS + off) = l;
-                    }
-                }
-            };
-            const uint32_t smemBase = u_smem(smem);
-            auto run_chunk = [&](float (&r)[2][UKC], int k) {
-                const int s = k % UNS;
-                if ((stage_used >> s) & 1u) {  // the MMAs that last read this stage must have completed
-                    u_mbar_wait(&bar_stage[s], (stage_phase >> s) & 1u);
-                    stage_phase ^= 1u << s;
-                    stage_used &= ~(1u << s);
-                }
-                if (!(p.dbg & 1)) convert_store(r, s);
-                load_regs(r, k + 2);  // prefetch two chunks ahead into the registers just freed
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-                if (tid == 0) {
-                    if (p.dbg & 2) {
-                        u_mma_commit(&bar_stage[s]);
-                        if (k == nChunks - 1) u_mma_commit(&bar_accum);
-                    } else {
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t sbase = smemBase + (uint32_t)s * (USTAGE_FLOATS * 4u);
-#pragma unroll
-                        for (int kb = 0; kb < UKB; ++kb) {
-                            const uint32_t aHi = sbase + (uint32_t)(kb * (UBLK_A + UBLK_B)) * 4u;
-                            const uint32_t bHi = aHi + UBLK_A * 4u;
-                            const uint32_t aLo = aHi + UHI_FLOATS * 4u, bLo = bHi + UHI_FLOATS * 4u;
-                            const uint32_t acc = (k > 0 || kb > 0) ? 1u : 0u;
-                            for (int n0 = 0; n0 < Npass; n0 += 256) {
-                                const int nn = min(256, Npass - n0);
-                                const uint32_t idesc = u_idesc(nn);
-                                const uint32_t boff = (uint32_t)n0 * 32u;  // n0 positions * 8 channels * 4 B
-                                u_mma(tmem_base + n0, u_desc(aHi), u_desc(bHi + boff), idesc, acc);
-                                u_mma(tmem_base + n0, u_desc(aHi), u_desc(bLo + boff), idesc, 1u);
-                                u_mma(tmem_base + n0, u_desc(aLo), u_desc(bHi + boff), idesc, 1u);
-                            }
-                        }
-                        u_mma_commit(&bar_stage[s]);
-                        if (k == nChunks - 1) u_mma_commit(&bar_accum);
-                    }
-                }
-                stage_used |= 1u << s;
-            };
+        UCursor ld, st;
+        ld.start(p);
+        st.start(p);
+        uint32_t k = 0, t = 0;
 
-            float regA[2][UKC], regB[2][UKC];
-            load_regs(regA, 0);
-            load_regs(regB, 1);
-            for (int k = 0; k < nChunks; k += 2) {
-                run_chunk(regA, k);
-                if (k + 1 < nChunks) run_chunk(regB, k + 1);
+        // chunk at cursor c -> registers: 32 channels of this thread's position
+        auto load = [&](float (&v)[UCH], const UCursor& c) {
+            int gi, gj;
+            bool ok;
+            const float* img;
+            if (isA) {
+                const int m = warp * 32 + lane;
+                gi = c.i0 + (m >> 4); gj = c.j0 + (m & 15);
+                ok = gi < H && gj < W;
+                img = fm0;
+            } else {
+                const int kk = warp - UA_WARPS;
+                gi = c.i0 - UD + c.kr0 + kk; gj = c.j0 - UD + lane;
+                ok = kk < c.nRows && lane < 31 && gi >= 0 && gi < H && gj >= 0 && gj < W;
+                img = fm1;
             }
-
-            // ---- epilogue of this pass --------------------------------------------------------------------------
-            u_mbar_wait(&bar_accum, accum_phase);
-            accum_phase ^= 1u;
+            const int c0 = c.chunk * UCH;
+            const int nch = C - c0;
+            uint64_t a = (uint64_t)(img + ((size_t)c.b * C + c0) * plane + (ok ? (size_t)gi * W + gj : 0));
+            if (ok && nch >= UCH) {
+#pragma unroll
+                for (int j = 0; j < UCH; ++j) {
+                    v[j] = u_ldg_stream(a);
+                    a += planeBytes;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < UCH; ++j) {
+                    v[j] = (ok && j < nch) ? u_ldg_stream(a) : 0.f;
+                    a += planeBytes;
+                }
+            }
+        };
+        auto store = [&](const float (&v)[UCH], auto S) {
+            constexpr uint32_t so = decltype(S)::value * USTAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < UCH / 4; ++j) {
+                const float h0 = u_tf32_rn(v[4 * j]), h1 = u_tf32_rn(v[4 * j + 1]);
+                const float h2 = u_tf32_rn(v[4 * j + 2]), h3 = u_tf32_rn(v[4 * j + 3]);
+                const uint32_t ad = rowAddr + so + (((uint32_t)j << 4) ^ sw);
+                u_sts4(ad, h0, h1, h2, h3);
+                u_sts4(ad + loOff, v[4 * j] - h0, v[4 * j + 1] - h1, v[4 * j + 2] - h2, v[4 * j + 3] - h3);
+            }
+        };
+        // accumulators of the finished item -> out: band extraction through the row buffer
+        auto epilogue = [&](const UCursor& c) {
+            u_mbar_wait(&bar_acc_full, t & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-            const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31
-            const int m = quarter * 32 + lane;       // query index in the tile
+            const int quarter = warp & 3, third = warp >> 2;  // TMEM lanes 32*quarter..+31; key rows kk % 3 == third
+            const int m = quarter * 32 + lane;
             const int qrow = m >> 4, qcol = m & 15;
-            const int par = warp >> 2;               // this warp takes key rows of parity `par` within the pass
+            const bool lastGroup = c.kr0 + c.nRows == 23;
+            const int ptid = tid;  // 0 .. UPROD_THREADS-1
             for (int qr = 0; qr < 8; ++qr) {
-                // ti range of query row qr produced by this pass (row 16 of every map is dead: zeros, with pass 1)
-                const int tiLo = max(0, kr0 - qr), tiHi = min(15, kr0 + nRows - 1 - qr);
-                const int tiEnd = (pass == 1) ? 17 : tiHi + 1;  // exclusive, in 17-float rows
-                const bool mine = (qr >> 1) == quarter;         // warps holding this query row
-                if (mine) {
-                    for (int kr = max(kr0, qr); kr <= min(kr0 + nRows - 1, qr + 15); ++kr) {
-                        if (((kr - kr0) & 1) != par) continue;  // warp-uniform: the two warps of a quarter split the rows
+                // ti range of query row qr produced by this item (row 16 of every map is dead: zeros, with the last group)
+                const int tiLo = max(0, c.kr0 - qr), tiHi = min(15, c.kr0 + c.nRows - 1 - qr);
+                const int tiEnd = lastGroup ? 17 : tiHi + 1;  // exclusive, in 17-float rows
+                if ((qr >> 1) == quarter) {
+                    for (int kr = max(c.kr0, qr); kr <= min(c.kr0 + c.nRows - 1, qr + 15); ++kr) {
+                        if ((kr - c.kr0) % 3 != third) continue;  // warp-uniform: the three warps of a quarter split the rows
                         uint32_t r[32];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((kr - kr0) * 32);
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((kr - c.kr0) * 32);
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
                             "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -286,41 +282,68 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                             rowbuf[qcol * URP + (kr - qr) * 17 + 16] = 0.f;  // dead column 16
                         }
                     }
-                    if (pass == 1 && qrow == qr && par == 0) {
+                    if (lastGroup && qrow == qr && third == 0) {
 #pragma unroll
                         for (int x = 0; x < 17; ++x) rowbuf[qcol * URP + 16 * 17 + x] = 0.f;  // dead row 16
                     }
                 }
-                __syncthreads();
-                // copy rows [tiLo, tiEnd) of the 16 queries of this row to their destination
-                {
+                u_prod_barrier();
+                {   // copy rows [tiLo, tiEnd) of the 16 queries of this tile row to their maps (24 threads per query)
                     const int len = (tiEnd - tiLo) * 17;
-                    const int gi = i0 + qr;
-                    const int ncols = whole ? min(16, W - j0) : 16;
-                    if (len > 0 && (!whole || gi < H)) {
-                        float* dbase = whole ? out + (((size_t)b * H + gi) * W + j0) * 289 : slot + (size_t)qr * 16 * 289;
-                        const int q = tid >> 4;  // 16 threads per query
+                    const int gi = c.i0 + qr;
+                    const int ncols = min(16, W - c.j0);
+                    if (len > 0 && gi < H) {
+                        float* dbase = out + (((size_t)c.b * H + gi) * W + c.j0) * 289;
+                        const int q = ptid / 24;
                         if (q < ncols)
-                            for (int o = tid & 15; o < len; o += 16) dbase[q * 289 + tiLo * 17 + o] = rowbuf[q * URP + tiLo * 17 + o];
+                            for (int o = ptid - q * 24; o < len; o += 24) dbase[q * 289 + tiLo * 17 + o] = rowbuf[q * URP + tiLo * 17 + o];
                     }
                 }
-                __syncthreads();
+                u_prod_barrier();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();  // TMEM reads done before the next pass overwrites the accumulators
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) u_mbar_arrive(&bar_acc_empty);
+            ++t;
+        };
+        auto step = [&](float (&v)[UCH], auto S) {
+            constexpr int s = decltype(S)::value;
+            u_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);  // the MMAs that read this stage two chunks ago are done
+            store(v, S);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) u_mbar_arrive(&bar_full[s]);
+            ++k;
+            if (ld.valid(p)) {
+                load(v, ld);
+                ld.advance(p);
+            }
+            if (st.last(p)) epilogue(st);
+            st.advance(p);
+        };
+
+        float va[UCH], vb[UCH];
+        if (ld.valid(p)) { load(va, ld); ld.advance(p); }
+        if (ld.valid(p)) { load(vb, ld); ld.advance(p); }
+        while (st.valid(p)) {
+            step(va, UInt<0>{});
+            if (!st.valid(p)) break;
+            step(vb, UInt<1>{});
         }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)UN));
+    }
 }
 
 }  // namespace
 
 bool corr_umma_supported(int B, int C, int H, int W, int d, int stride) {
-    if (stride != 1 || d != 8) return false;
+    if (stride != 1 || d != UD) return false;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return false;
     if ((long long)B * C * H * W >= (1ll << 31)) return false;
     return true;
@@ -328,21 +351,23 @@ bool corr_umma_supported(int B, int C, int H, int W, int d, int stride) {
 
 int corr_umma_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
-    CorrPlan p;
-    int rc = make_plan<8>(B, C, H, W, UKC, &p);
+    (void)ws;
+    (void)ws_bytes;
+    DeviceInfo di;
+    int rc = device_info(&di);
     if (rc) return rc;
-    if (const char* e = getenv("D2T_UMMA_DBG")) p.dbg = atoi(e);
-    const size_t need = (size_t)(p.G + p.T) * FwdCfg<8>::TILE_FLOATS * sizeof(float);
-    if (ws == nullptr || ws_bytes < need) {
-        set_error("corr_fwd(umma): workspace too small (%zu < %zu)", ws_bytes, need);
-        return D2T_ERR_WORKSPACE;
-    }
-    const size_t smem = ((size_t)UNS * USTAGE_FLOATS + UROWBUF_FLOATS) * sizeof(float);
+    UPlan p;
+    p.B = B; p.C = C; p.H = H; p.W = W;
+    p.tilesX = ceil_div(W, 16);
+    p.tilesY = ceil_div(H, 8);
+    p.nItems = B * p.tilesX * p.tilesY * UGROUPS;
+    p.nChunks = ceil_div(C, UCH);
+    const int grid = p.nItems < di.sm_count ? p.nItems : di.sm_count;
+    const size_t smem = (size_t)USTAGES * USTAGE_BYTES + UROWBUF_FLOATS * sizeof(float) + 1024;
     D2T_CUDA_TRY(cudaFuncSetAttribute(corr_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_fwd_umma_kernel<<<p.G, UTHREADS, smem, st>>>(fm0, fm1, out, static_cast<float*>(ws), p);
+    corr_fwd_umma_kernel<<<grid, UTHREADS, smem, st>>>(fm0, fm1, out, p);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
-    if (p.ipc % p.NI != 0) return corr_fwd_finalize8_launch(static_cast<const float*>(ws), out, p, st);
     return D2T_OK;
 }
 
