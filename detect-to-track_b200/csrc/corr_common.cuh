@@ -33,7 +33,10 @@ struct CorrPlan {
     int tilesX, tilesY, T;  // tiles per image in x / y, total tiles
     int NI;                 // channel chunks per tile
     int G;                  // CTAs
-    int ipc;                // (tile, chunk) iterations per CTA
+    int ipc;                // (tile, chunk) iterations per CTA (backward: one contiguous range per CTA)
+    // forward: `rounds` whole tiles per CTA (tile = round * G + cta, all CTAs walk the channels in step, so the halos
+    // that neighbouring tiles share are fetched from L2, not HBM), then the `left` remaining tiles stream-K split
+    int rounds, left, ipcL;
     int dbg;                // experiment switches (0 in production)
 };
 
@@ -54,6 +57,9 @@ static inline int make_plan(int B, int C, int H, int W, int CK, CorrPlan* p) {
     p->G = (int)G;
     p->ipc = (int)((total + G - 1) / G);
     p->G = (int)((total + p->ipc - 1) / p->ipc);
+    p->rounds = p->T / p->G;
+    p->left = p->T - p->rounds * p->G;
+    p->ipcL = (int)(((long long)p->left * p->NI + p->G - 1) / p->G);
     return 0;
 }
 

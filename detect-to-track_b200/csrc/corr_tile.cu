@@ -54,6 +54,24 @@ __device__ __forceinline__ void cp_async_wait() {
 
 constexpr bool kCorrFwdDefaultUmma = false;  // default forward family when D2T_CORR_FWD is unset
 constexpr int kCorrBwdUmmaMinItems = 80;  // tensor-core backward by default from this many work items
+// packed FP32x2 FMA (Blackwell FFMA2): two independent fused multiply-adds per issue slot, same rounding as fmaf.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ float2 unpack2(f32x2_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
 constexpr int kStages = 3;  // operand ring depth (cp.async groups in flight: kStages - 1)
 
 
@@ -87,14 +105,26 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
     const int H = p.H, W = p.W, C = p.C;
     const size_t plane = (size_t)H * W;
 
-    long long it = (long long)blockIdx.x * p.ipc;
-    const long long itEnd = min((long long)p.T * p.NI, it + p.ipc);
+    int rnd = 0;
+    long long it = (long long)blockIdx.x * p.ipcL;
+    const long long itEnd = min((long long)p.left * p.NI, it + p.ipcL);
 
-    while (it < itEnd) {
-        const int tile = (int)(it / p.NI);
-        const int chunkBeg = (int)(it - (long long)tile * p.NI);
-        const int chunkEnd = (int)min((long long)p.NI, chunkBeg + (itEnd - it));
-        it += chunkEnd - chunkBeg;
+    while (true) {
+        int tile, chunkBeg, chunkEnd, lt = 0;
+        if (rnd < p.rounds) {  // whole tiles, in step with the other CTAs
+            tile = rnd * p.G + blockIdx.x;
+            chunkBeg = 0;
+            chunkEnd = p.NI;
+            ++rnd;
+        } else if (it < itEnd) {  // this CTA's share of the left-over tiles
+            lt = (int)(it / p.NI);
+            chunkBeg = (int)(it - (long long)lt * p.NI);
+            chunkEnd = (int)min((long long)p.NI, chunkBeg + (itEnd - it));
+            it += chunkEnd - chunkBeg;
+            tile = p.rounds * p.G + lt;
+        } else {
+            break;
+        }
 
         const int b = tile / (p.tilesX * p.tilesY);
         const int trem = tile - b * p.tilesX * p.tilesY;
@@ -135,11 +165,16 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         const bool taskLive = (i0 + qrow < H) && (i0 - D + kr >= 0) && (i0 - D + kr < H);
         const bool warpLive = __any_sync(0xffffffffu, taskLive);
 
-        float acc[8][TD];
+        // Accumulators as FP32 pairs along the key index e = a + t, so that every pair multiplies one (q, q) by one
+        // naturally aligned (kv[2m], kv[2m+1]) register pair from the LDS.128: even queries a hold t = (2j, 2j+1),
+        // j < TD/2; odd queries hold t = (2j-1, 2j), j <= TD/2, whose first and last halves (t = -1, t = TD) are
+        // unused.  68 FFMA2 per channel instead of 128 FFMA (d = 8): half the issue slots for the same FP32-pipe work.
+        constexpr int NP = TD / 2;
+        f32x2_t acc2[8][NP + 1];
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int t = 0; t < TD; ++t) acc[a][t] = 0.f;
+            for (int jj = 0; jj <= NP; ++jj) acc2[a][jj] = 0ull;
 
         // asynchronous staging of one channel chunk (cp.async: no staging registers, no scoreboard
         // coupling with the LDS of the compute loop).  Chunks are issued strictly in order, so the
@@ -184,15 +219,20 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                     const float* s = stage + cc * Cfg::CH_FLOATS;
                     const float4* sq = reinterpret_cast<const float4*>(s + qrow * Cfg::QP + 8 * l);
                     const float4* sk = reinterpret_cast<const float4*>(s + Cfg::QROWS * Cfg::QP + krow_off<D>(kr) + 8 * l);
-                    float q[8], kv[4 * Cfg::KV];
+                    float q[8];
+                    f32x2_t kk[2 * Cfg::KV];
                     *reinterpret_cast<float4*>(q) = sq[0];
                     *reinterpret_cast<float4*>(q + 4) = sq[1];
 #pragma unroll
-                    for (int v = 0; v < Cfg::KV; ++v) *reinterpret_cast<float4*>(kv + 4 * v) = sk[v];
+                    for (int v = 0; v < Cfg::KV; ++v) *reinterpret_cast<ulonglong2*>(kk + 2 * v) = reinterpret_cast<const ulonglong2*>(sk)[v];
 #pragma unroll
-                    for (int a = 0; a < 8; ++a)
+                    for (int a = 0; a < 8; ++a) {
+                        const f32x2_t qq = pack2(q[a], q[a]);
+                        const int m0 = a >> 1;               // first key pair used by query a
+                        const int np = (a & 1) ? NP + 1 : NP;
 #pragma unroll
-                        for (int t = 0; t < TD; ++t) acc[a][t] = fmaf(q[a], kv[a + t], acc[a][t]);
+                        for (int jj = 0; jj < np; ++jj) acc2[a][jj] = ffma2(qq, kk[m0 + jj], acc2[a][jj]);
+                    }
                 }
             }
         }
@@ -210,7 +250,9 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                 for (int t = 0; t < TD; ++t) {
                     const int dj = gj - D + t;
                     const bool live = taskLive && dj >= 0 && dj < W;
-                    base[a * KK + t] = live ? acc[a][t] : 0.f;
+                    const int u = (a & 1) ? t + 1 : t;  // position inside the query's pair sequence
+                    const float2 pr = unpack2(acc2[a][u >> 1]);
+                    base[a * KK + t] = live ? ((u & 1) ? pr.y : pr.x) : 0.f;
                 }
             }
             // dead row 2d and dead column 2d of every map in the tile
@@ -234,8 +276,8 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                 for (int e = tid; e < run; e += kCorrThreads) dst[e] = src[e];
             }
         } else {
-            // fixed slot per (cta, tile): slot = cta + tile (unique because tile is monotone in cta)
-            float4* dst = reinterpret_cast<float4*>(partial + (size_t)(blockIdx.x + tile) * Cfg::TILE_FLOATS);
+            // fixed slot per (cta, left-over tile): slot = cta + lt (unique because lt is monotone in cta)
+            float4* dst = reinterpret_cast<float4*>(partial + (size_t)(blockIdx.x + lt) * Cfg::TILE_FLOATS);
             const float4* src = reinterpret_cast<const float4*>(tileS);
             for (int e = tid; e < Cfg::TILE_FLOATS / 4; e += kCorrThreads) dst[e] = src[e];
         }
@@ -249,9 +291,10 @@ __global__ void __launch_bounds__(256)
 corr_fwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, CorrPlan p) {
     using Cfg = FwdCfg<D>;
     constexpr int KK = Cfg::KK;
-    const int tile = blockIdx.x;
-    const long long itBeg = (long long)tile * p.NI, itLast = itBeg + p.NI - 1;
-    const int gFirst = (int)(itBeg / p.ipc), gLast = (int)(itLast / p.ipc);
+    const int lt = blockIdx.x;  // left-over tile
+    const int tile = p.rounds * p.G + lt;
+    const long long itBeg = (long long)lt * p.NI, itLast = itBeg + p.NI - 1;
+    const int gFirst = (int)(itBeg / p.ipcL), gLast = (int)(itLast / p.ipcL);
     if (gFirst == gLast) return;  // written directly by its only CTA
     const int b = tile / (p.tilesX * p.tilesY);
     const int trem = tile - b * p.tilesX * p.tilesY;
@@ -265,7 +308,7 @@ corr_fwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ 
         const float* src = partial + (size_t)r * Cfg::QCOLS * KK;
         for (int e = threadIdx.x; e < run; e += blockDim.x) {
             float s = 0.f;
-            for (int g = gFirst; g <= gLast; ++g) s += src[(size_t)(g + tile) * Cfg::TILE_FLOATS + e];
+            for (int g = gFirst; g <= gLast; ++g) s += src[(size_t)(g + lt) * Cfg::TILE_FLOATS + e];
             dst[e] = s;
         }
     }
@@ -470,7 +513,8 @@ corr_bwd_tile_kernel(const float* __restrict__ go, const float* __restrict__ xsr
 constexpr int kFwdCK = 8;
 
 int corr_fwd_finalize8_launch(const float* partial, float* out, const CorrPlan& p, cudaStream_t st) {
-    dim3 grid(p.T, FwdCfg<8>::QROWS);
+    if (p.left <= 0) return D2T_OK;
+    dim3 grid(p.left, FwdCfg<8>::QROWS);
     corr_fwd_finalize_kernel<8><<<grid, 256, 0, st>>>(partial, out, p);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
@@ -531,6 +575,17 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     CorrPlan p;
     int rc = make_plan<D>(B, C, H, W, CK, &p);
     if (rc) return rc;
+    {   // Whole-tile rounds (all CTAs in step, halos shared through L2) were measured SLOWER than one contiguous
+        // (tile, chunk) range per CTA at B = 8 (c5: 587 vs ~510 us): with every CTA on the same channel planes at the
+        // same time the memory system is hit in bursts.  So the default is the staggered stream-K walk; D2T_CORR_SCHED=2
+        // selects the rounds for experiments.
+        const char* e = getenv("D2T_CORR_SCHED");
+        if (!(e && e[0] == '2')) {
+            p.rounds = 0;
+            p.left = p.T;
+            p.ipcL = p.ipc;
+        }
+    }
     const size_t need = (size_t)(p.G + p.T) * Cfg::TILE_FLOATS * sizeof(float);
     if (ws == nullptr || ws_bytes < need) {
         set_error("corr_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -544,8 +599,8 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     kern<<<p.G, kCorrThreads, smem, st>>>(fm0, fm1, out, static_cast<float*>(ws), p);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
-    if (p.ipc % p.NI != 0) {  // some tile is split over CTAs
-        dim3 grid(p.T, Cfg::QROWS);
+    if (p.left > 0 && p.ipcL % p.NI != 0) {  // some left-over tile is split over CTAs
+        dim3 grid(p.left, Cfg::QROWS);
         corr_fwd_finalize_kernel<D><<<grid, 256, 0, st>>>(static_cast<const float*>(ws), out, p);
         D2T_CUDA_TRY(cudaGetLastError());
         note_launch();
