@@ -446,6 +446,9 @@ int roipool_prefix_fwd_launch(const float*, const float*, float*, int, int, int,
 bool roipool_vec_supported(int R, int C, int H, int W, int k);
 int roipool_vec_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int roipool_vec_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+// float32 row-owner backward (pool_rows.cu)
+bool roipool_rows_bwd_supported(int R, int C, int H, int W, int k);
+int roipool_rows_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 template <typename T>
 struct FastPath {
     static bool fwd(const T*, const T*, T*, int, int, int, int, int, cudaStream_t, int*) { return false; }
@@ -473,6 +476,10 @@ struct FastPath<float> {
     }
     static bool bwd(const float* go, const float* rois, float* gin, int R, int C, int H, int W, int k, cudaStream_t st,
                     int* rc) {
+        if (roipool_rows_bwd_supported(R, C, H, W, k)) {
+            *rc = roipool_rows_bwd_launch(go, rois, gin, R, C, H, W, st);
+            return true;
+        }
         if (roipool_vec_supported(R, C, H, W, k)) {
             *rc = roipool_vec_bwd_launch(go, rois, gin, R, C, H, W, k, st);
             return true;

@@ -75,6 +75,20 @@ def test_corr_vs_reference_kernels(cuda, B, C, H, W, d, stride):
     close(g1, r1.cpu().numpy(), np.float32)
 
 
+def test_roipool_row_owner_backward_experiment(cuda, monkeypatch):
+    """pool_rows.cu (D2T_ROIPOOL_ROWS=1): lanes own pixel rows; same results as the default kernel within rounding,
+    bitwise reproducible, edge-case RoIs included."""
+    C, H, W, k = 45, 38, 63, 7
+    rois = np.concatenate([cases.rois_random(150, 21), cases.rois_edge_cases(H, W)], 0)
+    fm, go = cases.pool_inputs(C, H, W, (len(rois), C, k, k), seed=22)
+    want = oracle.roipool_bwd(go, rois, H, W)
+    monkeypatch.setenv("D2T_ROIPOOL_ROWS", "1")
+    a = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
+    b = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
+    close(a, want, np.float32)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("d_max", [3])
 @pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("input_b", [1, 2])
