@@ -22,13 +22,14 @@
 //              4 k-steps x 3 MMAs (128x256x8, kind::tf32) per chunk.
 //   warps 0-7  producers: lane = key column.  Warp w stages channels 32w..32w+31 of B (one coalesced 124-byte LDG and
 //              two conflict-free 128-byte-row STS per channel) and query row w of A.  Loads run two chunks ahead in
-//              registers, across item boundaries.  After the last chunk of an item they read the accumulators
-//              (tcgen05.ld) and store D[m][n] -> grad[b][n][position].
+//              registers, across item boundaries, and never stop for an epilogue.
 //   warp 8     issues the MMAs (one lane) once the stage's `full` barrier completes; tcgen05.commit -> `empty` barrier
 //              of the stage / `accum_full` of the item.  It must be a warp of its own: tcgen05.mma issue blocks while
 //              the tensor core's queue is full, and a producer warp that blocks there serialises staging and MMAs
 //              (measured: stage + MMA + handshake times added up exactly).  Registers are allocated per 4 warps, so the
-//              third warpgroup (warps 8-11) hands its registers to the producers with setmaxnreg (40 / 224).
+//              third warpgroup (warps 8-11) hands its registers to the producers with setmaxnreg (40 / 200).
+//   warps 12-15 epilogue: tcgen05.ld of the finished item's accumulators -> grad[b][n][position].  Two 256-column
+//              TMEM buffers alternate between items, so draining item t overlaps the MMAs of item t+1.
 //   grad_FM1   needs gradOut transposed (the queries whose window contains a key): corr_bwd_flip_kernel writes
 //              GT[b,p,si,sj] = gradOut[b, p + (si,sj) - 7, 15 - si, 15 - sj] (0 outside the image) into the workspace
 //              once per call (42 MB of traffic at B = 8), so that both gradients use the same staging code.
@@ -49,7 +50,8 @@ constexpr int XN = 256;                   // channels per item = UMMA N = TMEM c
 constexpr int XQROWS = 8, XQCOLS = 16;
 constexpr int XROWS = XQROWS + XTD - 1;   // 23 patch rows
 constexpr int XPROD_WARPS = 8;
-constexpr int XTHREADS = (XPROD_WARPS + 4) * 32;  // + one warpgroup: MMA issuer warp and three idle warps
+constexpr int XEPI_WARP0 = XPROD_WARPS + 4;        // warps 12-15: epilogue (TMEM lane quarter = warp % 4)
+constexpr int XTHREADS = (XPROD_WARPS + 8) * 32;  // + MMA issuer warp 8 (9-11 idle) + four epilogue warps
 constexpr int XA_BYTES = XM * 128;        // one A operand (hi or lo) of a chunk
 constexpr int XB_BYTES = XN * 128;        // one B operand (hi or lo) of a chunk
 constexpr int XSTAGE_BYTES = 2 * XA_BYTES + 2 * XB_BYTES;
@@ -149,7 +151,7 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
     constexpr int GROW = MODE == 0 ? XK1 : XTD;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bar_full[XSTAGES], bar_empty[XSTAGES], bar_acc_full, bar_acc_empty;
+    __shared__ __align__(8) uint64_t bar_full[XSTAGES], bar_empty[XSTAGES], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -158,7 +160,7 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
     const uint64_t planeBytes = (uint64_t)plane * sizeof(float);
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(x_smem(&tmem_base_s)), "r"((uint32_t)XN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(x_smem(&tmem_base_s)), "r"((uint32_t)(2 * XN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
@@ -166,8 +168,10 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
             x_mbar_init(&bar_full[s], XPROD_WARPS);
             x_mbar_init(&bar_empty[s], 1);
         }
-        x_mbar_init(&bar_acc_full, 1);
-        x_mbar_init(&bar_acc_empty, XPROD_WARPS);
+        for (int a = 0; a < 2; ++a) {
+            x_mbar_init(&bar_acc_full[a], 1);
+            x_mbar_init(&bar_acc_empty[a], 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -191,7 +195,61 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
 #pragma unroll
     for (int j = 0; j < XNA; ++j) amask |= (lane - j >= 0 && lane - j < XTD) ? (1u << j) : 0u;
 
-    if (warp >= XPROD_WARPS) {
+    if (warp >= XEPI_WARP0) {
+        // ================================ epilogue (warps 12-15) ================================================
+        // accumulators of a finished item -> grad[b][c][position]; items alternate between the two 256-column TMEM
+        // buffers, so the MMAs of item t+1 run while item t is drained and the producers never stop staging
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n" ::);
+        const int quarter = warp - XEPI_WARP0;
+        const int m = quarter * 32 + lane;
+        XCursor c;
+        c.start(p, OFF);
+        uint32_t t = 0;
+        while (c.valid(p)) {
+            const uint32_t ab = t & 1u;
+            x_mbar_wait(&bar_acc_full[ab], (t >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int gi = c.i0 + (m >> 4), gj = c.j0 + (m & 15);
+            const bool pok = gi < H && gj < W;
+            const int cbase = c.cb * XN;
+            float* dst = gout + ((size_t)c.b * C + cbase) * plane + (size_t)gi * W + gj;
+#pragma unroll 1
+            for (int q = 0; q < XN / 16; ++q) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * XN + (uint32_t)(q * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int nch = C - (cbase + q * 16);
+                if (pok) {
+                    if (nch >= 16) {
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) {
+                            *dst = __uint_as_float(r[x]);
+                            dst += plane;
+                        }
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 16; ++x)
+                            if (x < nch) dst[(size_t)x * plane] = __uint_as_float(r[x]);
+                        dst += 16 * plane;
+                    }
+                } else {
+                    dst += 16 * plane;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) x_mbar_arrive(&bar_acc_empty[ab]);
+            ++t;
+            c.item += gridDim.x;  // next item of this CTA
+            c.decode(p, OFF);
+        }
+    } else if (warp >= XPROD_WARPS) {
         // ================================ MMA issuer (warp 8; warps 9-11 only donate registers) ================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::);
         if (warp == XPROD_WARPS) {
@@ -200,23 +258,25 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
             uint32_t k = 0, t = 0;
             while (c.valid(p)) {
                 const uint32_t s = k & 1u;
+                const uint32_t ab = t & 1u;
                 const bool first = c.r == c.rLo, last = c.last();
-                if (first) x_mbar_wait(&bar_acc_empty, (t & 1u) ^ 1u);  // previous item's accumulators are drained
-                x_mbar_wait(&bar_full[s], (k >> 1) & 1u);                // all eight producer warps have staged chunk k
+                if (first) x_mbar_wait(&bar_acc_empty[ab], ((t >> 1) & 1u) ^ 1u);  // this buffer's previous item is drained
+                x_mbar_wait(&bar_full[s], (k >> 1) & 1u);                           // all producer warps have staged chunk k
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t aHi = smemBase + s * XSTAGE_BYTES, aLo = aHi + XA_BYTES;
                     const uint32_t bHi = aHi + 2 * XA_BYTES, bLo = bHi + XB_BYTES;
+                    const uint32_t dcol = tmem_base + ab * XN;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         if (p.dbg & 2) break;
                         const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte row
-                        x_mma(tmem_base, x_desc(aHi + ko), x_desc(bHi + ko), (first && ks == 0) ? 0u : 1u);
-                        x_mma(tmem_base, x_desc(aHi + ko), x_desc(bLo + ko), 1u);
-                        x_mma(tmem_base, x_desc(aLo + ko), x_desc(bHi + ko), 1u);
+                        x_mma(dcol, x_desc(aHi + ko), x_desc(bHi + ko), (first && ks == 0) ? 0u : 1u);
+                        x_mma(dcol, x_desc(aHi + ko), x_desc(bLo + ko), 1u);
+                        x_mma(dcol, x_desc(aLo + ko), x_desc(bHi + ko), 1u);
                     }
                     x_commit(&bar_empty[s]);
-                    if (last) x_commit(&bar_acc_full);
+                    if (last) x_commit(&bar_acc_full[ab]);
                 }
                 __syncwarp();
                 if (last) ++t;
@@ -225,12 +285,12 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
             }
         }
     } else {
-    // ================================ producers / epilogue (warps 0-7) =====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n" ::);
+    // ================================ producers (warps 0-7) ==================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;\n" ::);
     XCursor ld, st;
     ld.start(p, OFF);
     st.start(p, OFF);
-    uint32_t k = 0, t = 0;  // chunks stored, items finished
+    uint32_t k = 0;  // chunks stored
 
     // chunk at cursor c -> registers: v[0..31] = B (channel 32*warp + j, key column lane), v[32..47] = A (query
     // (warp, j), key column lane)
@@ -288,47 +348,6 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
             x_sts(ad + XB_BYTES, v[j] - hi);
         }
     };
-    // accumulators of the finished item -> grad[b][c][position]
-    auto epilogue = [&](const XCursor& c) {
-        x_mbar_wait(&bar_acc_full, t & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quarter = warp & 3, half = warp >> 2;
-        const int m = quarter * 32 + lane;
-        const int gi = c.i0 + (m >> 4), gj = c.j0 + (m & 15);
-        const bool pok = gi < H && gj < W;
-        const int cbase = c.cb * XN + half * (XN / 2);
-        float* dst = gout + ((size_t)c.b * C + cbase) * plane + (size_t)gi * W + gj;
-#pragma unroll 1
-        for (int q = 0; q < XN / 2 / 16; ++q) {
-            uint32_t r[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (XN / 2) + q * 16);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-                "%15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int nch = C - (cbase + q * 16);
-            if (pok) {
-                if (nch >= 16) {
-#pragma unroll
-                    for (int x = 0; x < 16; ++x) {
-                        *dst = __uint_as_float(r[x]);
-                        dst += plane;
-                    }
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 16; ++x)
-                        if (x < nch) dst[(size_t)x * plane] = __uint_as_float(r[x]);
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) x_mbar_arrive(&bar_acc_empty);
-        ++t;
-    };
     auto step = [&](float (&v)[XNB + XNA], auto S) {
         constexpr int s = decltype(S)::value;
         x_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);  // the MMAs that read this stage two chunks ago are done
@@ -341,7 +360,6 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
             load(v, ld);
             ld.advance(p, OFF);
         }
-        if (st.last()) epilogue(st);
         st.advance(p, OFF);
     };
 
@@ -361,7 +379,7 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)XN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * XN)));
     }
 }
 
