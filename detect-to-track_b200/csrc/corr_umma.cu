@@ -52,11 +52,11 @@ __device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__c
 __device__ __forceinline__ void u_mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(u_smem(bar)), "r"(count));
 }
-__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {  // suspend-time hint: see corr_umma_bwd.cu
     asm volatile(
-        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
             u_smem(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void u_mbar_arrive(uint64_t* bar) {
