@@ -364,12 +364,16 @@ roipool_vec_bwd_kernel(const float* __restrict__ go, const float* __restrict__ r
                 const int cRow = H >> 1, U2 = 2 * (H - 1 - cRow);
                 const int y = task < U2 ? ((task & 1) ? cRow + 1 + (task >> 1) : cRow - (task >> 1))
                                         : cRow - (U2 >> 1) - (task - U2);
-                unsigned long long masks = *reinterpret_cast<const unsigned long long*>(cov + y * RG);
+                const uint2 masks2 = *reinterpret_cast<const uint2*>(cov + y * RG);  // one cover byte per RoI of the group
                 char* row = reinterpret_cast<char*>(D + y * rowPitch);
-                while (masks != 0ull) {  // RoIs of the group that cover this row, in ascending order
-                    const int rr = (__ffsll((long long)masks) - 1) >> 3;
-                    unsigned cover = (unsigned)(masks >> (8 * rr)) & 0xffu;
-                    masks &= ~(0xffull << (8 * rr));
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                unsigned masks = half ? masks2.y : masks2.x;
+                while (masks != 0u) {  // RoIs of the group that cover this row, in ascending order
+                    const int r4 = (__ffs(masks) - 1) >> 3;
+                    unsigned cover = (masks >> (8 * r4)) & 0xffu;
+                    masks &= ~(0xffu << (8 * r4));
+                    const int rr = r4 + 4 * half;
                     const uint32_t w = offB[rr * 32];
                     const float* gR = gB + rr * (KK * 16);
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -410,6 +414,7 @@ roipool_vec_bwd_kernel(const float* __restrict__ go, const float* __restrict__ r
                             __syncwarp();
                         }
                     }
+                }
                 }
             }
             if (grp + 1 < nGroups) commit(grp + 1, buf ^ 1);
