@@ -537,8 +537,12 @@ static size_t fwd_ws_bytes(int B, int C, int H, int W) {
     return (size_t)(di.sm_count + p.T) * FwdCfg<D>::TILE_FLOATS * sizeof(float);  // enough for any stream-K split
 }
 
+bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
+size_t corr_umma_fwd_ws_bytes(int B, int C, int H, int W);
 size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d) {
-    return d == 8 ? fwd_ws_bytes<8>(B, C, H, W) : fwd_ws_bytes<4>(B, C, H, W);
+    const size_t simt = d == 8 ? fwd_ws_bytes<8>(B, C, H, W) : fwd_ws_bytes<4>(B, C, H, W);
+    const size_t umma = (d == 8 && corr_umma_supported(B, C, H, W, d, 1)) ? corr_umma_fwd_ws_bytes(B, C, H, W) : 0;
+    return simt > umma ? simt : umma;  // either forward family may be selected at call time
 }
 bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride) {
     return corr_tile_supported(B, C, H, W, d, stride);

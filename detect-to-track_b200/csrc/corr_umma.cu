@@ -46,6 +46,11 @@ constexpr int UGROUPS = 3;                // key-row groups per tile: rows [0,8)
 struct UPlan {
     int B, C, H, W;
     int tilesX, tilesY, nItems, nChunks;
+    // Work units of CTA `cta`: the whole items  round * G + cta  (round < rounds), then -- so that the last, partly
+    // filled wave does not leave most SMs idle -- one channel range (1 / split of the chunks) of a left-over item:
+    // unit  cta < left * split  ->  item rounds * G + cta / split, chunks [q, q + 1) * nChunks / split, q = cta % split,
+    // written to partial slot `cta` and summed in fixed order by corr_fwd_umma_finalize_kernel.
+    int G, rounds, left, split;
 };
 
 __device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,11 +105,28 @@ struct UInt { static constexpr int value = V; };
 
 // walks the (item, channel chunk) sequence of one CTA; item = (image, tile, key-row group)
 struct UCursor {
-    int item, chunk;
+    int rnd, item;          // rnd <= rounds: rnd == rounds is the split unit; item < 0: no more work
+    int chunk, chunkBeg, chunkEnd;
     int b, i0, j0, kr0, nRows;
-    __device__ __forceinline__ bool valid(const UPlan& p) const { return item < p.nItems; }
+    bool partial;
+    __device__ __forceinline__ bool valid(const UPlan&) const { return item >= 0; }
     __device__ __forceinline__ void decode(const UPlan& p) {
-        if (item >= p.nItems) return;
+        const int cta = blockIdx.x;
+        if (rnd < p.rounds) {
+            item = rnd * p.G + cta;
+            chunkBeg = 0;
+            chunkEnd = p.nChunks;
+            partial = false;
+        } else if (rnd == p.rounds && cta < p.left * p.split) {
+            item = p.rounds * p.G + cta / p.split;
+            const int q = cta % p.split;
+            chunkBeg = (int)((long long)q * p.nChunks / p.split);
+            chunkEnd = (int)((long long)(q + 1) * p.nChunks / p.split);
+            partial = p.split > 1;
+        } else {
+            item = -1;
+            return;
+        }
         const int g = item % UGROUPS;
         const int tile = item / UGROUPS;
         const int tpi = p.tilesX * p.tilesY;
@@ -114,17 +136,19 @@ struct UCursor {
         j0 = (t % p.tilesX) * 16;
         kr0 = 8 * g;
         nRows = g == UGROUPS - 1 ? 7 : 8;
-        chunk = 0;
+        chunk = chunkBeg;
     }
-    __device__ __forceinline__ void start(const UPlan& p) { item = blockIdx.x; decode(p); }
-    __device__ __forceinline__ bool last(const UPlan& p) const { return chunk == p.nChunks - 1; }
+    __device__ __forceinline__ void start(const UPlan& p) { rnd = 0; decode(p); }
+    __device__ __forceinline__ bool first() const { return chunk == chunkBeg; }
+    __device__ __forceinline__ bool last(const UPlan&) const { return chunk == chunkEnd - 1; }
     __device__ __forceinline__ void advance(const UPlan& p) {
-        if (++chunk >= p.nChunks) { item += gridDim.x; decode(p); }
+        if (++chunk >= chunkEnd) { ++rnd; decode(p); }
     }
 };
 
 __global__ void __launch_bounds__(UTHREADS, 1)
-corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm1, float* __restrict__ out, UPlan p) {
+corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm1, float* __restrict__ out,
+                     float* __restrict__ partial, UPlan p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* rowbuf = reinterpret_cast<float*>(smem + USTAGES * USTAGE_BYTES);
@@ -164,7 +188,7 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
             uint32_t k = 0, t = 0;
             while (c.valid(p)) {
                 const uint32_t s = k & 1u;
-                const bool first = c.chunk == 0, last = c.last(p);
+                const bool first = c.first(), last = c.last(p);
                 const uint32_t idesc = u_idesc(c.nRows * 32);
                 if (first) u_mbar_wait(&bar_acc_empty, (t & 1u) ^ 1u);  // previous item's accumulators are drained
                 u_mbar_wait(&bar_full[s], (k >> 1) & 1u);               // all producer warps have staged chunk k
@@ -291,9 +315,10 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                 {   // copy rows [tiLo, tiEnd) of the 16 queries of this tile row to their maps (24 threads per query)
                     const int len = (tiEnd - tiLo) * 17;
                     const int gi = c.i0 + qr;
-                    const int ncols = min(16, W - c.j0);
-                    if (len > 0 && gi < H) {
-                        float* dbase = out + (((size_t)c.b * H + gi) * W + c.j0) * 289;
+                    const int ncols = c.partial ? 16 : min(16, W - c.j0);
+                    if (len > 0 && (c.partial || gi < H)) {
+                        float* dbase = c.partial ? partial + ((size_t)blockIdx.x * UM + qr * 16) * 289
+                                                 : out + (((size_t)c.b * H + gi) * W + c.j0) * 289;
                         const int q = ptid / 24;
                         if (q < ncols)
                             for (int o = ptid - q * 24; o < len; o += 24) dbase[q * 289 + tiLo * 17 + o] = rowbuf[q * URP + tiLo * 17 + o];
@@ -340,6 +365,33 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
     }
 }
 
+// out <- sum over the `split` channel ranges of every left-over item (ascending range = ascending channel order)
+__global__ void __launch_bounds__(256)
+corr_fwd_umma_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, UPlan p) {
+    const int lt = blockIdx.x, qr = blockIdx.y;  // left-over item, query row of its tile
+    const int item = p.rounds * p.G + lt;
+    const int g = item % UGROUPS, tile = item / UGROUPS;
+    const int tpi = p.tilesX * p.tilesY;
+    const int b = tile / tpi, t = tile - b * tpi;
+    const int i0 = (t / p.tilesX) * 8, j0 = (t % p.tilesX) * 16;
+    const int kr0 = 8 * g, nRows = g == UGROUPS - 1 ? 7 : 8;
+    const int gi = i0 + qr;
+    if (gi >= p.H) return;
+    const int tiLo = max(0, kr0 - qr), tiHi = min(15, kr0 + nRows - 1 - qr);
+    const int tiEnd = (kr0 + nRows == 23) ? 17 : tiHi + 1;
+    const int len = (tiEnd - tiLo) * 17;
+    if (len <= 0) return;
+    const int ncols = min(16, p.W - j0);
+    float* dbase = out + (((size_t)b * p.H + gi) * p.W + j0) * 289 + tiLo * 17;
+    const float* src = partial + ((size_t)(lt * p.split) * UM + qr * 16) * 289 + tiLo * 17;
+    for (int e = threadIdx.x; e < ncols * len; e += blockDim.x) {
+        const int q = e / len, o = e - q * len;
+        float acc = 0.f;
+        for (int k = 0; k < p.split; ++k) acc += src[((size_t)k * UM + q) * 289 + o];
+        dbase[q * 289 + o] = acc;
+    }
+}
+
 }  // namespace
 
 bool corr_umma_supported(int B, int C, int H, int W, int d, int stride) {
@@ -349,25 +401,54 @@ bool corr_umma_supported(int B, int C, int H, int W, int d, int stride) {
     return true;
 }
 
-int corr_umma_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
-    (void)ws;
-    (void)ws_bytes;
+static int umma_fwd_plan(int B, int C, int H, int W, UPlan* p) {
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
+    p->B = B; p->C = C; p->H = H; p->W = W;
+    p->tilesX = ceil_div(W, 16);
+    p->tilesY = ceil_div(H, 8);
+    p->nItems = B * p->tilesX * p->tilesY * UGROUPS;
+    p->nChunks = ceil_div(C, UCH);
+    p->G = p->nItems < di.sm_count ? p->nItems : di.sm_count;
+    p->rounds = p->nItems / p->G;
+    p->left = p->nItems - p->rounds * p->G;
+    p->split = 1;
+    if (p->left > 0) {
+        p->split = p->G / p->left;
+        if (p->split > p->nChunks) p->split = p->nChunks;
+        if (p->split > 8) p->split = 8;
+        if (p->split < 1) p->split = 1;
+    }
+    return 0;
+}
+
+size_t corr_umma_fwd_ws_bytes(int B, int C, int H, int W) {
     UPlan p;
-    p.B = B; p.C = C; p.H = H; p.W = W;
-    p.tilesX = ceil_div(W, 16);
-    p.tilesY = ceil_div(H, 8);
-    p.nItems = B * p.tilesX * p.tilesY * UGROUPS;
-    p.nChunks = ceil_div(C, UCH);
-    const int grid = p.nItems < di.sm_count ? p.nItems : di.sm_count;
+    if (umma_fwd_plan(B, C, H, W, &p)) return 0;
+    return p.split > 1 ? (size_t)p.left * p.split * UM * 289 * sizeof(float) : 0;
+}
+
+int corr_umma_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+    UPlan p;
+    int rc = umma_fwd_plan(B, C, H, W, &p);
+    if (rc) return rc;
+    const size_t need = p.split > 1 ? (size_t)p.left * p.split * UM * 289 * sizeof(float) : 0;
+    if (need > 0 && (ws == nullptr || ws_bytes < need)) {
+        set_error("corr_fwd(umma): workspace too small (%zu < %zu)", ws_bytes, need);
+        return D2T_ERR_WORKSPACE;
+    }
     const size_t smem = (size_t)USTAGES * USTAGE_BYTES + UROWBUF_FLOATS * sizeof(float) + 1024;
     D2T_CUDA_TRY(cudaFuncSetAttribute(corr_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_fwd_umma_kernel<<<grid, UTHREADS, smem, st>>>(fm0, fm1, out, p);
+    corr_fwd_umma_kernel<<<p.G, UTHREADS, smem, st>>>(fm0, fm1, out, static_cast<float*>(ws), p);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
+    if (p.split > 1) {
+        corr_fwd_umma_finalize_kernel<<<dim3(p.left, 8), 256, 0, st>>>(static_cast<const float*>(ws), out, p);
+        D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
+    }
     return D2T_OK;
 }
 
