@@ -162,6 +162,48 @@ def test_corr_bwd_tensor_core_variant(cuda, B, C, H, W):
     assert torch.equal(g0, h0) and torch.equal(g1, h1)
 
 
+@pytest.mark.parametrize("B,C,H,W", [(1, 37, 38, 63), (2, 300, 9, 17), (1, 520, 20, 21)])
+def test_tensor_core_kernels_stay_inside_their_buffers(cuda, B, C, H, W):
+    """compute-sanitizer is not available on the GPU pool, so the tcgen05 kernels are run with every output and the
+    workspace embedded in larger buffers filled with a sentinel: the guard zones must come back untouched (ragged
+    channel counts, maps smaller than a tile, partial tiles in both directions)."""
+    from detect_to_track_b200 import _lib
+    lib = _lib.lib()
+    d, guard, sentinel = 8, 4096, 1234.5
+    g = torch.Generator(device="cpu").manual_seed(5)
+    fm0 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    fm1 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    go = torch.randn(B, H, W, 17, 17, generator=g).to(cuda)
+
+    def guarded(n):
+        buf = torch.full((n + 2 * guard,), sentinel, device=cuda)
+        return buf, buf[guard:guard + n]
+
+    def intact(buf, n):
+        return bool((buf[:guard] == sentinel).all()) and bool((buf[guard + n:] == sentinel).all())
+
+    stream = torch.cuda.current_stream().cuda_stream
+    n_ws = lib.d2t_corr_bwd_tc_workspace_bytes(B, C, H, W, d, 1) // 4
+    wsb, ws = guarded(n_ws)
+    g0b, g0 = guarded(fm0.numel())
+    g1b, g1 = guarded(fm1.numel())
+    rc = lib.d2t_corr_bwd_f32_tc(go.data_ptr(), fm0.data_ptr(), fm1.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, C, H, W, d, 1,
+                                 ws.data_ptr(), n_ws * 4, stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert intact(wsb, n_ws) and intact(g0b, fm0.numel()) and intact(g1b, fm1.numel())
+    assert bool(torch.isfinite(g0).all()) and bool(torch.isfinite(g1).all())
+
+    n_fws = lib.d2t_corr_fwd_workspace_bytes(B, C, H, W, d, 1, 4) // 4
+    fwb, fws = guarded(max(n_fws, 1))
+    ob, o = guarded(B * H * W * 289)
+    rc = lib.d2t_corr_fwd_f32_tc(fm0.data_ptr(), fm1.data_ptr(), o.data_ptr(), B, C, H, W, d, 1, fws.data_ptr(), n_fws * 4, stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert intact(fwb, max(n_fws, 1)) and intact(ob, B * H * W * 289)
+    assert not bool((o == sentinel).any())  # every output element is written (no memset needed)
+
+
 def test_corr_bwd_dispatch_env(cuda, monkeypatch):
     """D2T_CORR_BWD selects the kernel family behind d2t_corr_bwd_f32; both agree within the FP32 tolerance."""
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 72, 38, 63, 8, seed=15, dtype=np.float32))
