@@ -446,6 +446,12 @@ int roipool_prefix_fwd_launch(const float*, const float*, float*, int, int, int,
 bool roipool_vec_supported(int R, int C, int H, int W, int k);
 int roipool_vec_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int roipool_vec_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+// float32 column-owner backward with register accumulators (pool_col.cu)
+bool roipool_col_bwd_supported(int R, int C, int H, int W, int k);
+int roipool_col_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+// float32 [pixel][16 channel] backward, second cut: raw cp.async staging, per-row RoI lists (pool_vec2.cu)
+bool roipool_vec2_bwd_supported(int R, int C, int H, int W, int k);
+int roipool_vec2_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // float32 row-owner backward (pool_rows.cu)
 bool roipool_rows_bwd_supported(int R, int C, int H, int W, int k);
 int roipool_rows_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
@@ -478,6 +484,14 @@ struct FastPath<float> {
                     int* rc) {
         if (roipool_rows_bwd_supported(R, C, H, W, k)) {
             *rc = roipool_rows_bwd_launch(go, rois, gin, R, C, H, W, st);
+            return true;
+        }
+        if (roipool_col_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=col)
+            *rc = roipool_col_bwd_launch(go, rois, gin, R, C, H, W, st);
+            return true;
+        }
+        if (roipool_vec2_bwd_supported(R, C, H, W, k)) {  // default for r_hw = 7 (D2T_ROIPOOL_BWD=vec: previous kernel)
+            *rc = roipool_vec2_bwd_launch(go, rois, gin, R, C, H, W, st);
             return true;
         }
         if (roipool_vec_supported(R, C, H, W, k)) {

@@ -298,6 +298,27 @@ def test_roipool_vec_kernels_shapes(cuda, C, H, W, R):
     assert torch.equal(gin, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
 
 
+@pytest.mark.parametrize("variant", ["", "vec", "col"])
+@pytest.mark.parametrize("C,H,W,R", [(29, 38, 63, 300), (5, 38, 64, 1100), (18, 16, 20, 9), (1, 1, 1, 3), (7, 50, 70, 41)])
+def test_roipool_backward_variants(cuda, monkeypatch, variant, C, H, W, R):
+    """float32, r_hw = 7 backward kernels: the default (pool_vec2.cu: raw cp.async staging, per-row RoI lists, update
+    classes), the previous generation (D2T_ROIPOOL_BWD=vec, pool_vec.cu) and the column-owner experiment
+    (D2T_ROIPOOL_BWD=col, pool_col.cu; H <= 38, W <= 64, else it falls through to the default).  Each against the
+    oracle and bitwise reproducible; channel counts that are not a multiple of 4, RoI counts that are not a multiple
+    of the group size and exceed every table, RoIs whose bins are thinner than a pixel (update classes 1 and 2)."""
+    k = 7
+    rois = _roipool_rois(H, W, np.float32, R=R)
+    tiny = np.asarray([[0.4, 0.6, 3.0 / H, 4.5 / W], [0.7, 0.3, 5.0 / H, 2.0 / W], [0.2, 0.2, 0.5 / H, 0.4 / W]], np.float32)
+    rois = np.concatenate([rois, tiny], 0)
+    _, go = cases.pool_inputs(C, H, W, (rois.shape[0], C, k, k), 35, np.float32)
+    want = oracle.roipool_bwd(go, rois, H, W)
+    if variant:
+        monkeypatch.setenv("D2T_ROIPOOL_BWD", variant)
+    a = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
+    close(a, want, np.float32)
+    assert torch.equal(a, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
+
+
 def test_roipool_vs_reference_kernels(cuda):
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
