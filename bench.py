@@ -354,7 +354,7 @@ def run_ours(args):
         k2 = (2 * D + 1) ** 2
         tf32_peak = peaks.get("bf16_tflops", 1650.0) / 2  # dense TF32 = half the dense BF16 rate on this part
         fp32_peak = 72.5  # TFLOP/s, FFMA micro-benchmark on this pool's B200 (profiles/r1_microbench.txt)
-        # Dominant kernel of the step by time: roipool_vec_bwd_kernel<7> (8 launches, ~30 % of the step).  Algorithmic
+        # Dominant kernel of the step by time: roipool_vec2_bwd_kernel (8 launches, ~28 % of the step).  Algorithmic
         # bytes per launch: grad_out read + grad_fm written.
         rp_bytes = (R * TRACK_C * K * K + TRACK_C * H * W) * 4
         t_rpb, t_rpf = med("roipool_bwd"), med("roipool_fwd")
@@ -372,14 +372,14 @@ def run_ours(args):
                        "launch": ("one CUDA graph replay per step" if graph is not None else "eager launches") +
                                  f", independent ops on {n_streams} streams",
                        "parallelism": f"{world} independent pair shards, no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "roipool_vec_bwd_kernel<7> (track head: C=1891, R=300, 38x63)",
+            "roofline": {"bound": "hbm", "kernel": "roipool_vec2_bwd_kernel (track head: C=1891, R=300, 38x63)",
                          "achieved": rp_bytes / t_rpb * 1e-9, "peak": hbm, "unit": "GB/s",
-                         "frac": rp_bytes / t_rpb * 1e-9 / hbm, "traffic": 115.96e6, "peak_source": which,
+                         "frac": rp_bytes / t_rpb * 1e-9 / hbm, "traffic": 115.69e6, "peak_source": which,
                          "us_per_launch": t_rpb * 1e6, "algorithmic_bytes": rp_bytes,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
-                                           "(profiles/r1_ncu_pool_v4_summary.txt)",
-                         "note": "largest share of the step (8 launches); bound in practice by the shared-memory "
-                                 "read-modify-write pipe, see DESIGN.md section 2.3"},
+                                           "(profiles/r1_ncu_pool_v5_summary.txt)",
+                         "note": "largest share of the step (8 launches); bound in practice by warp-serial shared-memory "
+                                 "read-modify-write chains (5 warps per scheduler, 53 % issue), see DESIGN.md section 2.3"},
             "roofline_other": [
                 {"bound": "hbm", "kernel": "roipool_vec_fwd_kernel<7>", "achieved": rp_bytes / t_rpf * 1e-9, "peak": hbm,
                  "unit": "GB/s", "frac": rp_bytes / t_rpf * 1e-9 / hbm, "us_per_launch": t_rpf * 1e6},
