@@ -452,6 +452,9 @@ int roipool_col_bwd_launch(const float*, const float*, float*, int, int, int, in
 // float32 [pixel][16 channel] backward, second cut: raw cp.async staging, per-row RoI lists (pool_vec2.cu)
 bool roipool_vec2_bwd_supported(int R, int C, int H, int W, int k);
 int roipool_vec2_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+// float32 tensor-core backward experiment (pool_tc.cu)
+bool roipool_tc_bwd_supported(int R, int C, int H, int W, int k);
+int roipool_tc_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // float32 row-owner backward (pool_rows.cu)
 bool roipool_rows_bwd_supported(int R, int C, int H, int W, int k);
 int roipool_rows_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
@@ -484,6 +487,10 @@ struct FastPath<float> {
                     int* rc) {
         if (roipool_rows_bwd_supported(R, C, H, W, k)) {
             *rc = roipool_rows_bwd_launch(go, rois, gin, R, C, H, W, st);
+            return true;
+        }
+        if (roipool_tc_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=tc)
+            *rc = roipool_tc_bwd_launch(go, rois, gin, R, C, H, W, st);
             return true;
         }
         if (roipool_col_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=col)

@@ -1,0 +1,367 @@
+// pool_tc.cu -- float32 ROIPool backward on the 5th-generation tensor cores (tcgen05 + TMEM).  sm_100a.  EXPERIMENT
+// (opt-in, D2T_ROIPOOL_BWD=tc) -- see DESIGN.md section 2.3 for the measurements.
+//
+// The backward of average pooling is separable:
+//     grad_fm[c, y, x] = sum_{r,i,j} [I0_ri <= y < I1_ri] * [J0_rj <= x < J1_rj] * grad_out[r, c, i, j] / numel_rij
+// (reference: roipool_cuda.cu:115-125, one atomicAdd per bin pixel).  For ONE pair of pixel rows the sum over the
+// (RoI, bin row) pairs that touch it is a GEMM with a 0/1 operand:
+//     D[m = pixel (2 rows x 64 columns)][n = channel] = sum_{k = (r, i, j)} A[m][k] * B[n][k]
+//     A[(y, x)][(r, i, j)] = 1 if pixel (y, x) lies in bin (i, j) of RoI r, else 0        (exact in BF16)
+//     B[c][(r, i, j)]      = grad_out[r, c, i, j] / numel_rij, split into three BF16 pieces (hi + mid + lo = 24 bits)
+// and K only runs over the (r, i) that intersect the row pair (a fraction 3.8 / 38 of all bin rows), so the row
+// sparsity of the scatter is kept and the column expansion rides on the tensor core.  FP32 accumulation in TMEM in
+// ascending (r, i) order: bitwise reproducible, no atomics.
+//
+//   block      one (r, i): 8 K entries (7 bin columns + a zero pad) = one 16-byte row per pixel (A) / channel (B) in the
+//              K-major non-swizzled canonical layout; an MMA (K = 16) takes two blocks, the second one `LBO` bytes
+//              after the first (building block verified in tools/umma_bf16_blocks_test.cu).
+//   item       (row pair, tile of 192 channels): M = 128, N = 192 accumulators = 192 TMEM columns.  Items are ordered
+//              centre rows first (most RoIs) and dealt to the CTAs boustrophedon, so every CTA gets a heavy and a light one.
+//   chunk      8 blocks: A 16 KB + B 3 x 24 KB per stage, 2 stages.
+//   warps 0-15 B producers: lane = (channel of a quad, bin column); 4-byte loads of grad_out (the 7 floats of a bin row
+//              are contiguous, 4 channels per instruction), scale, split, 2-byte stores into the operand layout.
+//   warps 16-19 A producers (thread = pixel): indicator rows from the packed edge table; after the last chunk they are the
+//              epilogue: tcgen05.ld -> grad_fm[c][y][x] (lane = x: coalesced rows).
+//   warp 20    issues the MMAs, tcgen05.commit -> the stage's `empty` barrier / the item's accumulator barrier.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace d2t {
+
+namespace {
+
+constexpr int TK = 7, TKK = 49;
+constexpr int TN = 192;                         // channels per item = UMMA N = TMEM columns
+constexpr int TM = 128;                         // 2 pixel rows x 64 columns = UMMA M
+constexpr int TKB = 8;                          // blocks per chunk
+constexpr int TSTAGES = 2;
+constexpr int TA_BLK = TM * 16;                 // bytes of one A block
+constexpr int TB_BLK = TN * 16;                 // bytes of one B block (one piece)
+constexpr int TA_BYTES = TKB * TA_BLK;          // 16 KB
+constexpr int TB_BYTES = TKB * TB_BLK;          // 24 KB per piece
+constexpr int TSTAGE_BYTES = TA_BYTES + 3 * TB_BYTES;  // 88 KB
+constexpr int TPROD_WARPS = 16;
+constexpr int TA_WARP0 = TPROD_WARPS;           // warps 16-19 (TMEM lane quarter = warp % 4)
+constexpr int TMMA_WARP = TA_WARP0 + 4;
+constexpr int TTHREADS = (TMMA_WARP + 1) * 32;  // 672
+constexpr int TMAXR = 512;
+constexpr int TQUADS = TN / 4;                  // 48 channel quads per item
+constexpr int TCQ = TQUADS / TPROD_WARPS;       // 3 quads per producer warp and chunk
+constexpr uint32_t kTIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t t_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void t_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
+            t_smem(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ void t_mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(t_smem(bar)) : "memory");
+}
+// K-major SWIZZLE_NONE descriptor: 16-byte rows, 8-row groups 128 bytes apart (SBO), second K half `lbo` bytes on
+__device__ __forceinline__ uint64_t t_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void t_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kTIdesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void t_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void t_sts16(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// I0 | I1<<8 | J0<<16 | J1<<24 of bin index b (row edges from H, column edges from W); reference roipool_cuda.cu:38-50
+__device__ __forceinline__ uint32_t t_pack_edges(const float* __restrict__ roi, int b, int H, int W) {
+    int i0, i1, j0, j1;
+    bin_edge<float, true>(roi[0], roi[2], b, TK, H, i0, i1);
+    bin_edge<float, true>(roi[1], roi[3], b, TK, W, j0, j1);
+    return (uint32_t)i0 | ((uint32_t)i1 << 8) | ((uint32_t)j0 << 16) | ((uint32_t)j1 << 24);
+}
+
+__global__ void __launch_bounds__(TTHREADS, 1)
+roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, float* __restrict__ gin, int R,
+                      int C, int H, int W, int nTiles, int nPairs) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint32_t* edgeS = reinterpret_cast<uint32_t*>(smem + TSTAGES * TSTAGE_BYTES);   // [TMAXR][7]
+    uint16_t* listS = reinterpret_cast<uint16_t*>(edgeS + TMAXR * TK);              // [TMAXR * 7]  (r << 3 | i)
+    __shared__ __align__(8) uint64_t bar_full[TSTAGES], bar_empty[TSTAGES], bar_acc;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int kcntS;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int HW = H * W;
+    const int nItems = nTiles * nPairs;
+    const int G = gridDim.x;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t_smem(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; ++s) {
+            t_mbar_init(&bar_full[s], TPROD_WARPS + 4);
+            t_mbar_init(&bar_empty[s], 1);
+        }
+        t_mbar_init(&bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int idx = tid; idx < R * TK; idx += TTHREADS) {
+        const int rr = idx / TK, b = idx - rr * TK;
+        edgeS[idx] = t_pack_edges(rois + (size_t)rr * 4, b, H, W);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t smemBase = t_smem(smem);
+
+    uint32_t kg = 0;       // chunks processed so far by this CTA (all roles count alike): stage = kg & 1
+    uint32_t accItems = 0;  // items with at least one chunk so far: phase of bar_acc
+
+    for (int round = 0;; ++round) {
+        const int q = round * G + ((round & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+        if (round * G >= nItems) break;
+        if (q >= nItems) continue;  // (uniform per CTA; the next round starts past nItems and ends the loop)
+        const int rank = q / nTiles, tile = q - rank * nTiles;
+        // row pairs, centre first (most RoIs): c, c+1, c-1, c+2, ... then walk down to pair 0
+        const int cP = nPairs >> 1, U2 = 2 * (nPairs - 1 - cP);
+        const int p = rank < U2 ? ((rank & 1) ? cP + 1 + (rank >> 1) : cP - (rank >> 1)) : cP - (U2 >> 1) - (rank - U2);
+        const int y0 = 2 * p;
+        const int c0 = tile * TN;
+        const int cb = min(TN, C - c0);
+
+        // ---- the (RoI, bin row) blocks that touch rows y0, y0+1, ascending ------------------------------------
+        if (warp == 0) {
+            int cnt = 0;
+            for (int base = 0; base < R * TK; base += 32) {
+                const int e = base + lane;
+                bool f = false;
+                if (e < R * TK) {
+                    const uint32_t ed = edgeS[e];
+                    const int i0 = ed & 255, i1 = (ed >> 8) & 255;
+                    f = i1 > i0 && i0 < y0 + 2 && i1 > y0;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, f);
+                if (f) {
+                    const int rr = e / TK, i = e - rr * TK;
+                    listS[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((rr << 3) | i);
+                }
+                cnt += __popc(bal);
+            }
+            if (lane == 0) kcntS = cnt;
+        }
+        __syncthreads();
+        const int kp = kcntS;
+        const int nch = (kp + TKB - 1) / TKB;
+
+        if (warp < TPROD_WARPS) {
+            // ================================ B producers ===========================================================
+            const int j = lane & 7, chl = lane >> 3;
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t k = kg + c, s = k & 1u;
+                t_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);
+                const uint32_t bBase = smemBase + s * TSTAGE_BYTES + TA_BYTES;
+                // per block: source pointer of (channel c0, bin row i, bin column j) and 1 / numel
+                const float* src[TKB];
+                float inv[TKB];
+#pragma unroll
+                for (int b = 0; b < TKB; ++b) {
+                    const int e = c * TKB + b;
+                    src[b] = nullptr;
+                    inv[b] = 0.f;
+                    if (e < kp && j < TK) {
+                        const int ent = listS[e];
+                        const int rr = ent >> 3, i = ent & 7;
+                        const uint32_t ei = edgeS[rr * TK + i], ej = edgeS[rr * TK + j];
+                        const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
+                        const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
+                        if (hI > 0 && wJ > 0) {
+                            inv[b] = 1.0f / (float)(hI * wJ);
+                            src[b] = go + ((size_t)rr * C + c0) * TKK + i * TK + j;
+                        }
+                    }
+                }
+#pragma unroll 1
+                for (int cq = 0; cq < TCQ; ++cq) {
+                    const int ch = (cq * TPROD_WARPS + warp) * 4 + chl;
+                    const bool chOk = ch < cb;
+                    float v[TKB];
+#pragma unroll
+                    for (int b = 0; b < TKB; ++b) v[b] = (chOk && src[b] != nullptr) ? __ldg(src[b] + ch * TKK) : 0.f;
+                    const uint32_t dst = bBase + ch * 16 + j * 2;
+#pragma unroll
+                    for (int b = 0; b < TKB; ++b) {
+                        const float x = v[b] * inv[b];
+                        const __nv_bfloat16 p0 = __float2bfloat16_rn(x);
+                        const float r1 = x - __bfloat162float(p0);
+                        const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+                        const float r2 = r1 - __bfloat162float(p1);
+                        const __nv_bfloat16 p2 = __float2bfloat16_rn(r2);
+                        t_sts16(dst + b * TB_BLK, __bfloat16_as_ushort(p0));
+                        t_sts16(dst + b * TB_BLK + TB_BYTES, __bfloat16_as_ushort(p1));
+                        t_sts16(dst + b * TB_BLK + 2 * TB_BYTES, __bfloat16_as_ushort(p2));
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) t_mbar_arrive(&bar_full[s]);
+            }
+        } else if (warp < TMMA_WARP) {
+            // ================================ A producers, then epilogue ============================================
+            const int m = tid - TA_WARP0 * 32;  // pixel of the tile = TMEM lane
+            const int y = y0 + (m >> 6), x = m & 63;
+            const bool pixOk = y < H && x < W;
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t k = kg + c, s = k & 1u;
+                t_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);
+                const uint32_t aBase = smemBase + s * TSTAGE_BYTES + m * 16;
+#pragma unroll 2
+                for (int b = 0; b < TKB; ++b) {
+                    const int e = c * TKB + b;
+                    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;  // 8 bf16: bin columns 0..6 and the zero pad
+                    if (e < kp && pixOk) {
+                        const int ent = listS[e];
+                        const int rr = ent >> 3, i = ent & 7;
+                        const uint32_t ei = edgeS[rr * TK + i];
+                        if (y >= (int)(ei & 255) && y < (int)((ei >> 8) & 255)) {
+                            unsigned mask = 0;
+#pragma unroll
+                            for (int jj = 0; jj < TK; ++jj) {
+                                const uint32_t ej = edgeS[rr * TK + jj];
+                                mask |= (x >= (int)((ej >> 16) & 255) && x < (int)(ej >> 24)) ? (1u << jj) : 0u;
+                            }
+                            w0 = ((mask & 1u) ? 0x3F80u : 0u) | ((mask & 2u) ? 0x3F800000u : 0u);
+                            w1 = ((mask & 4u) ? 0x3F80u : 0u) | ((mask & 8u) ? 0x3F800000u : 0u);
+                            w2 = ((mask & 16u) ? 0x3F80u : 0u) | ((mask & 32u) ? 0x3F800000u : 0u);
+                            w3 = (mask & 64u) ? 0x3F80u : 0u;
+                        }
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aBase + b * TA_BLK), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) t_mbar_arrive(&bar_full[s]);
+            }
+            // epilogue: accumulators -> grad_fm[c0 + n][y][x]; lane = x, so every store instruction writes one row segment
+            if (nch > 0) {
+                t_mbar_wait(&bar_acc, accItems & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            float* dst = gin + (size_t)c0 * HW + (size_t)y * W + x;
+            const int quarter = warp - TA_WARP0;
+#pragma unroll 1
+            for (int n0 = 0; n0 < TN; n0 += 32) {
+                uint32_t r[32];
+                if (nch > 0) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)n0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) r[t] = 0u;  // no RoI touches this row pair
+                }
+                if (pixOk) {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t)
+                        if (n0 + t < cb) dst[(size_t)(n0 + t) * HW] = __uint_as_float(r[t]);
+                }
+            }
+        } else {
+            // ================================ MMA issuer ============================================================
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t k = kg + c, s = k & 1u;
+                t_mbar_wait(&bar_full[s], (k >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t aS = smemBase + s * TSTAGE_BYTES, bS = aS + TA_BYTES;
+                    const int nb = min(TKB, kp - c * TKB);  // live blocks of this chunk (the rest are zeros)
+#pragma unroll
+                    for (int ks = 0; ks < TKB / 2; ++ks) {
+                        if (2 * ks < nb) {
+                            const uint64_t da = t_desc(aS + 2 * ks * TA_BLK, TA_BLK);
+#pragma unroll
+                            for (int pc = 0; pc < 3; ++pc)
+                                t_mma(tmem_base, da, t_desc(bS + pc * TB_BYTES + 2 * ks * TB_BLK, TB_BLK),
+                                      (c == 0 && ks == 0 && pc == 0) ? 0u : 1u);
+                        }
+                    }
+                    t_commit(&bar_empty[s]);
+                    if (c == nch - 1) t_commit(&bar_acc);
+                }
+                __syncwarp();
+            }
+        }
+        kg += (uint32_t)nch;
+        if (nch > 0) ++accItems;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // the item's accumulators are drained and its list is no longer read
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    }
+}
+
+size_t tc_smem_bytes() {
+    return (size_t)TSTAGES * TSTAGE_BYTES + (size_t)TMAXR * TK * sizeof(uint32_t) + (size_t)TMAXR * TK * sizeof(uint16_t) + 128;
+}
+
+}  // namespace
+
+bool roipool_tc_bwd_supported(int R, int C, int H, int W, int k) {
+    if (k != TK || R <= 0 || R > TMAXR || C <= 0 || H <= 0 || W <= 0 || H > 255 || W > 64) return false;
+    if ((long long)R * C * TKK >= (1ll << 31)) return false;
+    const char* e = getenv("D2T_ROIPOOL_BWD");  // opt-in
+    if (!(e && e[0] == 't')) return false;
+    DeviceInfo di;
+    if (device_info(&di)) return false;
+    return tc_smem_bytes() <= (size_t)di.max_smem_optin;
+}
+
+int roipool_tc_bwd_launch(const float* go, const float* rois, float* gin, int R, int C, int H, int W, cudaStream_t st) {
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const int nTiles = ceil_div(C, TN), nPairs = ceil_div(H, 2);
+    const int nItems = nTiles * nPairs;
+    const int grid = nItems < di.sm_count ? nItems : di.sm_count;
+    const size_t smem = tc_smem_bytes();
+    D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roipool_tc_bwd_kernel<<<grid, TTHREADS, smem, st>>>(go, rois, gin, R, C, H, W, nTiles, nPairs);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
+}  // namespace d2t

@@ -298,7 +298,7 @@ def test_roipool_vec_kernels_shapes(cuda, C, H, W, R):
     assert torch.equal(gin, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
 
 
-@pytest.mark.parametrize("variant", ["", "vec", "col"])
+@pytest.mark.parametrize("variant", ["", "vec", "col", "tc"])
 @pytest.mark.parametrize("C,H,W,R", [(29, 38, 63, 300), (5, 38, 64, 1100), (18, 16, 20, 9), (1, 1, 1, 3), (7, 50, 70, 41)])
 def test_roipool_backward_variants(cuda, monkeypatch, variant, C, H, W, R):
     """float32, r_hw = 7 backward kernels: the default (pool_vec2.cu: raw cp.async staging, per-row RoI lists, update
