@@ -23,7 +23,6 @@
 //   warps 16-19 A producers (thread = pixel): indicator rows from the packed edge table; after the last chunk they are the
 //              epilogue: tcgen05.ld -> grad_fm[c][y][x] (lane = x: coalesced rows).
 //   warp 20    issues the MMAs, tcgen05.commit -> the stage's `empty` barrier / the item's accumulator barrier.
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -35,21 +34,24 @@ namespace {
 constexpr int TK = 7, TKK = 49;
 constexpr int TN = 192;                         // channels per item = UMMA N = TMEM columns
 constexpr int TM = 128;                         // 2 pixel rows x 64 columns = UMMA M
-constexpr int TKB = 8;                          // blocks per chunk
-constexpr int TSTAGES = 2;
-constexpr int TA_BLK = TM * 16;                 // bytes of one A block
-constexpr int TB_BLK = TN * 16;                 // bytes of one B block (one piece)
+constexpr int TKB = 4;                          // blocks per chunk
+constexpr int TSTAGES = 3;
+constexpr int TA_HALF = TM * 16;                // bytes of one K half (4 tf32 per row) of an A block
+constexpr int TB_HALF = TN * 16;                // ... of a B block
+constexpr int TA_BLK = 2 * TA_HALF;             // 4 KB
+constexpr int TB_BLK = 2 * TB_HALF;             // 6 KB per piece
 constexpr int TA_BYTES = TKB * TA_BLK;          // 16 KB
 constexpr int TB_BYTES = TKB * TB_BLK;          // 24 KB per piece
-constexpr int TSTAGE_BYTES = TA_BYTES + 3 * TB_BYTES;  // 88 KB
+constexpr int TSTAGE_BYTES = TA_BYTES + 2 * TB_BYTES;  // 64 KB
 constexpr int TPROD_WARPS = 16;
 constexpr int TA_WARP0 = TPROD_WARPS;           // warps 16-19 (TMEM lane quarter = warp % 4)
 constexpr int TMMA_WARP = TA_WARP0 + 4;
 constexpr int TTHREADS = (TMMA_WARP + 1) * 32;  // 672
 constexpr int TMAXR = 512;
 constexpr int TQUADS = TN / 4;                  // 48 channel quads per item
-constexpr int TCQ = TQUADS / TPROD_WARPS;       // 3 quads per producer warp and chunk
-constexpr uint32_t kTIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr int TCQ = TQUADS / (TPROD_WARPS / 2);  // 6 quads per producer warp and chunk (a group of 8 warps stages a chunk)
+// kind::tf32: FP32 accumulate, TF32 x TF32, both K-major
+constexpr uint32_t kTIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t t_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void t_mbar_init(uint64_t* bar, int count) {
@@ -77,16 +79,18 @@ __device__ __forceinline__ uint64_t t_desc(uint32_t saddr, uint32_t lbo_bytes) {
 __device__ __forceinline__ void t_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile(
         "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+        " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(kTIdesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void t_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_smem(bar)) : "memory");
 }
-__device__ __forceinline__ void t_sts16(uint32_t addr, unsigned short v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+__device__ __forceinline__ void t_sts32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// round-to-nearest TF32 (10 explicit mantissa bits); v - hi is exact in FP32 and |v - hi| <= 2^-11 |v|
+__device__ __forceinline__ float t_tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
 // I0 | I1<<8 | J0<<16 | J1<<24 of bin index b (row edges from H, column edges from W); reference roipool_cuda.cu:38-50
 __device__ __forceinline__ uint32_t t_pack_edges(const float* __restrict__ roi, int b, int H, int W) {
@@ -98,7 +102,7 @@ __device__ __forceinline__ uint32_t t_pack_edges(const float* __restrict__ roi, 
 
 __global__ void __launch_bounds__(TTHREADS, 1)
 roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, float* __restrict__ gin, int R,
-                      int C, int H, int W, int nTiles, int nPairs) {
+                      int C, int H, int W, int nTiles, int nPairs, int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint32_t* edgeS = reinterpret_cast<uint32_t*>(smem + TSTAGES * TSTAGE_BYTES);   // [TMAXR][7]
@@ -106,6 +110,7 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
     __shared__ __align__(8) uint64_t bar_full[TSTAGES], bar_empty[TSTAGES], bar_acc;
     __shared__ uint32_t tmem_base_s;
     __shared__ int kcntS;
+    __shared__ int wcntS[TTHREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -119,7 +124,7 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
     }
     if (tid == 0) {
         for (int s = 0; s < TSTAGES; ++s) {
-            t_mbar_init(&bar_full[s], TPROD_WARPS + 4);
+            t_mbar_init(&bar_full[s], TPROD_WARPS / 2 + 4);
             t_mbar_init(&bar_empty[s], 1);
         }
         t_mbar_init(&bar_acc, 1);
@@ -151,43 +156,72 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
         const int cb = min(TN, C - c0);
 
         // ---- the (RoI, bin row) blocks that touch rows y0, y0+1, ascending ------------------------------------
-        if (warp == 0) {
+        // every warp compacts one contiguous segment of the R x 7 candidates: count, prefix over the warps, write
+        {
+            constexpr int NW = TTHREADS / 32;
+            const int total = (dbg & 32) ? 0 : R * TK;
+            const int seg = ((total + NW - 1) / NW + 31) & ~31;  // candidates per warp, a multiple of 32
+            const int lo = warp * seg, hi = min(total, lo + seg);
+            constexpr int MAXR = (TMAXR * TK / NW + 31) / 32 + 1;  // ballot rounds per warp (R <= TMAXR)
+            unsigned bits[MAXR];
             int cnt = 0;
-            for (int base = 0; base < R * TK; base += 32) {
-                const int e = base + lane;
+#pragma unroll
+            for (int nr = 0; nr < MAXR; ++nr) {
+                const int e = lo + nr * 32 + lane;
                 bool f = false;
-                if (e < R * TK) {
+                if (e < hi) {
                     const uint32_t ed = edgeS[e];
                     const int i0 = ed & 255, i1 = (ed >> 8) & 255;
                     f = i1 > i0 && i0 < y0 + 2 && i1 > y0;
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, f);
-                if (f) {
-                    const int rr = e / TK, i = e - rr * TK;
-                    listS[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((rr << 3) | i);
-                }
-                cnt += __popc(bal);
+                bits[nr] = __ballot_sync(0xffffffffu, f);
+                cnt += __popc(bits[nr]);
             }
-            if (lane == 0) kcntS = cnt;
+            if (lane == 0) wcntS[warp] = cnt;
+            __syncthreads();
+            int off = 0, all = 0;
+            for (int w = 0; w < NW; ++w) {
+                const int cw = wcntS[w];
+                off += w < warp ? cw : 0;
+                all += cw;
+            }
+#pragma unroll
+            for (int nr = 0; nr < MAXR; ++nr) {
+                const int e = lo + nr * 32 + lane;
+                const unsigned bal = bits[nr];
+                if ((bal >> lane) & 1u) {
+                    const int rr = e / TK, i = e - rr * TK;
+                    listS[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((rr << 3) | i);
+                }
+                off += __popc(bal);
+            }
+            if (tid == 0) kcntS = all;
         }
         __syncthreads();
-        const int kp = kcntS;
+        const int kp = (dbg & 16) ? 0 : kcntS;
         const int nch = (kp + TKB - 1) / TKB;
 
         if (warp < TPROD_WARPS) {
             // ================================ B producers ===========================================================
+            // Two groups of 8 warps take alternate chunks: while one group waits for its loads of grad_out (24 per thread,
+            // all issued before the first use), the other converts and stores.  (All 16 warps on every chunk with a
+            // register prefetch one chunk ahead was measured slower, 229 vs 202 us: the per-chunk set-up below is then
+            // executed by twice as many warps, and the loads are bound by L1 wavefronts -- four 28-byte runs per
+            // instruction -- not by latency.)
             const int j = lane & 7, chl = lane >> 3;
+            const int grp = warp >> 3, wq = warp & 7;
             for (int c = 0; c < nch; ++c) {
-                const uint32_t k = kg + c, s = k & 1u;
-                t_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);
+                const uint32_t k = kg + c, s = k % TSTAGES;
+                if ((int)(k & 1u) != grp) continue;
+                t_mbar_wait(&bar_empty[s], ((k / TSTAGES) & 1u) ^ 1u);
                 const uint32_t bBase = smemBase + s * TSTAGE_BYTES + TA_BYTES;
-                // per block: source pointer of (channel c0, bin row i, bin column j) and 1 / numel
-                const float* src[TKB];
+                // per block: element offset of (channel c0, bin row i, bin column j) in grad_out (-1: none) and 1 / numel
+                int src[TKB];
                 float inv[TKB];
 #pragma unroll
                 for (int b = 0; b < TKB; ++b) {
                     const int e = c * TKB + b;
-                    src[b] = nullptr;
+                    src[b] = -1;
                     inv[b] = 0.f;
                     if (e < kp && j < TK) {
                         const int ent = listS[e];
@@ -197,29 +231,29 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
                         const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
                         if (hI > 0 && wJ > 0) {
                             inv[b] = 1.0f / (float)(hI * wJ);
-                            src[b] = go + ((size_t)rr * C + c0) * TKK + i * TK + j;
+                            src[b] = (rr * C + c0) * TKK + i * TK + j;
                         }
                     }
                 }
-#pragma unroll 1
-                for (int cq = 0; cq < TCQ; ++cq) {
-                    const int ch = (cq * TPROD_WARPS + warp) * 4 + chl;
-                    const bool chOk = ch < cb;
-                    float v[TKB];
+                float v[TCQ][TKB];
 #pragma unroll
-                    for (int b = 0; b < TKB; ++b) v[b] = (chOk && src[b] != nullptr) ? __ldg(src[b] + ch * TKK) : 0.f;
-                    const uint32_t dst = bBase + ch * 16 + j * 2;
+                for (int cq = 0; cq < TCQ; ++cq) {
+                    const int ch = (cq * 8 + wq) * 4 + chl;
+                    const bool chOk = ch < cb;
+#pragma unroll
+                    for (int b = 0; b < TKB; ++b) v[cq][b] = (chOk && src[b] >= 0 && !(dbg & 2)) ? __ldg(go + src[b] + ch * TKK) : 0.f;
+                }
+                if (!(dbg & 4))
+#pragma unroll
+                for (int cq = 0; cq < TCQ; ++cq) {
+                    const int ch = (cq * 8 + wq) * 4 + chl;
+                    const uint32_t dst = bBase + (j >> 2) * TB_HALF + ch * 16 + (j & 3) * 4;
 #pragma unroll
                     for (int b = 0; b < TKB; ++b) {
-                        const float x = v[b] * inv[b];
-                        const __nv_bfloat16 p0 = __float2bfloat16_rn(x);
-                        const float r1 = x - __bfloat162float(p0);
-                        const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
-                        const float r2 = r1 - __bfloat162float(p1);
-                        const __nv_bfloat16 p2 = __float2bfloat16_rn(r2);
-                        t_sts16(dst + b * TB_BLK, __bfloat16_as_ushort(p0));
-                        t_sts16(dst + b * TB_BLK + TB_BYTES, __bfloat16_as_ushort(p1));
-                        t_sts16(dst + b * TB_BLK + 2 * TB_BYTES, __bfloat16_as_ushort(p2));
+                        const float x = v[cq][b] * inv[b];
+                        const float hi = t_tf32_rn(x);
+                        t_sts32(dst + b * TB_BLK, hi);
+                        t_sts32(dst + b * TB_BLK + TB_BYTES, x - hi);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
@@ -232,31 +266,33 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
             const int y = y0 + (m >> 6), x = m & 63;
             const bool pixOk = y < H && x < W;
             for (int c = 0; c < nch; ++c) {
-                const uint32_t k = kg + c, s = k & 1u;
-                t_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);
+                const uint32_t k = kg + c, s = k % TSTAGES;
+                t_mbar_wait(&bar_empty[s], ((k / TSTAGES) & 1u) ^ 1u);
                 const uint32_t aBase = smemBase + s * TSTAGE_BYTES + m * 16;
+                if (!(dbg & 8))
 #pragma unroll 2
                 for (int b = 0; b < TKB; ++b) {
                     const int e = c * TKB + b;
-                    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;  // 8 bf16: bin columns 0..6 and the zero pad
+                    unsigned mask = 0;  // bin columns of block e that contain this pixel
                     if (e < kp && pixOk) {
                         const int ent = listS[e];
                         const int rr = ent >> 3, i = ent & 7;
                         const uint32_t ei = edgeS[rr * TK + i];
                         if (y >= (int)(ei & 255) && y < (int)((ei >> 8) & 255)) {
-                            unsigned mask = 0;
 #pragma unroll
                             for (int jj = 0; jj < TK; ++jj) {
                                 const uint32_t ej = edgeS[rr * TK + jj];
                                 mask |= (x >= (int)((ej >> 16) & 255) && x < (int)(ej >> 24)) ? (1u << jj) : 0u;
                             }
-                            w0 = ((mask & 1u) ? 0x3F80u : 0u) | ((mask & 2u) ? 0x3F800000u : 0u);
-                            w1 = ((mask & 4u) ? 0x3F80u : 0u) | ((mask & 8u) ? 0x3F800000u : 0u);
-                            w2 = ((mask & 16u) ? 0x3F80u : 0u) | ((mask & 32u) ? 0x3F800000u : 0u);
-                            w3 = (mask & 64u) ? 0x3F80u : 0u;
                         }
                     }
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aBase + b * TA_BLK), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                    const uint32_t one = 0x3F800000u;  // 1.0f: exact in TF32
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aBase + b * TA_BLK), "r"((mask & 1u) ? one : 0u),
+                                 "r"((mask & 2u) ? one : 0u), "r"((mask & 4u) ? one : 0u), "r"((mask & 8u) ? one : 0u)
+                                 : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aBase + b * TA_BLK + TA_HALF), "r"((mask & 16u) ? one : 0u),
+                                 "r"((mask & 32u) ? one : 0u), "r"((mask & 64u) ? one : 0u), "r"(0u)
+                                 : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -296,20 +332,18 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
         } else {
             // ================================ MMA issuer ============================================================
             for (int c = 0; c < nch; ++c) {
-                const uint32_t k = kg + c, s = k & 1u;
-                t_mbar_wait(&bar_full[s], (k >> 1) & 1u);
+                const uint32_t k = kg + c, s = k % TSTAGES;
+                t_mbar_wait(&bar_full[s], (k / TSTAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t aS = smemBase + s * TSTAGE_BYTES, bS = aS + TA_BYTES;
-                    const int nb = min(TKB, kp - c * TKB);  // live blocks of this chunk (the rest are zeros)
+                    const int nb = min(TKB, kp - c * TKB);  // live blocks of this chunk
 #pragma unroll
-                    for (int ks = 0; ks < TKB / 2; ++ks) {
-                        if (2 * ks < nb) {
-                            const uint64_t da = t_desc(aS + 2 * ks * TA_BLK, TA_BLK);
-#pragma unroll
-                            for (int pc = 0; pc < 3; ++pc)
-                                t_mma(tmem_base, da, t_desc(bS + pc * TB_BYTES + 2 * ks * TB_BLK, TB_BLK),
-                                      (c == 0 && ks == 0 && pc == 0) ? 0u : 1u);
+                    for (int b = 0; b < TKB; ++b) {
+                        if (b < nb && !(dbg & 1)) {  // one MMA (K = 8) per block and piece
+                            const uint64_t da = t_desc(aS + b * TA_BLK, TA_HALF);
+                            t_mma(tmem_base, da, t_desc(bS + b * TB_BLK, TB_HALF), (c == 0 && b == 0) ? 0u : 1u);
+                            t_mma(tmem_base, da, t_desc(bS + TB_BYTES + b * TB_BLK, TB_HALF), 1u);
                         }
                     }
                     t_commit(&bar_empty[s]);
@@ -358,7 +392,9 @@ int roipool_tc_bwd_launch(const float* go, const float* rois, float* gin, int R,
     const int grid = nItems < di.sm_count ? nItems : di.sm_count;
     const size_t smem = tc_smem_bytes();
     D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roipool_tc_bwd_kernel<<<grid, TTHREADS, smem, st>>>(go, rois, gin, R, C, H, W, nTiles, nPairs);
+    int dbg = 0;  // experiment switches (D2T_TC_DBG; results are wrong when set): 1 no MMAs, 2 no loads, 4 no B stores, 8 no A stores
+    if (const char* e = getenv("D2T_TC_DBG")) dbg = atoi(e);
+    roipool_tc_bwd_kernel<<<grid, TTHREADS, smem, st>>>(go, rois, gin, R, C, H, W, nTiles, nPairs, dbg);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;
