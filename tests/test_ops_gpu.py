@@ -204,6 +204,39 @@ def test_tensor_core_kernels_stay_inside_their_buffers(cuda, B, C, H, W):
     assert not bool((o == sentinel).any())  # every output element is written (no memset needed)
 
 
+@pytest.mark.parametrize("variant", ["", "vec", "col", "tc"])
+@pytest.mark.parametrize("C,H,W,R", [(29, 38, 63, 97), (200, 17, 64, 300), (3, 38, 20, 5)])
+def test_roipool_backward_variants_stay_inside_their_buffers(cuda, monkeypatch, variant, C, H, W, R):
+    """every float32 ROIPool backward kernel with its output embedded in a sentinel-filled buffer and grad_out at the very
+    end of its allocation: guard zones untouched, every output element written (ragged channel tiles, partial RoI
+    groups / chunks, a channel count above one 192-channel tensor-core tile)."""
+    from detect_to_track_b200 import _lib
+    lib = _lib.lib()
+    k, guard, sentinel = 7, 4096, 1234.5
+    rois_np = _roipool_rois(H, W, np.float32, R=R)
+    R = rois_np.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(6)
+    n_go = R * C * k * k
+    gob = torch.full((guard + n_go,), sentinel, device=cuda)
+    go = gob[guard:]
+    go.copy_(torch.randn(n_go, generator=g))
+    rois = dev(rois_np, cuda)
+    n = C * H * W
+    buf = torch.full((n + 2 * guard,), sentinel, device=cuda)
+    gin = buf[guard:guard + n]
+    if variant:
+        monkeypatch.setenv("D2T_ROIPOOL_BWD", variant)
+    rc = lib.d2t_roipool_bwd_f32(go.data_ptr(), rois.data_ptr(), gin.data_ptr(), R, C, H, W, k, None, 0,
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + n:] == sentinel).all())
+    assert bool((gob[:guard] == sentinel).all())
+    assert not bool((gin == sentinel).any()) and bool(torch.isfinite(gin).all())
+    want = oracle.roipool_bwd(go.view(R, C, k, k).cpu().numpy(), rois_np, H, W)
+    close(gin.view(C, H, W), want, np.float32)
+
+
 def test_corr_bwd_dispatch_env(cuda, monkeypatch):
     """D2T_CORR_BWD selects the kernel family behind d2t_corr_bwd_f32; both agree within the FP32 tolerance."""
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 72, 38, 63, 8, seed=15, dtype=np.float32))

@@ -38,6 +38,10 @@ for (C, H, W, k, dt) in [(37, 38, 63, 7, np.float32), (5, 11, 10, 6, np.float64)
         os.environ["D2T_ROIPOOL_ROWS"] = "1"
         rp.roipool_backward(torch.from_numpy(go).to(dev), r, H, W)
         os.environ.pop("D2T_ROIPOOL_ROWS")
+        for variant in ("vec", "col", "tc"):  # previous generation, column-owner and tensor-core experiments
+            os.environ["D2T_ROIPOOL_BWD"] = variant
+            rp.roipool_backward(torch.from_numpy(go).to(dev), r, H, W)
+        os.environ.pop("D2T_ROIPOOL_BWD")
 for (nT, H, W, k, dt) in [(31, 38, 63, 7, np.float32), (2, 11, 10, 6, np.float64)]:
     rois = np.concatenate([cases.rois_edge_cases(H, W, dt), cases.rois_random(70, 3, dt), cases.ROIS_OOB.astype(dt)])
     fm, go = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 9, dt)
