@@ -32,8 +32,6 @@ constexpr int V2K = 7, V2KK = 49;
 constexpr int V2Slots = 16;                 // channel slots per CTA (4 quads of 4)
 constexpr int V2RG = 8;                     // RoIs per staged group
 constexpr int V2ChPitch = 50;               // staged floats per channel
-constexpr int V2Slab = V2Slots * V2ChPitch;  // staged floats per RoI
-constexpr int V2Stage = V2RG * V2Slab;      // floats per stage
 constexpr int V2Threads = 640;
 constexpr int V2Copies = (V2RG * V2Slots * V2KK + V2Threads - 1) / V2Threads;  // cp.async per thread and group
 constexpr int V2EdgeSlot = 64;              // words per edge slot (56 used)
@@ -59,11 +57,14 @@ __device__ __forceinline__ uint32_t v2_pack_edges(const float* __restrict__ roi,
 struct V2Smem {
     size_t d, raw, inv, off, edge, list, cnt, counter, total;
 };
-__host__ __device__ inline V2Smem v2_layout(int H, int W) {
+// A RoI's staged slab holds CB channels (not 16 slots): with CB = 13 at the track-head size that leaves ~20 KB of the SM's
+// shared memory free, enough for a PSROIPool CTA of another stream to be co-resident.  Lanes of dead channel slots read
+// past their slab (another RoI's values or table bytes, always inside the allocation); nothing they compute is stored.
+__host__ __device__ inline V2Smem v2_layout(int H, int W, int CB) {
     V2Smem s;
     size_t o = 0;
     s.d = o;       o += (size_t)H * v2_row_pitch(W) * sizeof(float);
-    s.raw = o;     o += (size_t)2 * V2Stage * sizeof(float);
+    s.raw = o;     o += (size_t)2 * V2RG * CB * V2ChPitch * sizeof(float);
     s.inv = o;     o += (size_t)2 * V2RG * V2KK * sizeof(float);
     s.off = o;     o += (size_t)2 * V2RG * 32 * sizeof(uint32_t);
     s.edge = o;    o += (size_t)3 * V2EdgeSlot * sizeof(uint32_t);
@@ -78,10 +79,12 @@ __global__ void __launch_bounds__(V2Threads, 1)
 roipool_vec2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, float* __restrict__ gin, int R,
                         int C, int H, int W, int CB) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const V2Smem L = v2_layout(H, W);
+    const V2Smem L = v2_layout(H, W, CB);
+    const int slab = CB * V2ChPitch;   // staged floats per RoI
+    const int stage = V2RG * slab;     // floats per stage
     const int rowPitch = v2_row_pitch(W);
     float* D = reinterpret_cast<float*>(smem_raw + L.d);
-    float* rawS = reinterpret_cast<float*>(smem_raw + L.raw);           // [2][RG][16][50]
+    float* rawS = reinterpret_cast<float*>(smem_raw + L.raw);           // [2][RG][CB][50]
     float* invS = reinterpret_cast<float*>(smem_raw + L.inv);           // [2][RG][49]
     uint32_t* offS = reinterpret_cast<uint32_t*>(smem_raw + L.off);     // [2][RG][32]
     uint32_t* edgeG = reinterpret_cast<uint32_t*>(smem_raw + L.edge);   // [3][64]
@@ -111,7 +114,7 @@ roipool_vec2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ 
         if (idx < V2RG * slabN) {
             const int rr = idx / slabN, e = idx - rr * slabN;
             cpSrc[n] = rr * C * V2KK + e;
-            cpDst[n] = (uint32_t)((rr * V2Slab + e + e / V2KK) * 4) | ((uint32_t)rr << 16);
+            cpDst[n] = (uint32_t)((rr * slab + e + e / V2KK) * 4) | ((uint32_t)rr << 16);
         }
     }
 
@@ -126,7 +129,7 @@ roipool_vec2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ 
     // raw grad_out slabs of group g -> stage buf
     auto issue = [&](int g, int buf) {
         const float* srcG = go + ((size_t)g * V2RG * C + c0) * V2KK;
-        const uint32_t dstG = rawAddr + (uint32_t)buf * (V2Stage * 4);
+        const uint32_t dstG = rawAddr + (uint32_t)buf * (uint32_t)(stage * 4);
         const int nr = min(V2RG, R - g * V2RG);
 #pragma unroll
         for (int n = 0; n < V2Copies; ++n)
@@ -205,7 +208,7 @@ roipool_vec2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ 
         if (g + 1 < nG) issue(g + 1, buf ^ 1);
         if (g + 2 < nG) edges(g + 2);
 
-        const float* rawB = rawS + buf * V2Stage + laneRaw;
+        const float* rawB = rawS + buf * stage + laneRaw;
         const float* invB = invS + buf * (V2RG * V2KK) + jc;
         const uint32_t* offB = offS + buf * (V2RG * 32) + lane;
         const uint16_t* listB = listS + buf * H * V2RG;
@@ -228,7 +231,7 @@ roipool_vec2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ 
                 const int rr = ent >> 8;
                 unsigned cover = ent & 0xffu;
                 const uint32_t w = offB[rr * 32];
-                const float* gR = rawB + rr * V2Slab;
+                const float* gR = rawB + rr * slab;
                 const float* iR = invB + rr * V2KK;
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 do {  // bin rows containing y (1, or 2 where floor/ceil edges overlap)
@@ -324,7 +327,7 @@ bool roipool_vec2_bwd_supported(int R, int C, int H, int W, int k) {
     if (e && e[0] != '\0' && !(e[0] == 'v' && e[1] == '2')) return false;
     DeviceInfo di;
     if (device_info(&di)) return false;
-    return v2_layout(H, W).total <= (size_t)di.max_smem_optin;
+    return v2_layout(H, W, V2Slots).total <= (size_t)di.max_smem_optin;
 }
 
 int roipool_vec2_bwd_launch(const float* go, const float* rois, float* gin, int R, int C, int H, int W,
@@ -340,7 +343,7 @@ int roipool_vec2_bwd_launch(const float* go, const float* rois, float* gin, int 
         if (CB > V2Slots) CB = V2Slots;
     }
     if (CB < 1) CB = 1;
-    const size_t smem = v2_layout(H, W).total;
+    const size_t smem = v2_layout(H, W, CB).total;
     D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_vec2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roipool_vec2_bwd_kernel<<<ceil_div(C, CB), V2Threads, smem, st>>>(go, rois, gin, R, C, H, W, CB);
     D2T_CUDA_TRY(cudaGetLastError());
