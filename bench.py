@@ -338,7 +338,7 @@ def run_ours(args):
 
     # ---- end to end from host buffers through the nn.Module API ------------------------------------
     e2e_steps = max(1, min(args.steps, 5))
-    e2e_ms, h2d, d2h, e2e_mode = run_e2e(torch, dev, d2t, e2e_steps, barrier, rank)
+    e2e_ms, h2d, d2h, e2e_mode = run_e2e(torch, dev, d2t, e2e_steps, barrier, rank, world)
 
     ms, e2e_ms = global_max([ms, e2e_ms], dev)
 
@@ -395,7 +395,9 @@ def run_ours(args):
             ],
             "e2e": {"value": job_throughput(world, e2e_steps, e2e_ms), "unit": "frame-pairs/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "launch": e2e_mode},
+                    "launch": e2e_mode,
+                    "collective": ("NCCL all-reduce (average) of the tracker's parameter gradients once per step"
+                                   if world > 1 else "none (1 GPU)")},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -411,7 +413,7 @@ def run_ours(args):
     return 0
 
 
-def run_e2e(torch, dev, d2t, steps, barrier, rank):
+def run_e2e(torch, dev, d2t, steps, barrier, rank, world=1):
     """Host buffers -> public nn.Module API (wired like correlation_tracker.py / rfcn.py) -> scalar loss on the host.
 
     Per pair the host supplies the backbone pyramids of both frames (c3 at stride 8, down-sampled on the device
@@ -460,6 +462,16 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
             loss = loss + reg_pool(d["reg_map"][f], d["rois"][f]).mean(-1).mean(-1).square().mean()
         return loss
 
+    def allreduce_grads():
+        """the one collective of the path: the data-parallel gradient all-reduce of the parameters
+        the ops' callers own (the tracker's regression layer), averaged over the pair shards; NCCL, N > 1 only"""
+        if world > 1:
+            import torch.distributed as dist
+            for prm in tracker.parameters():
+                if prm.grad is not None:
+                    dist.all_reduce(prm.grad, op=dist.ReduceOp.SUM)
+                    prm.grad.div_(world)
+
     def upload(it):
         """pair -> device on the copy stream (pinned host memory, asynchronous); returns (tensors, ready-event)"""
         with torch.cuda.stream(copy_stream):
@@ -488,6 +500,7 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
             loss = pair_loss(d)
             loss.backward()
             total = total + loss.detach()
+        allreduce_grads()
         loss_host.copy_(total.reshape(1), non_blocking=True)
         main.synchronize()
         tracker.zero_grad(set_to_none=True)
@@ -518,18 +531,18 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
                     pair_loss(d).backward()
         main.wait_stream(side)
         torch.cuda.synchronize(dev)
+        for prm in tracker.parameters():  # both graphs accumulate the parameter gradients in place into these
+            prm.grad = torch.zeros_like(prm)
         for d in sets:
             for k in grad_keys:
                 for t in d[k]:
                     t.grad = None
-            tracker.zero_grad(set_to_none=True)
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr):
                 loss = pair_loss(d)
                 loss.backward()
                 totals.add_(loss.detach())
             graphs.append(gr)
-        tracker.zero_grad(set_to_none=True)
         ready = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
 
@@ -546,6 +559,8 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
 
         def step():
             totals.zero_()
+            for prm in tracker.parameters():
+                prm.grad.zero_()
             if not state["have0"]:
                 for st in range(2):
                     done[st].record(main)
@@ -562,6 +577,7 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
             # first one's pair 0 during the warm-up step, the last one prefetches a pair nobody uses)
             fill(0)
             state["have0"] = True
+            allreduce_grads()
             loss_host.copy_(totals.reshape(1), non_blocking=True)
             main.synchronize()
             return float(loss_host[0])
@@ -570,14 +586,22 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank):
 
     want = eager_step()
     one_step, mode = eager_step, "eager module calls"
+    graph_step = None
     try:
         graph_step = build_graph_step()
+    except Exception as exc:  # capture unsupported: keep the eager step and say so
+        print(f"[bench] e2e graph capture failed ({exc!r}); timing the eager step", file=sys.stderr, flush=True)
+    if world > 1:  # every rank must run the same step (it contains a collective)
+        import torch.distributed as dist
+        flag = torch.tensor([1 if graph_step is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            graph_step = None
+    if graph_step is not None:
         got = graph_step()
         if not (got == got and abs(got - want) <= 1e-4 * max(1.0, abs(want))):
             raise RuntimeError(f"graph-replayed step loss {got} != eager loss {want}")
         one_step, mode = graph_step, "module calls of a pair captured as a CUDA graph (2 static input sets)"
-    except Exception as exc:  # capture unsupported: keep the eager step and say so
-        print(f"[bench] e2e graph capture failed ({exc!r}); timing the eager step", file=sys.stderr, flush=True)
     one_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
