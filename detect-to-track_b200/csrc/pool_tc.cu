@@ -47,9 +47,10 @@ constexpr int TPROD_WARPS = 16;
 constexpr int TA_WARP0 = TPROD_WARPS;           // warps 16-19 (TMEM lane quarter = warp % 4)
 constexpr int TMMA_WARP = TA_WARP0 + 4;
 constexpr int TTHREADS = (TMMA_WARP + 1) * 32;  // 672
-constexpr int TMAXR = 512;
+constexpr int TMAXR = 320;
+constexpr int THDR = 576;                        // list entries with a precomputed header (offset + 8 reciprocals)
 constexpr int TQUADS = TN / 4;                  // 48 channel quads per item
-constexpr int TCQ = TQUADS / (TPROD_WARPS / 2);  // 6 quads per producer warp and chunk (a group of 8 warps stages a chunk)
+constexpr int TCQ = TQUADS / TPROD_WARPS;       // 3 quads per producer warp and chunk
 // kind::tf32: FP32 accumulate, TF32 x TF32, both K-major
 constexpr uint32_t kTIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
@@ -57,11 +58,13 @@ __device__ __forceinline__ uint32_t t_smem(const void* p) { return (uint32_t)__c
 __device__ __forceinline__ void t_mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem(bar)), "r"(count));
 }
+// plain try_wait spin (no suspend-time hint): chunks are short here and the wake-up latency of a suspended wait would be
+// exposed once per chunk
 __device__ __forceinline__ void t_mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
-        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
             t_smem(bar)),
-        "r"(parity), "r"(0x989680u)
+        "r"(parity)
         : "memory");
 }
 __device__ __forceinline__ void t_mbar_arrive(uint64_t* bar) {
@@ -107,6 +110,8 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint32_t* edgeS = reinterpret_cast<uint32_t*>(smem + TSTAGES * TSTAGE_BYTES);   // [TMAXR][7]
     uint16_t* listS = reinterpret_cast<uint16_t*>(edgeS + TMAXR * TK);              // [TMAXR * 7]  (r << 3 | i)
+    int* hdrSrc = reinterpret_cast<int*>(listS + TMAXR * TK);                       // [THDR] grad_out offset of (c0, i, j=0)
+    float* hdrInv = reinterpret_cast<float*>(hdrSrc + THDR);                        // [THDR][8] 1 / numel (0: empty bin / pad)
     __shared__ __align__(8) uint64_t bar_full[TSTAGES], bar_empty[TSTAGES], bar_acc;
     __shared__ uint32_t tmem_base_s;
     __shared__ int kcntS;
@@ -124,7 +129,7 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
     }
     if (tid == 0) {
         for (int s = 0; s < TSTAGES; ++s) {
-            t_mbar_init(&bar_full[s], TPROD_WARPS / 2 + 4);
+            t_mbar_init(&bar_full[s], TPROD_WARPS + 4);
             t_mbar_init(&bar_empty[s], 1);
         }
         t_mbar_init(&bar_acc, 1);
@@ -199,38 +204,51 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
         }
         __syncthreads();
         const int kp = (dbg & 16) ? 0 : kcntS;
+        // per-entry headers, once per item: what every producer lane would otherwise recompute for every chunk
+        for (int idx = tid; idx < min(kp, THDR) * 8; idx += TTHREADS) {
+            const int e = idx >> 3, jj = idx & 7;
+            const int ent = listS[e];
+            const int rr = ent >> 3, i = ent & 7;
+            const uint32_t ei = edgeS[rr * TK + i];
+            const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
+            float inv = 0.f;
+            if (jj < TK) {
+                const uint32_t ej = edgeS[rr * TK + jj];
+                const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
+                if (hI > 0 && wJ > 0) inv = 1.0f / (float)(hI * wJ);
+            }
+            hdrInv[idx] = inv;
+            if (jj == 0) hdrSrc[e] = (rr * C + c0) * TKK + i * TK;
+        }
+        __syncthreads();
         const int nch = (kp + TKB - 1) / TKB;
 
         if (warp < TPROD_WARPS) {
             // ================================ B producers ===========================================================
-            // Two groups of 8 warps take alternate chunks: while one group waits for its loads of grad_out (24 per thread,
-            // all issued before the first use), the other converts and stores.  (All 16 warps on every chunk with a
-            // register prefetch one chunk ahead was measured slower, 229 vs 202 us: the per-chunk set-up below is then
-            // executed by twice as many warps, and the loads are bound by L1 wavefronts -- four 28-byte runs per
-            // instruction -- not by latency.)
+            // All 16 warps stage every chunk: 12 values per thread, loaded before the stage wait.  What bounds this kernel is
+            // the number of instructions a warp executes per chunk (each warp issues once per ~8 cycles with 21 warps on
+            // the SM), so the per-block set-up comes from the item's header table instead of being recomputed per lane.
             const int j = lane & 7, chl = lane >> 3;
-            const int grp = warp >> 3, wq = warp & 7;
             for (int c = 0; c < nch; ++c) {
                 const uint32_t k = kg + c, s = k % TSTAGES;
-                if ((int)(k & 1u) != grp) continue;
-                t_mbar_wait(&bar_empty[s], ((k / TSTAGES) & 1u) ^ 1u);
-                const uint32_t bBase = smemBase + s * TSTAGE_BYTES + TA_BYTES;
-                // per block: element offset of (channel c0, bin row i, bin column j) in grad_out (-1: none) and 1 / numel
                 int src[TKB];
                 float inv[TKB];
 #pragma unroll
                 for (int b = 0; b < TKB; ++b) {
                     const int e = c * TKB + b;
-                    src[b] = -1;
+                    src[b] = 0;
                     inv[b] = 0.f;
-                    if (e < kp && j < TK) {
-                        const int ent = listS[e];
-                        const int rr = ent >> 3, i = ent & 7;
-                        const uint32_t ei = edgeS[rr * TK + i], ej = edgeS[rr * TK + j];
-                        const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
-                        const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
-                        if (hI > 0 && wJ > 0) {
-                            inv[b] = 1.0f / (float)(hI * wJ);
+                    if (e < kp) {
+                        if (e < THDR) {
+                            src[b] = hdrSrc[e] + j;
+                            inv[b] = hdrInv[e * 8 + j];
+                        } else if (j < TK) {  // more blocks than header slots (very many RoIs on one row pair)
+                            const int ent = listS[e];
+                            const int rr = ent >> 3, i = ent & 7;
+                            const uint32_t ei = edgeS[rr * TK + i], ej = edgeS[rr * TK + j];
+                            const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
+                            const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
+                            if (hI > 0 && wJ > 0) inv[b] = 1.0f / (float)(hI * wJ);
                             src[b] = (rr * C + c0) * TKK + i * TK + j;
                         }
                     }
@@ -238,15 +256,18 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
                 float v[TCQ][TKB];
 #pragma unroll
                 for (int cq = 0; cq < TCQ; ++cq) {
-                    const int ch = (cq * 8 + wq) * 4 + chl;
+                    const int ch = (cq * TPROD_WARPS + warp) * 4 + chl;
                     const bool chOk = ch < cb;
 #pragma unroll
-                    for (int b = 0; b < TKB; ++b) v[cq][b] = (chOk && src[b] >= 0 && !(dbg & 2)) ? __ldg(go + src[b] + ch * TKK) : 0.f;
+                    for (int b = 0; b < TKB; ++b)  // an empty bin (inv = 0) is not loaded: 0 * Inf would poison the tile
+                        v[cq][b] = (chOk && inv[b] != 0.f && !(dbg & 2)) ? __ldg(go + src[b] + ch * TKK) : 0.f;
                 }
+                t_mbar_wait(&bar_empty[s], ((k / TSTAGES) & 1u) ^ 1u);
+                const uint32_t bBase = smemBase + s * TSTAGE_BYTES + TA_BYTES;
                 if (!(dbg & 4))
 #pragma unroll
                 for (int cq = 0; cq < TCQ; ++cq) {
-                    const int ch = (cq * 8 + wq) * 4 + chl;
+                    const int ch = (cq * TPROD_WARPS + warp) * 4 + chl;
                     const uint32_t dst = bBase + (j >> 2) * TB_HALF + ch * 16 + (j & 3) * 4;
 #pragma unroll
                     for (int b = 0; b < TKB; ++b) {
@@ -256,7 +277,7 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
                         t_sts32(dst + b * TB_BLK + TB_BYTES, x - hi);
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+                if (!(dbg & 64)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) t_mbar_arrive(&bar_full[s]);
             }
@@ -265,36 +286,53 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
             const int m = tid - TA_WARP0 * 32;  // pixel of the tile = TMEM lane
             const int y = y0 + (m >> 6), x = m & 63;
             const bool pixOk = y < H && x < W;
+            // staging map: thread = (pixel column ax, half of the chunk's blocks), both pixel rows of the pair -- the column
+            // mask of a RoI is computed once for the two rows and reused while consecutive blocks belong to the same RoI
+            const int ax = m & 63, ahalf = m >> 6;
+            int lastR = -1;
+            unsigned lastMask = 0;
             for (int c = 0; c < nch; ++c) {
                 const uint32_t k = kg + c, s = k % TSTAGES;
                 t_mbar_wait(&bar_empty[s], ((k / TSTAGES) & 1u) ^ 1u);
-                const uint32_t aBase = smemBase + s * TSTAGE_BYTES + m * 16;
+                const uint32_t aBase = smemBase + s * TSTAGE_BYTES + ax * 16;
                 if (!(dbg & 8))
-#pragma unroll 2
-                for (int b = 0; b < TKB; ++b) {
+#pragma unroll
+                for (int bb = 0; bb < TKB / 2; ++bb) {
+                    const int b = ahalf * (TKB / 2) + bb;
                     const int e = c * TKB + b;
-                    unsigned mask = 0;  // bin columns of block e that contain this pixel
-                    if (e < kp && pixOk) {
+                    unsigned mask = 0;  // bin columns of block e that contain pixel column ax
+                    bool cov0 = false, cov1 = false;
+                    if (e < kp && ax < W) {
                         const int ent = listS[e];
                         const int rr = ent >> 3, i = ent & 7;
                         const uint32_t ei = edgeS[rr * TK + i];
-                        if (y >= (int)(ei & 255) && y < (int)((ei >> 8) & 255)) {
+                        const int I0 = ei & 255, I1 = (ei >> 8) & 255;
+                        cov0 = y0 >= I0 && y0 < I1;
+                        cov1 = y0 + 1 >= I0 && y0 + 1 < I1 && y0 + 1 < H;
+                        if (rr != lastR) {
+                            lastMask = 0;
 #pragma unroll
                             for (int jj = 0; jj < TK; ++jj) {
                                 const uint32_t ej = edgeS[rr * TK + jj];
-                                mask |= (x >= (int)((ej >> 16) & 255) && x < (int)(ej >> 24)) ? (1u << jj) : 0u;
+                                lastMask |= (ax >= (int)((ej >> 16) & 255) && ax < (int)(ej >> 24)) ? (1u << jj) : 0u;
                             }
+                            lastR = rr;
                         }
+                        mask = lastMask;
                     }
                     const uint32_t one = 0x3F800000u;  // 1.0f: exact in TF32
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aBase + b * TA_BLK), "r"((mask & 1u) ? one : 0u),
-                                 "r"((mask & 2u) ? one : 0u), "r"((mask & 4u) ? one : 0u), "r"((mask & 8u) ? one : 0u)
-                                 : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aBase + b * TA_BLK + TA_HALF), "r"((mask & 16u) ? one : 0u),
-                                 "r"((mask & 32u) ? one : 0u), "r"((mask & 64u) ? one : 0u), "r"(0u)
-                                 : "memory");
+                    const unsigned m0 = cov0 ? mask : 0u, m1 = cov1 ? mask : 0u;
+                    const uint32_t a0 = aBase + b * TA_BLK, a1 = a0 + 64 * 16;  // rows y0 and y0 + 1 of the tile
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"((m0 & 1u) ? one : 0u), "r"((m0 & 2u) ? one : 0u),
+                                 "r"((m0 & 4u) ? one : 0u), "r"((m0 & 8u) ? one : 0u) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0 + TA_HALF), "r"((m0 & 16u) ? one : 0u),
+                                 "r"((m0 & 32u) ? one : 0u), "r"((m0 & 64u) ? one : 0u), "r"(0u) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"((m1 & 1u) ? one : 0u), "r"((m1 & 2u) ? one : 0u),
+                                 "r"((m1 & 4u) ? one : 0u), "r"((m1 & 8u) ? one : 0u) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1 + TA_HALF), "r"((m1 & 16u) ? one : 0u),
+                                 "r"((m1 & 32u) ? one : 0u), "r"((m1 & 64u) ? one : 0u), "r"(0u) : "memory");
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (!(dbg & 64)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) t_mbar_arrive(&bar_full[s]);
             }
@@ -346,8 +384,13 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
                             t_mma(tmem_base, da, t_desc(bS + TB_BYTES + b * TB_BLK, TB_HALF), 1u);
                         }
                     }
-                    t_commit(&bar_empty[s]);
-                    if (c == nch - 1) t_commit(&bar_acc);
+                    if (dbg & 128) {  // experiment: software arrives instead of tcgen05.commit (only meaningful with dbg & 1)
+                        t_mbar_arrive(&bar_empty[s]);
+                        if (c == nch - 1) t_mbar_arrive(&bar_acc);
+                    } else {
+                        t_commit(&bar_empty[s]);
+                        if (c == nch - 1) t_commit(&bar_acc);
+                    }
                 }
                 __syncwarp();
             }
@@ -368,7 +411,8 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
 }
 
 size_t tc_smem_bytes() {
-    return (size_t)TSTAGES * TSTAGE_BYTES + (size_t)TMAXR * TK * sizeof(uint32_t) + (size_t)TMAXR * TK * sizeof(uint16_t) + 128;
+    return (size_t)TSTAGES * TSTAGE_BYTES + (size_t)TMAXR * TK * sizeof(uint32_t) + (size_t)TMAXR * TK * sizeof(uint16_t) +
+           (size_t)THDR * 9 * sizeof(float) + 128;
 }
 
 }  // namespace
