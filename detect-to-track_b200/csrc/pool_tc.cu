@@ -229,49 +229,72 @@ roipool_tc_bwd_kernel(const float* __restrict__ go, const float* __restrict__ ro
             // the number of instructions a warp executes per chunk (each warp issues once per ~8 cycles with 21 warps on
             // the SM), so the per-block set-up comes from the item's header table instead of being recomputed per lane.
             const int j = lane & 7, chl = lane >> 3;
-            for (int c = 0; c < nch; ++c) {
-                const uint32_t k = kg + c, s = k % TSTAGES;
-                int src[TKB];
-                float inv[TKB];
+            // loop-invariant per item: one base pointer per channel quad (channels past the tile's end are clamped to its
+            // last channel -- their operand rows feed accumulator columns that are never stored), one operand offset
+            const float* base[TCQ];
+            uint32_t dstOff[TCQ];
+#pragma unroll
+            for (int cq = 0; cq < TCQ; ++cq) {
+                const int ch = (cq * TPROD_WARPS + warp) * 4 + chl;
+                base[cq] = go + (size_t)min(ch, cb - 1) * TKK + min(j, TK - 1);
+                dstOff[cq] = (uint32_t)(TA_BYTES + (j >> 2) * TB_HALF + ch * 16 + (j & 3) * 4);
+            }
+            // operands of chunk c -> registers: per block the header's offset and reciprocal (0 for the pad column, an
+            // empty bin or a block past the list's end), then 12 unconditional loads
+            float vN[TCQ][TKB], invN[TKB];
+            auto fetch = [&](int c) {
+                int off[TKB];
 #pragma unroll
                 for (int b = 0; b < TKB; ++b) {
                     const int e = c * TKB + b;
-                    src[b] = 0;
-                    inv[b] = 0.f;
+                    off[b] = 0;
+                    invN[b] = 0.f;
                     if (e < kp) {
                         if (e < THDR) {
-                            src[b] = hdrSrc[e] + j;
-                            inv[b] = hdrInv[e * 8 + j];
-                        } else if (j < TK) {  // more blocks than header slots (very many RoIs on one row pair)
+                            off[b] = hdrSrc[e];
+                            invN[b] = hdrInv[e * 8 + j];
+                        } else {  // more blocks than header slots (very many RoIs on one row pair)
                             const int ent = listS[e];
                             const int rr = ent >> 3, i = ent & 7;
-                            const uint32_t ei = edgeS[rr * TK + i], ej = edgeS[rr * TK + j];
+                            const uint32_t ei = edgeS[rr * TK + i], ej = edgeS[rr * TK + min(j, TK - 1)];
                             const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
                             const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
-                            if (hI > 0 && wJ > 0) inv[b] = 1.0f / (float)(hI * wJ);
-                            src[b] = (rr * C + c0) * TKK + i * TK + j;
+                            if (j < TK && hI > 0 && wJ > 0) invN[b] = 1.0f / (float)(hI * wJ);
+                            off[b] = (rr * C + c0) * TKK + i * TK;
                         }
                     }
                 }
-                float v[TCQ][TKB];
+                if (!(dbg & 2))
 #pragma unroll
-                for (int cq = 0; cq < TCQ; ++cq) {
-                    const int ch = (cq * TPROD_WARPS + warp) * 4 + chl;
-                    const bool chOk = ch < cb;
+                for (int cq = 0; cq < TCQ; ++cq)
 #pragma unroll
-                    for (int b = 0; b < TKB; ++b)  // an empty bin (inv = 0) is not loaded: 0 * Inf would poison the tile
-                        v[cq][b] = (chOk && inv[b] != 0.f && !(dbg & 2)) ? __ldg(go + src[b] + ch * TKK) : 0.f;
+                    for (int b = 0; b < TKB; ++b) vN[cq][b] = __ldg(base[cq] + off[b]);
+            };
+#pragma unroll
+            for (int cq = 0; cq < TCQ; ++cq)
+#pragma unroll
+                for (int b = 0; b < TKB; ++b) vN[cq][b] = 0.f;
+            if (nch > 0) fetch(0);
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t k = kg + c, s = k % TSTAGES;
+                float v[TCQ][TKB], inv[TKB];
+#pragma unroll
+                for (int b = 0; b < TKB; ++b) {
+                    inv[b] = invN[b];
+#pragma unroll
+                    for (int cq = 0; cq < TCQ; ++cq) v[cq][b] = vN[cq][b];
                 }
+                if (c + 1 < nch) fetch(c + 1);  // the next chunk's loads fly while this one is converted
                 t_mbar_wait(&bar_empty[s], ((k / TSTAGES) & 1u) ^ 1u);
-                const uint32_t bBase = smemBase + s * TSTAGE_BYTES + TA_BYTES;
+                const uint32_t sBase = smemBase + s * TSTAGE_BYTES;
                 if (!(dbg & 4))
 #pragma unroll
                 for (int cq = 0; cq < TCQ; ++cq) {
-                    const int ch = (cq * TPROD_WARPS + warp) * 4 + chl;
-                    const uint32_t dst = bBase + (j >> 2) * TB_HALF + ch * 16 + (j & 3) * 4;
+                    const uint32_t dst = sBase + dstOff[cq];
 #pragma unroll
                     for (int b = 0; b < TKB; ++b) {
-                        const float x = v[cq][b] * inv[b];
+                        // inv = 0 must give 0 whatever was loaded (0 * Inf would poison the whole tile)
+                        const float x = inv[b] != 0.f ? v[cq][b] * inv[b] : 0.f;
                         const float hi = t_tf32_rn(x);
                         t_sts32(dst + b * TB_BLK, hi);
                         t_sts32(dst + b * TB_BLK + TB_BYTES, x - hi);
