@@ -37,7 +37,8 @@ constexpr int TM = 128;                         // 2 pixel rows x 64 columns = U
 constexpr int TKB = 4;                          // blocks per chunk
 constexpr int TSTAGES = 3;
 constexpr int TA_HALF = TM * 16;                // bytes of one K half (4 tf32 per row) of an A block
-constexpr int TB_HALF = TN * 16;                // ... of a B block
+constexpr int TB_HALF = TN * 16 + 64;           // ... of a B block, plus 64 bytes: the lanes of bin columns 4-7 store into the
+                                                // second half and must not land on the banks of columns 0-3 (LBO is free)
 constexpr int TA_BLK = 2 * TA_HALF;             // 4 KB
 constexpr int TB_BLK = 2 * TB_HALF;             // 6 KB per piece
 constexpr int TA_BYTES = TKB * TA_BLK;          // 16 KB
@@ -48,7 +49,7 @@ constexpr int TA_WARP0 = TPROD_WARPS;           // warps 16-19 (TMEM lane quarte
 constexpr int TMMA_WARP = TA_WARP0 + 4;
 constexpr int TTHREADS = (TMMA_WARP + 1) * 32;  // 672
 constexpr int TMAXR = 320;
-constexpr int THDR = 576;                        // list entries with a precomputed header (offset + 8 reciprocals)
+constexpr int THDR = 480;                        // list entries with a precomputed header (offset + 8 reciprocals)
 constexpr int TQUADS = TN / 4;                  // 48 channel quads per item
 constexpr int TCQ = TQUADS / TPROD_WARPS;       // 3 quads per producer warp and chunk
 // kind::tf32: FP32 accumulate, TF32 x TF32, both K-major
