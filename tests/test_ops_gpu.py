@@ -237,6 +237,24 @@ def test_roipool_backward_variants_stay_inside_their_buffers(cuda, monkeypatch, 
     close(gin.view(C, H, W), want, np.float32)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_pooling_with_no_rois(cuda, dtype):
+    """R = 0: the forward returns an empty tensor and the backward a zero gradient of the map's shape (the reference
+    allocates zeros and launches nothing: roipool_cuda.cu:141/172, ps_roipool_cuda.cu:155/188)."""
+    C, H, W, k, nT = 10, 12, 13, 7, 2
+    rois = torch.zeros(0, 4, dtype=dtype, device=cuda)
+    fm = torch.randn(C, H, W, dtype=dtype, device=cuda)
+    out = rp_mod.roipool_forward(fm, rois, k)
+    assert tuple(out.shape) == (0, C, k, k)
+    gin = rp_mod.roipool_backward(torch.zeros(0, C, k, k, dtype=dtype, device=cuda), rois, H, W)
+    assert tuple(gin.shape) == (C, H, W) and not bool(gin.any())
+    sfm = torch.randn(nT * k * k, H, W, dtype=dtype, device=cuda)
+    pout = ps_mod.ps_roipool_forward(sfm, rois, nT, k)
+    assert tuple(pout.shape) == (0, nT, k, k)
+    pgin = ps_mod.ps_roipool_backward(torch.zeros(0, nT, k, k, dtype=dtype, device=cuda), rois, H, W)
+    assert tuple(pgin.shape) == (nT * k * k, H, W) and not bool(pgin.any())
+
+
 def test_corr_bwd_dispatch_env(cuda, monkeypatch):
     """D2T_CORR_BWD selects the kernel family behind d2t_corr_bwd_f32; both agree within the FP32 tolerance."""
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 72, 38, 63, 8, seed=15, dtype=np.float32))
