@@ -255,6 +255,21 @@ def test_pooling_with_no_rois(cuda, dtype):
     assert tuple(pgin.shape) == (nT * k * k, H, W) and not bool(pgin.any())
 
 
+def test_pooling_on_maps_larger_than_the_packed_edge_range(cuda):
+    """H or W above 255: the float32 fast paths pack bin edges into bytes and must hand such maps to the generic kernels."""
+    C, H, W, k, nT = 3, 20, 300, 7, 1
+    rois = _roipool_rois(H, W, np.float32, R=30)
+    fm, go = cases.pool_inputs(C, H, W, (rois.shape[0], C, k, k), 41, np.float32)
+    want = oracle.roipool_fwd(fm, rois, k)
+    out = rp_mod.roipool_forward(dev(fm, cuda), dev(rois, cuda), k)
+    close(out, want, np.float32, scale=float(np.nanmax(np.abs(want))), equal_nan=True)
+    close(rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W), oracle.roipool_bwd(go, rois, H, W), np.float32)
+    sfm, sgo = cases.pool_inputs(nT * k * k, W, H, (rois.shape[0], nT, k, k), 42, np.float32)   # 300 rows x 20 columns
+    np.testing.assert_array_equal(ps_mod.ps_roipool_forward(dev(sfm, cuda), dev(rois, cuda), nT, k).cpu().numpy(),
+                                  oracle.psroipool_fwd(sfm, rois, nT, k))
+    close(ps_mod.ps_roipool_backward(dev(sgo, cuda), dev(rois, cuda), W, H), oracle.psroipool_bwd(sgo, rois, W, H), np.float32)
+
+
 def test_corr_bwd_dispatch_env(cuda, monkeypatch):
     """D2T_CORR_BWD selects the kernel family behind d2t_corr_bwd_f32; both agree within the FP32 tolerance."""
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 72, 38, 63, 8, seed=15, dtype=np.float32))
