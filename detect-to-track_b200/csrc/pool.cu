@@ -455,6 +455,9 @@ int roipool_vec2_bwd_launch(const float*, const float*, float*, int, int, int, i
 // float32 tensor-core backward experiment (pool_tc.cu)
 bool roipool_tc_bwd_supported(int R, int C, int H, int W, int k);
 int roipool_tc_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+// float32 8-channel slabs at two CTAs per SM, two pixel rows per warp (pool_vec3.cu; opt-in)
+bool roipool_vec3_bwd_supported(int R, int C, int H, int W, int k);
+int roipool_vec3_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // float32 row-owner backward (pool_rows.cu)
 bool roipool_rows_bwd_supported(int R, int C, int H, int W, int k);
 int roipool_rows_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
@@ -495,6 +498,10 @@ struct FastPath<float> {
         }
         if (roipool_col_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=col)
             *rc = roipool_col_bwd_launch(go, rois, gin, R, C, H, W, st);
+            return true;
+        }
+        if (roipool_vec3_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=v3)
+            *rc = roipool_vec3_bwd_launch(go, rois, gin, R, C, H, W, st);
             return true;
         }
         if (roipool_vec2_bwd_supported(R, C, H, W, k)) {  // default for r_hw = 7 (D2T_ROIPOOL_BWD=vec: previous kernel)

@@ -204,7 +204,7 @@ def test_tensor_core_kernels_stay_inside_their_buffers(cuda, B, C, H, W):
     assert not bool((o == sentinel).any())  # every output element is written (no memset needed)
 
 
-@pytest.mark.parametrize("variant", ["", "vec", "col", "tc"])
+@pytest.mark.parametrize("variant", ["", "vec", "col", "tc", "v3"])
 @pytest.mark.parametrize("C,H,W,R", [(29, 38, 63, 97), (200, 17, 64, 300), (3, 38, 20, 5)])
 def test_roipool_backward_variants_stay_inside_their_buffers(cuda, monkeypatch, variant, C, H, W, R):
     """every float32 ROIPool backward kernel with its output embedded in a sentinel-filled buffer and grad_out at the very
@@ -364,7 +364,7 @@ def test_roipool_vec_kernels_shapes(cuda, C, H, W, R):
     assert torch.equal(gin, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
 
 
-@pytest.mark.parametrize("variant", ["", "vec", "col", "tc"])
+@pytest.mark.parametrize("variant", ["", "vec", "col", "tc", "v3"])
 @pytest.mark.parametrize("C,H,W,R", [(29, 38, 63, 300), (5, 38, 64, 1100), (18, 16, 20, 9), (1, 1, 1, 3), (7, 50, 70, 41)])
 def test_roipool_backward_variants(cuda, monkeypatch, variant, C, H, W, R):
     """float32, r_hw = 7 backward kernels: the default (pool_vec2.cu: raw cp.async staging, per-row RoI lists, update

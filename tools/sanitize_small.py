@@ -38,7 +38,7 @@ for (C, H, W, k, dt) in [(37, 38, 63, 7, np.float32), (5, 11, 10, 6, np.float64)
         os.environ["D2T_ROIPOOL_ROWS"] = "1"
         rp.roipool_backward(torch.from_numpy(go).to(dev), r, H, W)
         os.environ.pop("D2T_ROIPOOL_ROWS")
-        for variant in ("vec", "col", "tc"):  # previous generation, column-owner and tensor-core experiments
+        for variant in ("vec", "v3", "col", "tc"):  # previous generation, column-owner and tensor-core experiments
             os.environ["D2T_ROIPOOL_BWD"] = variant
             rp.roipool_backward(torch.from_numpy(go).to(dev), r, H, W)
         os.environ.pop("D2T_ROIPOOL_BWD")
