@@ -3,6 +3,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -28,21 +30,44 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 int device_info(DeviceInfo* out) {
     static DeviceInfo cache[64];
-    static bool have[64];
+    static std::atomic<int> have[64];  // 0 = unknown, 1 = cache[dev] published (release / acquire)
     int dev = 0;
     D2T_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) {
         set_error("device index %d out of range", dev);
         return D2T_ERR_BAD_ARG;
     }
-    if (!have[dev]) {
-        DeviceInfo di;
-        D2T_CUDA_TRY(cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev));
-        D2T_CUDA_TRY(cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        cache[dev] = di;  // benign race: every thread writes the same values
-        have[dev] = true;
+    if (have[dev].load(std::memory_order_acquire) == 0) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        if (have[dev].load(std::memory_order_relaxed) == 0) {
+            DeviceInfo di;
+            D2T_CUDA_TRY(cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev));
+            D2T_CUDA_TRY(cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            cache[dev] = di;
+            have[dev].store(1, std::memory_order_release);
+        }
     }
     *out = cache[dev];
+    return 0;
+}
+
+int ensure_dyn_smem(const void* func, size_t bytes) {
+    struct Key {
+        int dev;
+        const void* fn;
+        bool operator<(const Key& o) const { return dev != o.dev ? dev < o.dev : fn < o.fn; }
+    };
+    static std::mutex mu;
+    static std::map<Key, size_t> set;
+    int dev = 0;
+    D2T_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = set[Key{dev, func}];
+    if (bytes > have) {
+        D2T_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
     return 0;
 }
 
@@ -68,8 +93,6 @@ size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd);
 int psb_fwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 int psb_bwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 
-bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
-int corr_umma_fwd_launch(const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 bool corr_umma_bwd_supported(int B, int C, int H, int W, int d, int stride);
 size_t corr_umma_bwd_ws_bytes(int B, int C, int H, int W);
 int corr_umma_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, void*, size_t,
@@ -82,6 +105,8 @@ size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d);
 int corr_tile_fwd_launch(const float*, const float*, float*, int, int, int, int, int, void*, size_t, cudaStream_t);
 int corr_tile_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int, void*,
                          size_t, cudaStream_t);
+int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
+                              cudaStream_t);
 
 static int check_corr(const void* a, const void* b, const void* c, int B, int C, int H, int W, int d, int stride,
                       const char* who) {
@@ -151,13 +176,18 @@ int d2t_corr_bwd_f64(const double* grad_out, const double* fm0, const double* fm
                                            (cudaStream_t)stream);
 }
 
-// tensor-core (tcgen05, 3xTF32) forward, d_max = 8, stride 1 only; experimental, looser tolerance
-int d2t_corr_fwd_f32_tc(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
-                        void* ws, size_t ws_bytes, void* stream) {
-    int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, "d2t_corr_fwd_f32_tc");
+// FP32-pipe backward chosen explicitly (what d2t_corr_bwd_f32 runs for d_max = 4 or C < 128); no workspace
+int d2t_corr_bwd_f32_simt(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0, float* grad_fm1, int B,
+                          int C, int H, int W, int d_max, int stride, void* ws, size_t ws_bytes, void* stream) {
+    (void)ws;
+    (void)ws_bytes;
+    int rc = check_corr(grad_out, fm0, fm1, B, C, H, W, d_max, stride, "d2t_corr_bwd_f32_simt");
     if (rc) return rc;
-    D2T_REQUIRE(corr_umma_supported(B, C, H, W, d_max, stride), "d2t_corr_fwd_f32_tc: needs d_max = 8, stride = 1");
-    return corr_umma_fwd_launch(fm0, fm1, out, B, C, H, W, ws, ws_bytes, (cudaStream_t)stream);
+    D2T_REQUIRE((long long)B * C * H * W == 0 || (grad_fm0 && grad_fm1), "d2t_corr_bwd_f32_simt: null output pointer");
+    if (corr_tile_bwd_supported(B, C, H, W, d_max, stride))
+        return corr_tile_bwd_simt_launch(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, (cudaStream_t)stream);
+    return corr_bwd_generic_launch<float>(grad_out, fm0, fm1, grad_fm0, grad_fm1, B, C, H, W, d_max, stride,
+                                          (cudaStream_t)stream);
 }
 
 // tensor-core (tcgen05, 3xTF32) backward, d_max = 8, stride 1 only; looser tolerance (see d2t_b200.h)

@@ -34,6 +34,15 @@ struct DeviceInfo {
 };
 int device_info(DeviceInfo* out);
 
+// opt a kernel into `bytes` of dynamic shared memory; the attribute is set once per (device, kernel) and raised only
+// when a later launch needs more (cudaFuncSetAttribute is not free: it takes the context lock on every call)
+int ensure_dyn_smem(const void* func, size_t bytes);
+#define D2T_SMEM_OPTIN(func, bytes)                                                   \
+    do {                                                                              \
+        int _rc = ::d2t::ensure_dyn_smem(reinterpret_cast<const void*>(func), bytes); \
+        if (_rc) return _rc;                                                          \
+    } while (0)
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

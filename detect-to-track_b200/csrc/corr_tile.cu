@@ -52,8 +52,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-constexpr bool kCorrFwdDefaultUmma = false;  // default forward family when D2T_CORR_FWD is unset
-constexpr int kCorrBwdUmmaMinItems = 80;  // tensor-core backward by default from this many work items
+constexpr int kCorrBwdUmmaMinC = 128;  // tensor-core backward from this many channels (see use_umma_bwd)
 // packed FP32x2 FMA (Blackwell FFMA2): two independent fused multiply-adds per issue slot, same rounding as fmaf.
 typedef unsigned long long f32x2_t;
 __device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
@@ -537,12 +536,8 @@ static size_t fwd_ws_bytes(int B, int C, int H, int W) {
     return (size_t)(di.sm_count + p.T) * FwdCfg<D>::TILE_FLOATS * sizeof(float);  // enough for any stream-K split
 }
 
-bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
-size_t corr_umma_fwd_ws_bytes(int B, int C, int H, int W);
 size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d) {
-    const size_t simt = d == 8 ? fwd_ws_bytes<8>(B, C, H, W) : fwd_ws_bytes<4>(B, C, H, W);
-    const size_t umma = (d == 8 && corr_umma_supported(B, C, H, W, d, 1)) ? corr_umma_fwd_ws_bytes(B, C, H, W) : 0;
-    return simt > umma ? simt : umma;  // either forward family may be selected at call time
+    return d == 8 ? fwd_ws_bytes<8>(B, C, H, W) : fwd_ws_bytes<4>(B, C, H, W);
 }
 bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride) {
     return corr_tile_supported(B, C, H, W, d, stride);
@@ -554,18 +549,13 @@ size_t corr_umma_bwd_ws_bytes(int B, int C, int H, int W);
 int corr_umma_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, void*, size_t,
                          cudaStream_t);
 
-// D2T_CORR_BWD = umma | simt selects the backward kernel family (read per call, so a test can flip it); see DESIGN.md
-// for the measurements behind the default.
+// Which kernel family d2t_corr_bwd_f32 runs.  The rule depends on (C, d_max, stride) ONLY -- never on B, H or W -- so
+// that gradients are batch-invariant: the tensor-core kernel (3xTF32) for d_max = 8, stride = 1 and at least
+// kCorrBwdUmmaMinC channels, the FP32-pipe kernel otherwise.  d2t_corr_bwd_f32_simt / d2t_corr_bwd_f32_tc select a
+// family explicitly.  Measured on B200 (38x63, d=8; profiles/r1_time_ops_v4.txt): B=8 c3/c4/c5 253/386/620 us against
+// 437/861/1729 us for the FP32-pipe kernel; B=1: c4 112 vs 142, c5 185 vs 236, c3 112 vs 95.
 static bool use_umma_bwd(int B, int C, int H, int W, int d) {
-    if (!corr_umma_bwd_supported(B, C, H, W, d, 1)) return false;
-    const char* e = getenv("D2T_CORR_BWD");
-    if (e && strcmp(e, "umma") == 0) return true;
-    if (e && strcmp(e, "simt") == 0) return false;
-    // default: the tensor-core kernel once there are enough (tile, 256-channel block) work items to fill the SMs.
-    // Measured on B200 (38x63, d=8; profiles/r1_time_ops_v4.txt): B=8 c3/c4/c5 253/386/620 us against 437/861/1729 us for
-    // the FP32-pipe kernel; B=1: c4 112 vs 142, c5 185 vs 236, but c3 (40 items) 112 vs 95.
-    const long long items = (long long)B * ceil_div(C, 256) * ceil_div(H, 8) * ceil_div(W, 16);
-    return items >= kCorrBwdUmmaMinItems;
+    return corr_umma_bwd_supported(B, C, H, W, d, 1) && C >= kCorrBwdUmmaMinC;
 }
 size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d) {
     return use_umma_bwd(B, C, H, W, d) ? corr_umma_bwd_ws_bytes(B, C, H, W) : 0;
@@ -579,17 +569,12 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     CorrPlan p;
     int rc = make_plan<D>(B, C, H, W, CK, &p);
     if (rc) return rc;
-    {   // Whole-tile rounds (all CTAs in step, halos shared through L2) were measured SLOWER than one contiguous
-        // (tile, chunk) range per CTA at B = 8 (c5: 587 vs ~510 us): with every CTA on the same channel planes at the
-        // same time the memory system is hit in bursts.  So the default is the staggered stream-K walk; D2T_CORR_SCHED=2
-        // selects the rounds for experiments.
-        const char* e = getenv("D2T_CORR_SCHED");
-        if (!(e && e[0] == '2')) {
-            p.rounds = 0;
-            p.left = p.T;
-            p.ipcL = p.ipc;
-        }
-    }
+    // Whole-tile rounds (all CTAs in step, halos shared through L2) were measured SLOWER than one contiguous
+    // (tile, chunk) range per CTA at B = 8 (c5: 587 vs ~510 us): with every CTA on the same channel planes at the
+    // same time the memory system is hit in bursts.  So the schedule is the staggered stream-K walk.
+    p.rounds = 0;
+    p.left = p.T;
+    p.ipcL = p.ipc;
     const size_t need = (size_t)(p.G + p.T) * Cfg::TILE_FLOATS * sizeof(float);
     if (ws == nullptr || ws_bytes < need) {
         set_error("corr_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -599,7 +584,7 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     const size_t tileBytes = (size_t)Cfg::TILE_FLOATS * sizeof(float);
     const size_t smem = opBytes > tileBytes ? opBytes : tileBytes;
     auto kern = corr_fwd_tile_kernel<D, CK>;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(kern, smem);
     kern<<<p.G, kCorrThreads, smem, st>>>(fm0, fm1, out, static_cast<float*>(ws), p);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
@@ -612,27 +597,14 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     return D2T_OK;
 }
 
-// tensor-core forward (corr_umma.cu)
-bool corr_umma_supported(int B, int C, int H, int W, int d, int stride);
-int corr_umma_fwd_launch(const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
-
-// D2T_CORR_FWD = umma | simt selects the forward kernel family (read per call, so a test can flip it); see DESIGN.md
-// for the measurements behind the default.
-static bool use_umma_fwd(int B, int C, int H, int W, int d) {
-    if (d != 8 || !corr_umma_supported(B, C, H, W, d, 1)) return false;
-    const char* e = getenv("D2T_CORR_FWD");
-    if (e && strcmp(e, "umma") == 0) return true;
-    if (e && strcmp(e, "simt") == 0) return false;
-    return kCorrFwdDefaultUmma;
-}
-
 int corr_tile_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
-    if (use_umma_fwd(B, C, H, W, d))
-        return corr_umma_fwd_launch(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);
     return d == 8 ? fwd_launch<8>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st)
                   : fwd_launch<4>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);
 }
+
+int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
+                              cudaStream_t);
 
 template <int D>
 static int bwd_launch(const float* go, const float* fm0, const float* fm1, float* g0, float* g1, int B, int C, int H,
@@ -642,18 +614,12 @@ static int bwd_launch(const float* go, const float* fm0, const float* fm1, float
     CorrPlan p;
     int rc = make_plan<D>(B, C, H, W, CK, &p);
     if (rc) return rc;
-    {   // channel-group size for the L2-friendly walk: ~256 channels, must divide NI; D2T_BWD_GC overrides (chunks)
-        int gc = p.NI;  // measured: grouping (L2-friendlier) is SLOWER (segment restarts), so one group by default
-        if (const char* e = getenv("D2T_BWD_GC")) gc = atoi(e);
-        if (gc <= 0 || gc > p.NI) gc = p.NI;
-        while (p.NI % gc != 0) --gc;
-        p.dbg = gc;
-    }
+    p.dbg = p.NI;  // one channel group: grouping the walk for L2 reuse was measured slower (segment restarts)
     const size_t smem = ((size_t)kStages * CK * Cfg::KPATCH + (size_t)2 * kCorrThreads * (CK * 8 + 4)) * sizeof(float);
     auto k0 = corr_bwd_tile_kernel<D, CK, 0>;
     auto k1 = corr_bwd_tile_kernel<D, CK, 1>;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    D2T_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(k0, smem);
+    D2T_SMEM_OPTIN(k1, smem);
     k0<<<p.G, kCorrThreads, smem, st>>>(go, fm1, g0, p);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
@@ -665,8 +631,18 @@ static int bwd_launch(const float* go, const float* fm0, const float* fm1, float
 
 int corr_tile_bwd_launch(const float* go, const float* fm0, const float* fm1, float* g0, float* g1, int B, int C,
                          int H, int W, int d, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (use_umma_bwd(B, C, H, W, d) && ws != nullptr && ws_bytes >= corr_umma_bwd_ws_bytes(B, C, H, W))
+    if (use_umma_bwd(B, C, H, W, d)) {
+        if (ws == nullptr || ws_bytes < corr_umma_bwd_ws_bytes(B, C, H, W)) {
+            set_error("corr_bwd: workspace too small (%zu < %zu)", ws_bytes, corr_umma_bwd_ws_bytes(B, C, H, W));
+            return D2T_ERR_WORKSPACE;  // never a silent change of kernel family (and of numerics)
+        }
         return corr_umma_bwd_launch(go, fm0, fm1, g0, g1, B, C, H, W, ws, ws_bytes, st);
+    }
+    return corr_tile_bwd_simt_launch(go, fm0, fm1, g0, g1, B, C, H, W, d, st);
+}
+
+int corr_tile_bwd_simt_launch(const float* go, const float* fm0, const float* fm1, float* g0, float* g1, int B, int C,
+                              int H, int W, int d, cudaStream_t st) {
     return d == 8 ? bwd_launch<8>(go, fm0, fm1, g0, g1, B, C, H, W, st)
                   : bwd_launch<4>(go, fm0, fm1, g0, g1, B, C, H, W, st);
 }

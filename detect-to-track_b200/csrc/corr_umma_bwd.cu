@@ -63,7 +63,6 @@ constexpr int XFLIP_PITCH = 290;          // shared-memory pitch of one gradOut 
 struct XPlan {
     int B, C, H, W;
     int tilesX, tilesY, nCb, nItems;
-    int dbg;  // experiment switches (D2T_UMMA_DBG; results are wrong when set): 1 = no staging stores, 2 = no MMAs, 4 = no loads
 };
 
 __device__ __forceinline__ uint32_t x_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -272,7 +271,6 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
                     const uint32_t dcol = tmem_base + ab * XN;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        if (p.dbg & 2) break;
                         const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte row
                         x_mma(dcol, x_desc(aHi + ko), x_desc(bHi + ko), (first && ks == 0) ? 0u : 1u);
                         x_mma(dcol, x_desc(aHi + ko), x_desc(bLo + ko), 1u);
@@ -305,11 +303,6 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
         // byte addresses, advanced one plane per channel (kept as integers so that the compiler does not fall back to
         // element-index arithmetic: 2 instructions per load instead of 4)
         uint64_t ba = (uint64_t)(xsrc + ((size_t)c.b * C + c0) * plane + (size_t)gi * W + gj);
-        if (p.dbg & 4) {
-#pragma unroll
-            for (int j = 0; j < XNB + XNA; ++j) v[j] = 0.f;
-            return;
-        }
         if (bok && nch >= XNB) {
 #pragma unroll
             for (int j = 0; j < XNB; ++j) {
@@ -364,7 +357,7 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
         {
             const int si = st.r - warp;  // same (warp-uniform) liveness test as in load()
             const bool aDead = !(si >= 0 && si < XTD && st.i0 + warp < H);
-            if (!(p.dbg & 1)) store(v, S, aDead);
+            store(v, S, aDead);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         __syncwarp();
@@ -469,15 +462,13 @@ int corr_umma_bwd_launch(const float* go, const float* fm0, const float* fm1, fl
     p.tilesY = ceil_div(H, XQROWS);
     p.nCb = ceil_div(C, XN);
     p.nItems = B * p.nCb * p.tilesX * p.tilesY;
-    p.dbg = 0;
-    if (const char* e = getenv("D2T_UMMA_DBG")) p.dbg = atoi(e);
     const int grid = p.nItems < di.sm_count ? p.nItems : di.sm_count;
     const size_t smem = (size_t)XSTAGES * XSTAGE_BYTES + 1024;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(corr_bwd_umma_kernel<0>, smem);
+    D2T_SMEM_OPTIN(corr_bwd_umma_kernel<1>, smem);
 
     const size_t fsmem = (size_t)W * XFLIP_PITCH * sizeof(float);
-    D2T_CUDA_TRY(cudaFuncSetAttribute(corr_bwd_flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    D2T_SMEM_OPTIN(corr_bwd_flip_kernel, fsmem);
     corr_bwd_flip_kernel<<<B * (H + 2 * (XD - 1) + 1), XFLIP_THREADS, fsmem, st>>>(go, gt, B, H, W);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();

@@ -436,31 +436,16 @@ __global__ void pool_bins_kernel(const T* __restrict__ rois, int32_t* __restrict
 // =================================================================================
 // host launchers
 // =================================================================================
-// float32 fast path (pool_fast.cu)
+// float32 fast paths for r_hw <= 15 (pool_fast.cu)
 bool roipool_fast_supported(int R, int C, int H, int W, int k);
-int roipool_fast_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int roipool_fast_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 bool roipool_prefix_supported(int R, int C, int H, int W, int k);
 int roipool_prefix_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
-// float32 [pixel][16 channel] kernels (pool_vec.cu)
+// float32, r_hw = 7: [pixel][16 channel] slabs -- forward pool_vec.cu, backward pool_vec2.cu
 bool roipool_vec_supported(int R, int C, int H, int W, int k);
 int roipool_vec_fwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
-int roipool_vec_bwd_launch(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
-// float32 column-owner backward with register accumulators (pool_col.cu)
-bool roipool_col_bwd_supported(int R, int C, int H, int W, int k);
-int roipool_col_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
-// float32 [pixel][16 channel] backward, second cut: raw cp.async staging, per-row RoI lists (pool_vec2.cu)
 bool roipool_vec2_bwd_supported(int R, int C, int H, int W, int k);
 int roipool_vec2_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
-// float32 tensor-core backward experiment (pool_tc.cu)
-bool roipool_tc_bwd_supported(int R, int C, int H, int W, int k);
-int roipool_tc_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
-// float32 8-channel slabs at two CTAs per SM, two pixel rows per warp (pool_vec3.cu; opt-in)
-bool roipool_vec3_bwd_supported(int R, int C, int H, int W, int k);
-int roipool_vec3_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
-// float32 row-owner backward (pool_rows.cu)
-bool roipool_rows_bwd_supported(int R, int C, int H, int W, int k);
-int roipool_rows_bwd_launch(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 template <typename T>
 struct FastPath {
     static bool fwd(const T*, const T*, T*, int, int, int, int, int, cudaStream_t, int*) { return false; }
@@ -468,16 +453,10 @@ struct FastPath {
 };
 template <>
 struct FastPath<float> {
+    // forward: row-prefix kernels (rounding-level differences from the reference's summation order);
+    // d2t_roipool_fwd_f32_exact bypasses them and keeps the bit-identical slab kernel below
     static bool fwd(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int k, cudaStream_t st,
                     int* rc) {
-        // default: row-prefix kernel (rounding-level differences from the reference's summation order);
-        // D2T_ROIPOOL_EXACT=1 keeps the bit-identical slab kernel below
-        static int exact = -1;
-        if (exact < 0) {
-            const char* e = getenv("D2T_ROIPOOL_EXACT");
-            exact = (e && e[0] == '1') ? 1 : 0;
-        }
-        if (exact) return false;
         if (roipool_vec_supported(R, C, H, W, k)) {
             *rc = roipool_vec_fwd_launch(fm, rois, out, R, C, H, W, k, st);
             return true;
@@ -488,28 +467,8 @@ struct FastPath<float> {
     }
     static bool bwd(const float* go, const float* rois, float* gin, int R, int C, int H, int W, int k, cudaStream_t st,
                     int* rc) {
-        if (roipool_rows_bwd_supported(R, C, H, W, k)) {
-            *rc = roipool_rows_bwd_launch(go, rois, gin, R, C, H, W, st);
-            return true;
-        }
-        if (roipool_tc_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=tc)
-            *rc = roipool_tc_bwd_launch(go, rois, gin, R, C, H, W, st);
-            return true;
-        }
-        if (roipool_col_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=col)
-            *rc = roipool_col_bwd_launch(go, rois, gin, R, C, H, W, st);
-            return true;
-        }
-        if (roipool_vec3_bwd_supported(R, C, H, W, k)) {  // opt-in experiment (D2T_ROIPOOL_BWD=v3)
-            *rc = roipool_vec3_bwd_launch(go, rois, gin, R, C, H, W, st);
-            return true;
-        }
-        if (roipool_vec2_bwd_supported(R, C, H, W, k)) {  // default for r_hw = 7 (D2T_ROIPOOL_BWD=vec: previous kernel)
+        if (roipool_vec2_bwd_supported(R, C, H, W, k)) {
             *rc = roipool_vec2_bwd_launch(go, rois, gin, R, C, H, W, st);
-            return true;
-        }
-        if (roipool_vec_supported(R, C, H, W, k)) {
-            *rc = roipool_vec_bwd_launch(go, rois, gin, R, C, H, W, k, st);
             return true;
         }
         if (!roipool_fast_supported(R, C, H, W, k)) return false;
@@ -566,7 +525,7 @@ int roipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int C, int H, 
     SlabPlan p;
     int rc = plan_slab(R, C, H, W, k, sizeof(T), 0, &p);
     if (rc) return rc;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    D2T_SMEM_OPTIN(roipool_fwd_kernel<T>, p.smem);
     roipool_fwd_kernel<T><<<p.grid, kSlabThreads, p.smem, st>>>(fm, rois, out, R, C, H, W, k, p.CB, p.RCH,
                                                                  make_fastdiv(p.CB * k), make_fastdiv(k));
     D2T_CUDA_TRY(cudaGetLastError());
@@ -589,7 +548,7 @@ int roipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int C, int H, 
     SlabPlan p;
     int rc = plan_slab(R, C, H, W, k, sizeof(T), (size_t)k * k * sizeof(T), &p);
     if (rc) return rc;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    D2T_SMEM_OPTIN(roipool_bwd_kernel<T>, p.smem);
     roipool_bwd_kernel<T><<<p.grid, kSlabThreads, p.smem, st>>>(go, rois, gin, R, C, H, W, k, p.CB, p.RCH,
                                                                  make_fastdiv(W));
     D2T_CUDA_TRY(cudaGetLastError());

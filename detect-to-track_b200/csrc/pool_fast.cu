@@ -223,116 +223,8 @@ roipool_fast_bwd_kernel(const float* __restrict__ go, const float* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------------------------------
-// forward
+// forward (row prefix sums, any r_hw <= 32)
 // ----------------------------------------------------------------------------------------------------
-// smem: plane[HW][16] | per-warp output staging [nWarps][16][kk] | edges (group) | tmp for the load transposition
-struct FastFwdLayout {
-    size_t planeOff, stageOff, edgeOff, total;
-    int RG, tmpChunk;
-};
-__host__ __device__ inline FastFwdLayout fast_fwd_layout(int H, int W, int k, int nWarps, int RG) {
-    FastFwdLayout L;
-    L.RG = RG;
-    const int kk = k * k;
-    size_t off = 0;
-    L.planeOff = off; off += (size_t)H * W * kFastCB * sizeof(float);
-    L.stageOff = off; off += (size_t)nWarps * kFastCB * kk * sizeof(float);
-    L.edgeOff = off;  off += ((size_t)RG * k * 4 * sizeof(short) + 15) / 16 * 16;
-    L.total = off;
-    const size_t sBytes = (size_t)nWarps * kFastCB * kk * sizeof(float);
-    int chunk = (int)(sBytes / sizeof(float) / kFastCB) - 1;
-    L.tmpChunk = chunk < 32 ? 0 : (chunk / 32) * 32;
-    return L;
-}
-
-template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 1)
-roipool_fast_fwd_kernel(const float* __restrict__ fm, const float* __restrict__ rois, float* __restrict__ out, int R,
-                        int C, int H, int W, int k, int RG) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const FastFwdLayout L = fast_fwd_layout(H, W, k, NWARPS, RG);
-    float* plane = reinterpret_cast<float*>(smem_raw + L.planeOff);
-    float* stageAll = reinterpret_cast<float*>(smem_raw + L.stageOff);
-    short* edgeS = reinterpret_cast<short*>(smem_raw + L.edgeOff);
-
-    const int kk = k * k;
-    const int HW = H * W;
-    const int c0 = blockIdx.x * kFastCB;
-    const int cb = min(kFastCB, C - c0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = lane >> 4, c = lane & 15;
-    constexpr int NT = NWARPS * 32;
-
-    // ---- slab load: fm[c0+cc][px] -> plane[px][cc], transposed through the staging area -----------------
-    {
-        float* tmp = stageAll;
-        const int CH = L.tmpChunk, TP = CH + 1;
-        for (int p0 = 0; p0 < HW; p0 += CH) {
-            const int n = min(CH, HW - p0);
-            for (int e = tid; e < kFastCB * n; e += NT) {
-                const int cc = e / n, px = e - cc * n;
-                tmp[cc * TP + px] = cc < cb ? __ldg(fm + (size_t)(c0 + cc) * HW + p0 + px) : 0.f;
-            }
-            __syncthreads();
-            for (int e = tid; e < n * kFastCB; e += NT) {
-                const int px = e >> 4, cc = e & 15;
-                plane[(size_t)(p0 + px) * kFastCB + cc] = tmp[cc * TP + px];
-            }
-            __syncthreads();
-        }
-    }
-
-    float* stage = stageAll + warp * kFastCB * kk;  // this warp's [16][kk] output block
-    for (int r0 = 0; r0 < R; r0 += RG) {
-        const int nr = min(RG, R - r0);
-        __syncthreads();
-        fast_tables(rois, r0, nr, k, H, W, edgeS, nullptr, nullptr, false);
-        __syncthreads();
-        for (int rr = warp; rr < nr; rr += NWARPS) {  // a warp owns whole RoIs
-            const short* ed = edgeS + rr * k * 4;
-            // bins are processed two at a time: half-warp 0 takes bin 2s, half-warp 1 bin 2s+1
-            for (int s = 0; s < (kk + 1) / 2; ++s) {
-                const int b = 2 * s + half;
-                if (b < kk) {
-                    const int i = b / k, j = b - i * k;
-                    const int i0 = ed[i * 4 + 0], i1 = ed[i * 4 + 1];
-                    const int j0 = ed[j * 4 + 2], j1 = ed[j * 4 + 3];
-                    float a = 0.f;
-                    for (int pi = i0; pi < i1; ++pi) {
-                        const float* row = plane + ((size_t)pi * W + j0) * kFastCB + c;
-                        // 8 independent (predicated) loads in flight, then the adds in the reference's order
-                        for (int w0 = 0; w0 < j1 - j0; w0 += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) v[u] = (w0 + u < j1 - j0) ? row[(w0 + u) * kFastCB] : 0.f;
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (w0 + u < j1 - j0) a += v[u];
-                        }
-                    }
-                    const int numel = (i1 - i0) * (j1 - j0);
-                    a /= numel;  // 0/0 = NaN on empty bins, like roipool_cuda.cu:61
-                    stage[c * kk + b] = a;
-                }
-            }
-            __syncwarp();
-            // out[r][c0 .. c0+cb)[kk] is one contiguous run
-            float* dst = out + ((size_t)(r0 + rr) * C + c0) * kk;
-            for (int e = lane; e < cb * kk; e += 32) dst[e] = stage[e];
-            __syncwarp();
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------
-// forward, row-prefix variant (default for float32)
-// ----------------------------------------------------------------------------------------------------
-// The exact-order kernels (pool.cu roipool_fwd_kernel, roipool_fast_fwd_kernel above) pay one LDS + one FADD per
-// bin pixel, ~200 issued instructions per output: they are instruction-bound at 11x the HBM roof.  Here the CTA turns
-// every row of its channel slab into an exclusive prefix sum once (P[y][x] = sum of the row left of x), after which a
-// bin is  sum over its rows of (P[y][J1] - P[y][J0]) : two loads per bin ROW instead of one per bin PIXEL.  The result
-// differs from the reference's left-to-right sum only by float rounding (|err| <~ 1e-6 * row magnitude; tested at
-// rtol 1e-4); D2T_ROIPOOL_EXACT=1 selects the bit-identical kernel instead.
 struct FastDivP {
     uint32_t m, s;
 };
@@ -424,8 +316,6 @@ roipool_prefix_fwd_kernel(const float* __restrict__ fm, const float* __restrict_
 // ----------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------
-constexpr int kFwdWarps = 16;
-
 static bool pick_rg_bwd(int H, int W, int k, size_t budget, int* RG) {
     for (int rg = 8; rg >= 2; rg /= 2) {
         FastLayout L = fast_layout(H, W, k, rg);
@@ -443,9 +333,7 @@ bool roipool_fast_supported(int R, int C, int H, int W, int k) {
     if (device_info(&di)) return false;
     const size_t budget = (size_t)di.max_smem_optin;
     int rg;
-    if (!pick_rg_bwd(H, W, k, budget, &rg)) return false;
-    FastFwdLayout F = fast_fwd_layout(H, W, k, kFwdWarps, 64);
-    return F.total <= budget && F.tmpChunk >= 32;
+    return pick_rg_bwd(H, W, k, budget, &rg);
 }
 
 int roipool_fast_bwd_launch(const float* go, const float* rois, float* gin, int R, int C, int H, int W, int k,
@@ -460,7 +348,7 @@ int roipool_fast_bwd_launch(const float* go, const float* rois, float* gin, int 
     }
     const FastLayout L = fast_layout(H, W, k, RG);
     auto kern = (k == 7) ? roipool_fast_bwd_kernel<7> : roipool_fast_bwd_kernel<0>;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    D2T_SMEM_OPTIN(kern, L.total);
     kern<<<ceil_div(C, kFastCB), kFastThreads, L.total, st>>>(go, rois, gin, R, C, H, W, k, RG);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
@@ -497,22 +385,10 @@ int roipool_prefix_fwd_launch(const float* fm, const float* rois, float* out, in
     if ((size_t)CB * k * k * 4 > 8192) CB = (int)(8192 / ((size_t)k * k * 4));
     if (CB < 1) CB = 1;
     const size_t smem = (size_t)CB * planePitch * sizeof(float) + tabBytes + (size_t)CB * k * k * sizeof(uint32_t);
-    D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_prefix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(roipool_prefix_fwd_kernel, smem);
     roipool_prefix_fwd_kernel<<<ceil_div(C, CB), kFastThreads, smem, st>>>(
         fm, rois, out, R, C, H, W, k, CB, RG, rowPitch, planePitch, make_fastdiv_p(CB * k * k), make_fastdiv_p(k * k),
         make_fastdiv_p(k), make_fastdiv_p(W));
-    D2T_CUDA_TRY(cudaGetLastError());
-    note_launch();
-    return D2T_OK;
-}
-
-int roipool_fast_fwd_launch(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int k,
-                            cudaStream_t st) {
-    const int RG = 64;
-    const FastFwdLayout L = fast_fwd_layout(H, W, k, kFwdWarps, RG);
-    auto kern = roipool_fast_fwd_kernel<kFwdWarps>;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    kern<<<ceil_div(C, kFastCB), kFwdWarps * 32, L.total, st>>>(fm, rois, out, R, C, H, W, k, RG);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;

@@ -322,12 +322,6 @@ bool psb_supported(int N, int R, int nT, int H, int W, int k) {
     if (N <= 0 || R <= 0 || nT <= 0 || k <= 0 || H <= 0 || W <= 0) return false;
     if (H > 255 || W > 255 || R >= 65534 || k * k > kPsbFwdThreads || nT >= 0xFFFF || N > 65535) return false;
     if ((long long)nT * k * k > 0x7fffffffLL / 4) return false;
-    static int off = -1;
-    if (off < 0) {
-        const char* e = getenv("D2T_PSROI_BATCHED");
-        off = (e && e[0] == '0') ? 1 : 0;
-    }
-    if (off) return false;
     DeviceInfo di;
     if (device_info(&di)) return false;
     const size_t fwdSmem = (size_t)H * W * 4 + (size_t)k * k * 4 + 64;
@@ -358,7 +352,7 @@ int psb_fwd_launch(const float* fm, const float* rois, float* out, int N, int R,
     int rc = psb_edges_launch(rois, edges, nullptr, N, R, k, H, W, st);
     if (rc) return rc;
     const size_t smem = (size_t)H * W * 4 + (size_t)k * k * 4 + 64;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(psb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(psb_fwd_kernel, smem);
     psb_fwd_kernel<<<dim3(nT * k * k, N), kPsbFwdThreads, smem, st>>>(fm, edges, out, R, nT, H, W, k,
                                                                      (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0);
     D2T_CUDA_TRY(cudaGetLastError());
@@ -390,7 +384,7 @@ int psb_bwd_launch(const float* go, const float* rois, float* gin, int N, int R,
     psb_rowlists_kernel<<<ceil_div(lists, kPsbThreads / 32), kPsbThreads, 0, st>>>(edgesT, rowlist, rowcnt, N, R, H, k);
     D2T_CUDA_TRY(cudaGetLastError());
     const size_t smem = (size_t)H * ((W + 1) | 1) * 4 + 8 + (size_t)R * 8 + (size_t)kk * 4 + 64;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(psb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(psb_bwd_kernel, smem);
     psb_bwd_kernel<<<dim3(nT * kk, N), kPsbRowThreads, smem, st>>>(vt, rowlist, rowcnt, edgesT, gin, R, nT, H, W, k,
                                                                   canonical ? 1 : 0);
     D2T_CUDA_TRY(cudaGetLastError());

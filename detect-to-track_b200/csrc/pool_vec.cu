@@ -1,5 +1,5 @@
-// pool_vec.cu -- float32 ROIPool forward/backward, third generation: [pixel][16 channel] slabs walked with
-// 128-bit shared-memory accesses, row prefix sums (forward) / row difference arrays (backward).  sm_100a.
+// pool_vec.cu -- float32 ROIPool forward: [pixel][16 channel] slabs walked with 128-bit shared-memory accesses,
+// row prefix sums.  sm_100a.  (The backward built on the same slab layout is pool_vec2.cu.)
 //
 // Why: ROIPool at the D&T track-head size (C=1891, 38x63, R=300, k=7) moves 129 MB per direction, 20 us at the HBM
 // roof.  The earlier kernels (pool.cu, pool_fast.cu) were instruction-bound at 150-370 us because every lane carried
@@ -17,14 +17,6 @@
 //             Results are staged per warp and leave as one contiguous run  out[r, c0:c0+cb, :, :].
 //             Differs from the reference's left-to-right pixel sum (roipool_cuda.cu:52-61) only by float rounding
 //             (tested at rtol 1e-4); d2t_roipool_fwd_f32_exact keeps the bit-identical kernel.
-//   backward  the adjoint: D[y][J0_j] += t, D[y][J1_j] -= t with t = sum_{i covers y} grad_out[r,c,i,j] / numel_ij,
-//             then grad_fm[y][x] = sum_{x' <= x} D[y][x'] (inclusive row prefix in the epilogue).  Every WARP owns
-//             pixel rows (y % nWarps == warp) for all RoIs and walks the RoIs in ascending order, so each row is
-//             updated by exactly one warp, in a fixed order: no atomics (reference: atomicAdd per bin pixel,
-//             roipool_cuda.cu:119-125), bitwise reproducible.  grad_out blocks of RoI groups are prefetched through
-//             registers into a double-buffered shared stage.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace d2t {
@@ -33,8 +25,6 @@ constexpr int kVecFwdWarps = 16;
 constexpr int kVecFwdThreads = kVecFwdWarps * 32;
 constexpr int kVecSlots = 16;     // channel slots per CTA (4 quads of 4)
 constexpr int kVecRChunk = 512;   // RoIs per edge-table chunk
-constexpr int kVecBwdMaxWarps = 20;
-constexpr int kVecBwdRG = 8;      // RoIs per staged grad_out group
 
 // float offset of channel quad q of pixel column x inside a row
 __device__ __forceinline__ int vec_pix_off(int x, int q) { return x * kVecSlots + ((q ^ ((x >> 1) & 3)) << 2); }
@@ -203,258 +193,6 @@ roipool_vec_fwd_kernel(const float* __restrict__ fm, const float* __restrict__ r
 }
 
 // ----------------------------------------------------------------------------------------------------
-// backward
-// ----------------------------------------------------------------------------------------------------
-// smem: D[H][rowPitch] | gstage[2][RG][KK][16] | edges[RCH][K] | simple[RCH] | cover[2][H][RG] | off[2][RG][32] | counter[2]
-//
-// Work unit = (RoI group, pixel row).  Within a group every pixel row is claimed by exactly one warp (dynamic queue),
-// which applies the group's RoIs to that row in ascending RoI order; groups are separated by one CTA barrier.  So each
-// D row sees its updates in a fixed order whichever warp applies them: deterministic without atomics.
-template <int K>
-__global__ void __launch_bounds__(kVecBwdMaxWarps * 32, 1)
-roipool_vec_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, float* __restrict__ gin, int R,
-                       int C, int H, int W, int CB) {
-    constexpr int KK = K * K;
-    constexpr int SP = vec_stage_pitch(KK);
-    constexpr int RG = kVecBwdRG;
-    static_assert(RG == 8, "cover masks of a row are read as one 64-bit word");
-    constexpr int GSZ = RG * kVecSlots * SP;  // floats per stage buffer
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int rowPitch = vec_row_pitch(W);
-    float* D = reinterpret_cast<float*>(smem_raw);
-    float* gS = D + (size_t)H * rowPitch;
-    uint32_t* edgeS = reinterpret_cast<uint32_t*>(gS + 2 * GSZ);                 // [kVecRChunk][K]
-    unsigned char* simpleS = reinterpret_cast<unsigned char*>(edgeS + kVecRChunk * K);  // [kVecRChunk]
-    unsigned char* coverS = simpleS + kVecRChunk;                                // [2][H][RG], 8-byte aligned rows
-    uint32_t* offS = reinterpret_cast<uint32_t*>(coverS + (size_t)2 * ((H * RG + 15) / 16 * 16));  // [2][RG][32]
-    int* counter = reinterpret_cast<int*>(offS + 2 * RG * 32);
-    constexpr int NITEM = 4;  // (RoI, quad, bin) staging items per thread and group: the host guarantees 4 * threads >= RG * 4 * KK
-
-    const int NT = blockDim.x;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int c0 = blockIdx.x * CB;
-    const int cb = min(CB, C - c0);
-    const int HW = H * W;
-    const int coverBuf = (H * RG + 15) / 16 * 16;
-
-    for (int idx = tid; idx < H * rowPitch / 4; idx += NT) st4(D + idx * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-
-    const int j = lane >> 2, q = lane & 3;
-    const bool jact = j < K;
-
-    for (int rc0 = 0; rc0 < R; rc0 += kVecRChunk) {  // RoI chunks: one edge table each (a single chunk for R <= 512)
-        const int nrc = min(kVecRChunk, R - rc0);
-        __syncthreads();
-        for (int idx = tid; idx < nrc * K; idx += NT) {
-            const int rr = idx / K, b = idx - rr * K;
-            edgeS[idx] = vec_pack_edges(rois + (size_t)(rc0 + rr) * 4, b, K, H, W);
-        }
-        __syncthreads();
-        // "simple" RoI: column edges strictly increasing => the lanes of one update instruction touch distinct pixels
-        for (int rr = tid; rr < nrc; rr += NT) {
-            const uint32_t* ed = edgeS + rr * K;
-            bool simple = true;
-#pragma unroll
-            for (int b = 1; b < K; ++b) {
-                const uint32_t a = ed[b - 1], c = ed[b];
-                simple = simple && (((c >> 16) & 255) > ((a >> 16) & 255)) && ((c >> 24) > (a >> 24));
-            }
-            simpleS[rr] = simple ? 1 : 0;
-        }
-
-        // ---- staging of grad_out, pre-scaled and transposed ------------------------------------------------------
-        // An item is (RoI rr of the group, channel quad qq, bin): 4 coalesced loads (lanes = consecutive bins of one
-        // channel), scaled by 1 / (bin rows x bin columns) (0 for an empty bin), one STS.128 into
-        //   gS[buf][rr][bin][slot], slot = qq ^ (j & 3)   (16-byte slots; j = bin column)
-        // so that lane (j, q) of the update loop reads its four channels of bin (i, j) with ONE conflict-free LDS.128
-        // and needs no edge arithmetic or reciprocal per pixel row.
-        int itRR[NITEM], itBin[NITEM], itQ[NITEM];
-#pragma unroll
-        for (int n = 0; n < NITEM; ++n) {
-            const int it = tid + n * NT;
-            itRR[n] = it / (4 * KK);
-            const int rem = it - itRR[n] * (4 * KK);
-            itQ[n] = rem / KK;
-            itBin[n] = rem - itQ[n] * KK;
-            if (itRR[n] >= RG) itRR[n] = -1;
-        }
-        float4 pre[NITEM];
-        auto prefetch = [&](int grp) {
-            const int r0 = rc0 + grp * RG;
-#pragma unroll
-            for (int n = 0; n < NITEM; ++n) {
-                const int rr = itRR[n];
-                const bool ok = rr >= 0 && grp * RG + rr < nrc;
-                const int ch = 4 * itQ[n];
-                const float* src = go + ((size_t)(ok ? r0 + rr : rc0) * C + c0 + ch) * KK + itBin[n];
-                pre[n].x = (ok && ch + 0 < cb) ? __ldg(src) : 0.f;
-                pre[n].y = (ok && ch + 1 < cb) ? __ldg(src + KK) : 0.f;
-                pre[n].z = (ok && ch + 2 < cb) ? __ldg(src + 2 * KK) : 0.f;
-                pre[n].w = (ok && ch + 3 < cb) ? __ldg(src + 3 * KK) : 0.f;
-            }
-        };
-        // stage the prefetched grad_out of group `grp`; build its row cover masks
-        // (cover[y][rr] bit i set <=> bin row i of RoI rr contains pixel row y) and its per-lane update offsets
-        auto commit = [&](int grp, int buf) {
-            float* g = gS + buf * GSZ;
-            const int nr = min(RG, nrc - grp * RG);
-#pragma unroll
-            for (int n = 0; n < NITEM; ++n) {
-                const int rr = itRR[n];
-                if (rr < 0 || rr >= nr) continue;
-                const int bi = itBin[n] / K, bj = itBin[n] - bi * K;
-                const uint32_t* ed = edgeS + (grp * RG + rr) * K;
-                const uint32_t ei = ed[bi], ej = ed[bj];
-                const int hI = (int)((ei >> 8) & 255) - (int)(ei & 255);
-                const int wJ = (int)(ej >> 24) - (int)((ej >> 16) & 255);
-                const float inv = (hI > 0 && wJ > 0) ? rcp_approx((float)(hI * wJ)) : 0.f;
-                float4 v = pre[n];
-                v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-                st4(g + ((rr * KK + itBin[n]) * 4 + (itQ[n] ^ (bj & 3))) * 4, v);
-            }
-            for (int idx = tid; idx < H * RG; idx += NT) {
-                const int y = idx / RG, rr = idx - y * RG;
-                unsigned m = 0;
-                if (rr < nr) {
-                    const uint32_t* ed = edgeS + (grp * RG + rr) * K;
-#pragma unroll
-                    for (int b = 0; b < K; ++b) {
-                        const uint32_t e = ed[b];
-                        const int i0 = e & 255, i1 = (e >> 8) & 255;
-                        m |= (i0 <= y && y < i1) ? (1u << b) : 0u;
-                    }
-                }
-                coverS[buf * coverBuf + idx] = (unsigned char)m;
-            }
-            // per (RoI, lane): byte offsets inside a D row of the lane's two updates (+t at J0_j, -t at J1_j), bit 31 = simple
-            for (int idx = tid; idx < RG * 32; idx += NT) {
-                const int rr = idx >> 5, ln = idx & 31;
-                uint32_t w = 0;
-                if (rr < nr) {
-                    const int jj = min(ln >> 2, K - 1), qq = ln & 3;
-                    const uint32_t ej = edgeS[(grp * RG + rr) * K + jj];
-                    const int J0 = (ej >> 16) & 255, J1 = ej >> 24;
-                    w = (uint32_t)(vec_pix_off(J0, qq) * 4) | ((uint32_t)(vec_pix_off(J1, qq) * 4) << 14) |
-                        (simpleS[grp * RG + rr] ? 0x80000000u : 0u);
-                }
-                offS[buf * RG * 32 + idx] = w;
-            }
-            if (tid == 0) counter[buf] = 0;
-        };
-
-        const int nGroups = (nrc + RG - 1) / RG;
-        prefetch(0);
-        commit(0, 0);
-        const int laneG = jact ? (j * 4 + (q ^ (j & 3))) * 4 : 0;  // float offset of this lane's slot inside a bin row
-
-        for (int grp = 0; grp < nGroups; ++grp) {
-            const int buf = grp & 1;
-            __syncthreads();  // stage / cover / offsets / counter of `buf` complete; everyone is done with group grp-1
-            if (grp + 1 < nGroups) prefetch(grp + 1);
-            const float* gB = gS + buf * GSZ + laneG;
-            const unsigned char* cov = coverS + buf * coverBuf;
-            const uint32_t* offB = offS + buf * RG * 32 + lane;
-            while (true) {
-                int task = 0;
-                if (lane == 0) task = atomicAdd(&counter[buf], 1);
-                task = __shfl_sync(0xffffffffu, task, 0);
-                if (task >= H) break;
-                // centre rows first (they are covered by most RoIs): better tail balance.  c = H/2; tasks alternate
-                // c, c+1, c-1, c+2, ... while rows above c last (there are U = H-1-c <= c of them), then walk down to 0.
-                const int cRow = H >> 1, U2 = 2 * (H - 1 - cRow);
-                const int y = task < U2 ? ((task & 1) ? cRow + 1 + (task >> 1) : cRow - (task >> 1))
-                                        : cRow - (U2 >> 1) - (task - U2);
-                const uint2 masks2 = *reinterpret_cast<const uint2*>(cov + y * RG);  // one cover byte per RoI of the group
-                char* row = reinterpret_cast<char*>(D + y * rowPitch);
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                unsigned masks = half ? masks2.y : masks2.x;
-                while (masks != 0u) {  // RoIs of the group that cover this row, in ascending order
-                    const int r4 = (__ffs(masks) - 1) >> 3;
-                    unsigned cover = (masks >> (8 * r4)) & 0xffu;
-                    masks &= ~(0xffu << (8 * r4));
-                    const int rr = r4 + 4 * half;
-                    const uint32_t w = offB[rr * 32];
-                    const float* gR = gB + rr * (KK * 16);
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    while (cover) {  // bin rows containing y (1, or 2 where floor/ceil edges overlap)
-                        const int i = __ffs(cover) - 1;
-                        cover &= cover - 1;
-                        const float4 v = ld4(gR + i * (K * 16));
-                        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-                    }
-                    float* pA = reinterpret_cast<float*>(row + (w & 0x3fffu));
-                    float* pB = reinterpret_cast<float*>(row + ((w >> 14) & 0x3fffu));
-                    if (w & 0x80000000u) {
-                        if (jact) {
-                            float4 a = ld4(pA);
-                            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-                            st4(pA, a);
-                        }
-                        __syncwarp();
-                        if (jact) {
-                            float4 b = ld4(pB);
-                            b.x -= t.x; b.y -= t.y; b.z -= t.z; b.w -= t.w;
-                            st4(pB, b);
-                        }
-                        __syncwarp();
-                    } else {
-                        for (int jj = 0; jj < K; ++jj) {  // degenerate RoI (bins thinner than a pixel / clamped): one bin column at a time
-                            if (j == jj) {
-                                float4 a = ld4(pA);
-                                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-                                st4(pA, a);
-                            }
-                            __syncwarp();
-                            if (j == jj) {
-                                float4 b = ld4(pB);
-                                b.x -= t.x; b.y -= t.y; b.z -= t.z; b.w -= t.w;
-                                st4(pB, b);
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-                }
-            }
-            if (grp + 1 < nGroups) commit(grp + 1, buf ^ 1);
-        }
-    }
-    __syncthreads();
-
-    // ---- epilogue: inclusive row scan, then transposed write-out (LDS.128 -> 4 coalesced plane stores) -------
-    for (int t = tid; t < H * 4; t += NT) {
-        const int y = t >> 2, qq = t & 3;
-        float* row = D + y * rowPitch;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int x = 0; x < W; ++x) {
-            float* p = row + vec_pix_off(x, qq);
-            const float4 v = ld4(p);
-            acc.x += v.x;
-            acc.y += v.y;
-            acc.z += v.z;
-            acc.w += v.w;
-            st4(p, acc);
-        }
-    }
-    __syncthreads();
-    {
-        const int total = 4 * HW;
-        for (int idx = tid; idx < total; idx += NT) {
-            const int qq = idx / HW, pix = idx - qq * HW;
-            const int y = pix / W, x = pix - y * W;
-            const float4 v = ld4(D + y * rowPitch + vec_pix_off(x, qq));
-            float* dst = gin + (size_t)(c0 + 4 * qq) * HW + pix;
-            if (4 * qq + 0 < cb) dst[0] = v.x;
-            if (4 * qq + 1 < cb) dst[HW] = v.y;
-            if (4 * qq + 2 < cb) dst[2 * HW] = v.z;
-            if (4 * qq + 3 < cb) dst[3 * HW] = v.w;
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------
 static int vec_pick_cb(int C, int sms) {
@@ -473,32 +211,11 @@ static size_t vec_fwd_smem(int H, int W, int k) {
     return (size_t)H * vec_row_pitch(W) * sizeof(float) + (size_t)kVecFwdWarps * kVecSlots * SP * sizeof(float) +
            (size_t)kVecRChunk * k * sizeof(uint32_t) + 16;
 }
-static size_t vec_bwd_smem(int H, int W, int k) {
-    const int SP = vec_stage_pitch(k * k);
-    return (size_t)H * vec_row_pitch(W) * sizeof(float) + (size_t)2 * kVecBwdRG * kVecSlots * SP * sizeof(float) +
-           (size_t)kVecRChunk * k * sizeof(uint32_t) + kVecRChunk + (size_t)2 * ((H * kVecBwdRG + 15) / 16 * 16) +
-           (size_t)2 * kVecBwdRG * 32 * sizeof(uint32_t) + 16;
-}
-static int vec_bwd_warps(int H) {
-    const int rowsPerWarp = ceil_div(H, kVecBwdMaxWarps);
-    return ceil_div(H, rowsPerWarp);
-}
-
 bool roipool_vec_supported(int R, int C, int H, int W, int k) {
     if (k != 7 || R <= 0 || C <= 0 || H > 255 || W > 255) return false;
-    static int off = -1;
-    if (off < 0) {
-        const char* e = getenv("D2T_ROIPOOL_VEC");
-        off = (e && e[0] == '0') ? 1 : 0;
-    }
-    if (off) return false;
     DeviceInfo di;
     if (device_info(&di)) return false;
-    if (vec_fwd_smem(H, W, k) > (size_t)di.max_smem_optin || vec_bwd_smem(H, W, k) > (size_t)di.max_smem_optin) return false;
-    // backward staging map: two elements per thread must cover a RoI's 16*k*k floats
-    int nw = vec_bwd_warps(H);
-    if (nw < 13) nw = 13;
-    return 4 * nw * 32 >= kVecBwdRG * 4 * k * k;  // backward staging: 4 items per thread cover a group
+    return vec_fwd_smem(H, W, k) <= (size_t)di.max_smem_optin;
 }
 
 int roipool_vec_fwd_launch(const float* fm, const float* rois, float* out, int R, int C, int H, int W, int k,
@@ -509,25 +226,8 @@ int roipool_vec_fwd_launch(const float* fm, const float* rois, float* out, int R
     const int CB = vec_pick_cb(C, di.sm_count);
     const size_t smem = vec_fwd_smem(H, W, k);
     auto kern = roipool_vec_fwd_kernel<7>;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(kern, smem);
     kern<<<ceil_div(C, CB), kVecFwdThreads, smem, st>>>(fm, rois, out, R, C, H, W, CB);
-    D2T_CUDA_TRY(cudaGetLastError());
-    note_launch();
-    return D2T_OK;
-}
-
-int roipool_vec_bwd_launch(const float* go, const float* rois, float* gin, int R, int C, int H, int W, int k,
-                           cudaStream_t st) {
-    DeviceInfo di;
-    int rc = device_info(&di);
-    if (rc) return rc;
-    const int CB = vec_pick_cb(C, di.sm_count);
-    const size_t smem = vec_bwd_smem(H, W, k);
-    int nw = vec_bwd_warps(H);
-    if (nw < 13) nw = 13;  // staging needs 4 * threads >= 8 * 4 * 49
-    auto kern = roipool_vec_bwd_kernel<7>;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ceil_div(C, CB), nw * 32, smem, st>>>(go, rois, gin, R, C, H, W, CB);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;

@@ -323,8 +323,6 @@ roipool_vec2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ 
 bool roipool_vec2_bwd_supported(int R, int C, int H, int W, int k) {
     if (k != V2K || R <= 0 || C <= 0 || H <= 0 || W <= 0 || H > 255 || W > 254) return false;
     if ((long long)C * V2KK * V2RG >= (1ll << 31)) return false;  // copy offsets are ints
-    const char* e = getenv("D2T_ROIPOOL_BWD");  // "vec": the third-generation kernel, "col": pool_col.cu
-    if (e && e[0] != '\0' && !(e[0] == 'v' && e[1] == '2')) return false;
     DeviceInfo di;
     if (device_info(&di)) return false;
     return v2_layout(H, W, V2Slots).total <= (size_t)di.max_smem_optin;
@@ -344,7 +342,7 @@ int roipool_vec2_bwd_launch(const float* go, const float* rois, float* gin, int 
     }
     if (CB < 1) CB = 1;
     const size_t smem = v2_layout(H, W, CB).total;
-    D2T_CUDA_TRY(cudaFuncSetAttribute(roipool_vec2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D2T_SMEM_OPTIN(roipool_vec2_bwd_kernel, smem);
     roipool_vec2_bwd_kernel<<<ceil_div(C, CB), V2Threads, smem, st>>>(go, rois, gin, R, C, H, W, CB);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();

@@ -65,22 +65,15 @@ def pointwise_correlation_backward(
 
 
 class PointwiseCorrelationFunction(Function):
-    """pointwise local correlations.
-    see https://arxiv.org/abs/1710.03958"""
+    """autograd node of the D&T cross-frame correlation layer (arXiv 1710.03958, eq. 4); same `apply` signature as
+    the reference Function (pointwise_correlation.py:25-67)."""
 
     @staticmethod
     def forward(ctx, FM0: Tensor, FM1: Tensor, d_max: int, stride: int) -> Tensor:
-        """pointwise correlations between FM0 and FM1.
-
-        Args:
-            FM0: (|B|, C, H, W) feature map at time t.
-            FM1: (|B|, C, H, W) feature mat at time t+tau.
-            d_max: maximum displacement.
-            stride: stride between displacements.
-
-        Returns:
-            out: (|B|, H, W, (2d+1), (2d+1)) pointwise correlations.
-        """
+        """FM0, FM1: (B, C, H, W) CUDA, contiguous, same dtype (frames t and t+tau).
+        Returns (B, H, W, 2*d_max+1, 2*d_max+1): entry (ci, cj) of position (i, j) is the channel dot product of
+        FM0[:, :, i, j] with FM1[:, :, i-d_max+ci, j-d_max+cj] for the displacements the reference samples
+        (the last row/column is never sampled; stride phase follows the clamped start), 0 elsewhere."""
         ctx.save_for_backward(FM0, FM1)
         ctx.d_max = d_max
         ctx.stride = stride
@@ -88,7 +81,7 @@ class PointwiseCorrelationFunction(Function):
 
     @staticmethod
     def backward(ctx, grad_out: Tensor) -> Tuple[Tensor, Tensor, None, None]:
-        """given derivatives wrt out, compute derivatives wrt FM0 and FM1."""
+        """grad_out (B, H, W, k, k) -> (grad_FM0, grad_FM1, None, None); deterministic (no atomics)."""
         grad_out = grad_out.contiguous()
         FM0, FM1 = ctx.saved_tensors
         grad_FM0, grad_FM1 = pointwise_correlation_backward(grad_out, FM0, FM1, ctx.d_max, ctx.stride)
@@ -96,13 +89,8 @@ class PointwiseCorrelationFunction(Function):
 
 
 class PointwiseCorrelation(Module):
-    """pointwise local correlations.
-    see https://arxiv.org/abs/1710.03958
-
-    Args:
-        d_max: maximum displacement.
-        stride: displacement stride.
-    """
+    """nn.Module face of `PointwiseCorrelationFunction`; constructor `(d_max, stride)` and attributes `.d_max`,
+    `.stride` as in the reference (pointwise_correlation.py:70-95)."""
 
     def __init__(self, d_max: int, stride: int) -> None:
         super().__init__()
@@ -110,12 +98,5 @@ class PointwiseCorrelation(Module):
         self.stride = stride
 
     def forward(self, FM0: Tensor, FM1: Tensor) -> Tensor:
-        """
-        Args:
-            FM0: (|B|, C, H, W) feature map at time t.
-            FM1: (|B|, C, H, W) feature map at time t+tau.
-
-        Returns:
-            out: (|B|, H, W, (2d+1), (2d+1)) pointwise correlations.
-        """
+        """(B, C, H, W) x 2 -> (B, H, W, 2d+1, 2d+1); see `PointwiseCorrelationFunction.forward`."""
         return PointwiseCorrelationFunction.apply(FM0, FM1, self.d_max, self.stride)

@@ -133,22 +133,14 @@ class PSROIPoolBatchedFunction(Function):
 
 
 class PSROIPoolFunction(Function):
-    """position-sensitive ROI-pooling function.
-    see https://arxiv.org/abs/1605.06409"""
+    """autograd node of R-FCN's position-sensitive RoI pooling (arXiv 1605.06409) as the reference implements it
+    (ps_roipool.py:24-72): same `apply` signature plus the optional trailing `canonical_map`."""
 
     @staticmethod
     def forward(ctx, FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
-        """
-        Args:
-            FM: (n_targets * r_hw^2, H, W); feature map for position-sensitive
-                pooling.
-            rois: (|R|, 4); region of interest bounding boxes.
-            n_targets: number of targets per ROI.
-            r_hw: height and width of pooled features.
-
-        Returns:
-            pooled: (|R|, n_targets, r_hw, r_hw) pooled feature map.
-        """
+        """FM (n_targets*r_hw^2, H, W), rois (R, 4) fractional ijhw -> (R, n_targets, r_hw, r_hw): cell (i, j) of
+        target t is the mean of channel (t+1)*(i*r_hw+j) (the reference's map, F6) over the cell's pixels; the RoI
+        start is NOT clamped and an empty cell gives 0 (F7).  Raises ValueError on a channel-count mismatch."""
         ctx.save_for_backward(rois)
         _, ctx.fm_h, ctx.fm_w = FM.shape
         ctx.canonical_map = canonical_map
@@ -164,15 +156,7 @@ class PSROIPoolFunction(Function):
 
     @staticmethod
     def backward(ctx: object, grad_out: Tensor) -> Tuple[Tensor, None, None, None, None]:
-        """
-        Args:
-            grad_out: (|R|, n_targets, r_hw, r_hw); loss derivatives wrt
-                pooling output.
-
-        Returns:
-            grad_FM: (n_targets * r_hw^2, H, W); loss derivatives wrt
-                pooling input.
-        """
+        """grad_out (R, n_targets, r_hw, r_hw) -> (grad_FM (n_targets*r_hw^2, H, W), None, ...)."""
         grad_out = grad_out.contiguous()
         rois, = ctx.saved_tensors
         grad_FM = ps_roipool_backward(grad_out, rois, ctx.fm_h, ctx.fm_w, ctx.canonical_map)
@@ -180,14 +164,8 @@ class PSROIPoolFunction(Function):
 
 
 class PSROIPool(Module):
-    """position-sensitive ROI-Pooling layer.
-    see https://arxiv.org/abs/1605.06409
-
-    Args:
-        n_targets: number of targets per ROI.
-        r_hw: height and with of pooled features.
-        canonical_map: opt-in extension, see module docstring (default: reference behaviour).
-    """
+    """nn.Module face of `PSROIPoolFunction`; constructor `(n_targets, r_hw)` and attributes `.n_targets`, `.r_hw` as
+    in the reference (ps_roipool.py:75-99).  `canonical_map=True` is an opt-in extension (module docstring)."""
 
     def __init__(self, n_targets: int, r_hw: int, canonical_map: bool = False) -> None:
         super().__init__()
@@ -196,15 +174,7 @@ class PSROIPool(Module):
         self.canonical_map = canonical_map
 
     def forward(self, FM: Tensor, rois: Tensor) -> Tensor:
-        """
-        Args:
-            FM: (n_targets * r_hw^2, H, W); feature map for position-sensitive
-                pooling.
-            rois: (|R|, 4) region of interest bounding boxes.
-
-        Returns:
-            pooled: (|R|, n_targets, r_hw, r_hw): pooled output.
-        """
+        """(n_targets*r_hw^2, H, W), (R, 4) -> (R, n_targets, r_hw, r_hw); see `PSROIPoolFunction.forward`."""
         if self.canonical_map:
             return PSROIPoolFunction.apply(FM, rois, self.n_targets, self.r_hw, True)
         return PSROIPoolFunction.apply(FM, rois, self.n_targets, self.r_hw)

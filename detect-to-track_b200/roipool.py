@@ -82,27 +82,20 @@ def pool_bins(rois: Tensor, H: int, W: int, r_hw: int, clamp_start: bool) -> Ten
 
 
 class ROIPoolFunction(Function):
-    """RoI Pooling function."""
+    """autograd node of the reference's AVERAGE RoI pooling (roipool.py:22-57): same `apply` signature."""
 
     @staticmethod
     def forward(ctx: object, FM: Tensor, rois: Tensor, r_hw: int) -> Tensor:
-        """RoI Pooling from FM, directed by rois.
-
-        Args:
-            FM: (C, H, W) feature map to pool from.
-            rois: (|R|, 4) rois to pool from. (ijhw, fractional)
-            r_hw: height and width of pooled feature maps.
-
-        Returns:
-            out: (|R|, C, r_hw, r_hw) pooled features.
-        """
+        """FM (C, H, W), rois (R, 4) = fractional (centre_i, centre_j, height, width) of the same dtype ->
+        (R, C, r_hw, r_hw) bin means.  The RoI start is clamped to the map (a box crossing the top/left border is
+        shifted, F7); an empty bin gives 0/0 = NaN like the reference."""
         ctx.i_h, ctx.i_w = FM.shape[-2:]
         ctx.save_for_backward(rois)
         return roipool_forward(FM, rois, r_hw)
 
     @staticmethod
     def backward(ctx: object, grad_out: Tensor) -> Tuple[Tensor, None, None]:
-        """given loss derivatives wrt output, compute loss derivatives wrt input."""
+        """grad_out (R, C, r_hw, r_hw) -> (grad_FM, None, None); there is no gradient for `rois`."""
         grad_out = grad_out.contiguous()
         rois, = ctx.saved_tensors
         grad_fm = roipool_backward(grad_out, rois, ctx.i_h, ctx.i_w)
@@ -110,24 +103,13 @@ class ROIPoolFunction(Function):
 
 
 class ROIPool(Module):
-    """RoI Pooling from FM, directed by rois.
-    see https://arxiv.org/abs/1504.08083.
-
-    Args:
-        r_hw: height and width of pooled feature maps.
-    """
+    """nn.Module face of `ROIPoolFunction`; constructor `(r_hw)` and attribute `.r_hw` as in the reference
+    (roipool.py:60-81)."""
 
     def __init__(self, r_hw: int) -> None:
         super().__init__()
         self.r_hw = r_hw
 
     def forward(self, FM: Tensor, rois: Tensor) -> Tensor:
-        """
-        Args:
-            FM0: (C, H, W) input feature map.
-            rois: (|R|, 4) regions of interest (ijhw, fractional).
-
-        Returns:
-            out: (|R|, C, r_hw, r_hw) pooled features.
-        """
+        """(C, H, W), (R, 4) -> (R, C, r_hw, r_hw); see `ROIPoolFunction.forward`."""
         return ROIPoolFunction.apply(FM, rois, self.r_hw)

@@ -36,7 +36,8 @@
  *     function returns 0.  Contents are undefined afterwards.
  *   - Return value: 0 on success; non-zero on bad arguments or a CUDA launch
  *     error, with a message retrievable from d2t_last_error() (thread-local).
- *   - Re-entrant; no global mutable state besides a per-device attribute cache.
+ *   - Re-entrant; no global mutable state besides per-device caches of device attributes and of the kernels'
+ *     shared-memory opt-in, and the launch counter.  No environment variable is read anywhere.
  *   - Results are deterministic: no floating-point atomics anywhere.
  *
  * RoIs are fractional (centre_i, centre_j, height, width) in [0,1] map units,
@@ -83,13 +84,21 @@ D2T_API int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int
 D2T_API int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
                      int stride, void* ws, size_t ws_bytes, void* stream);
 
-/* Experimental tensor-core forward (tcgen05 + TMEM, 3xTF32 split; d_max = 8, stride = 1 only).  Same contract and
- * workspace as d2t_corr_fwd_f32; values agree with it to |err| <= 4e-6 * sum_c |fm0*fm1| (looser than the FP32-pipe
- * kernel).  No counterpart in the reference; not used by the Python mirror unless D2T_CORR_FWD=umma. */
-D2T_API int d2t_corr_fwd_f32_tc(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max,
-                        int stride, void* ws, size_t ws_bytes, void* stream);
-
-/* grad_out : (B, H, W, 2d+1, 2d+1);  grad_fm0, grad_fm1 : (B, C, H, W) */
+/* grad_out : (B, H, W, 2d+1, 2d+1);  grad_fm0, grad_fm1 : (B, C, H, W)
+ *
+ * Kernel family of d2t_corr_bwd_f32 -- a function of (C, d_max, stride) only, never of B, H or W, so the gradients of
+ * an image do not depend on the batch it is in:
+ *   d_max == 8, stride == 1, C >= 128 : tensor cores (tcgen05 + TMEM, 3xTF32 split with a round-to-nearest hi part).
+ *       Each gradient element agrees with the exact sum to |err| <= 2e-6 * sum |grad_out * fm| over its 256 terms
+ *       (measured 9e-7, tools/umma_sw128_test.cu): inside rtol 1e-4 of the result's scale, looser than FP32 FMAs.
+ *       Needs the workspace d2t_corr_bwd_workspace_bytes reports (a flipped copy of grad_out); a missing workspace is
+ *       an error (D2T_ERR_WORKSPACE), never a silent change of kernel.  Non-finite inputs: the hi/lo split turns
+ *       +-Inf into NaN and the dense 128-position tile product spreads a NaN/Inf of a 23x31 halo patch to every
+ *       position of that tile, whereas the reference only poisons the windows that contain the value.
+ *   otherwise : FP32 FMAs (SIMT band kernel for d_max in {4, 8} with stride 1, generic gather kernel for the rest).
+ * d2t_corr_bwd_f32_simt / d2t_corr_bwd_f32_tc select a family explicitly (same contract; _tc requires d_max == 8,
+ * stride == 1 and uses d2t_corr_bwd_tc_workspace_bytes).  All families are bitwise reproducible run to run (no atomics).
+ */
 D2T_API size_t d2t_corr_bwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size);
 D2T_API int d2t_corr_bwd_f32(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0,
                      float* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,
@@ -97,12 +106,9 @@ D2T_API int d2t_corr_bwd_f32(const float* grad_out, const float* fm0, const floa
 D2T_API int d2t_corr_bwd_f64(const double* grad_out, const double* fm0, const double* fm1, double* grad_fm0,
                      double* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,
                      size_t ws_bytes, void* stream);
-
-/* Tensor-core backward (tcgen05 + TMEM, 3xTF32 split with a round-to-nearest hi part; d_max = 8, stride = 1 only).
- * Same contract as d2t_corr_bwd_f32 with its own workspace size (a flipped copy of grad_out, B*H*W*256 floats).  Each
- * gradient element agrees with the exact sum to |err| <= 2e-6 * sum |grad_out * fm| over its 256 terms (measured 9e-7,
- * tools/umma_sw128_test.cu) -- looser than the FP32-pipe kernel, inside rtol 1e-4 of the result's scale.  Bitwise
- * reproducible run to run (no atomics).  d2t_corr_bwd_f32 dispatches here when D2T_CORR_BWD=umma. */
+D2T_API int d2t_corr_bwd_f32_simt(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0,
+                        float* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,
+                        size_t ws_bytes, void* stream);
 D2T_API size_t d2t_corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int d_max, int stride);
 D2T_API int d2t_corr_bwd_f32_tc(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0,
                         float* grad_fm1, int B, int C, int H, int W, int d_max, int stride, void* ws,

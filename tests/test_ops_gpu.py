@@ -36,6 +36,21 @@ def close(got: torch.Tensor, want, dtype, scale=None, equal_nan=False):
     np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, equal_nan=equal_nan)
 
 
+def corr_live_mask(H, W, d, stride):
+    """(H, W, 2d+1, 2d+1) bool: entry (i, j, ci, cj) is sampled by the reference's loops
+    (pointwise_correlation_cuda.cu:92-100) iff ci < 2d, 0 <= i-d+ci < H and ((i-d+ci) - max(0, i-d)) % stride == 0,
+    and the same along j."""
+    def axis(n):
+        m = np.zeros((n, 2 * d + 1), bool)
+        for i in range(n):
+            lo = max(0, i - d)
+            for p in range(lo, min(i + d, n), stride):
+                m[i, p - i + d] = True
+        return m
+    mi, mj = axis(H), axis(W)
+    return mi[:, None, :, None] & mj[None, :, None, :]
+
+
 # ------------------------------------------------------------------ correlation
 CORR_CASES = [
     (1, 2, 10, 10, 3, 1), (2, 2, 11, 10, 3, 2), (2, 2, 10, 11, 3, 1), (1, 2, 11, 11, 3, 2),    # reference grid
@@ -54,13 +69,96 @@ def test_corr_fwd_bwd_vs_oracle(cuda, B, C, H, W, d, stride, dtype):
     out = pc_mod.pointwise_correlation_forward(dev(fm0, cuda), dev(fm1, cuda), d, stride)
     want = oracle.corr_fwd(fm0, fm1, d, stride)
     close(out, want, dtype)
-    # live mask exact: dead entries are exactly zero
-    assert torch.equal(out.cpu() == 0, torch.from_numpy(want == 0)) or np.count_nonzero(want == 0) <= np.count_nonzero(out.cpu().numpy() == 0)
+    # structural live mask (SURVEY.md F4/F5 closed form): every dead entry is EXACTLY zero, in our output and in the oracle's
+    live = torch.from_numpy(corr_live_mask(H, W, d, stride))
+    assert torch.equal((out.cpu() != 0) & ~live, torch.zeros_like(live).expand_as(out))
+    assert not bool(((torch.from_numpy(want) != 0) & ~live).any())
     assert float(out[..., 2 * d, :].abs().max()) == 0 and float(out[..., :, 2 * d].abs().max()) == 0
     g0, g1 = pc_mod.pointwise_correlation_backward(dev(go, cuda), dev(fm0, cuda), dev(fm1, cuda), d, stride)
     w0, w1 = oracle.corr_bwd(go, fm0, fm1, d, stride)
     close(g0, w0, dtype)
     close(g1, w1, dtype)
+
+
+def test_corr_live_mask_is_exact_on_strictly_positive_inputs(cuda):
+    """with strictly positive maps every sampled entry is > 0, so the zero pattern of the output IS the structural
+    mask: torch.equal against the closed form, for both strides and both tuned / generic kernels."""
+    for (B, C, H, W, d, stride) in [(2, 3, 11, 10, 3, 2), (1, 24, 38, 63, 8, 1), (2, 8, 12, 13, 4, 1), (1, 4, 9, 14, 2, 3)]:
+        g = torch.Generator(device="cpu").manual_seed(3)
+        fm0 = (torch.rand(B, C, H, W, generator=g) + 0.5).to(cuda)
+        fm1 = (torch.rand(B, C, H, W, generator=g) + 0.5).to(cuda)
+        out = pc_mod.pointwise_correlation_forward(fm0, fm1, d, stride)
+        live = torch.from_numpy(corr_live_mask(H, W, d, stride)).to(cuda)
+        assert torch.equal(out != 0, live.expand_as(out))
+
+
+@pytest.mark.parametrize("name,C", [("c3", 512), ("c4", 1024), ("c5", 2048)])
+def test_corr_bench_shapes_vs_reference_kernels(cuda, name, C):
+    """BASELINE config 3 at FULL size with DEFAULT dispatch -- B = 8, 38x63, d = 8: the SIMT band forward and the
+    tcgen05 (3xTF32) backward, the exact kernels and shapes bench.py times -- against the reference's own CUDA kernels
+    (oracle/_ref) run on the same device.  Same tolerance as everywhere: rtol 1e-4, atol 1e-5 * max|ref|."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    B, H, W, d = 8, 38, 63, 8
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    fm0 = (torch.randn(B, C, H, W, generator=g).relu_() / 16).to(cuda)
+    fm1 = (torch.randn(B, C, H, W, generator=g).relu_() / 16).to(cuda)
+    go = torch.randn(B, H, W, 17, 17, generator=g).to(cuda)
+    out = pc_mod.pointwise_correlation_forward(fm0, fm1, d, 1)
+    ref = ref_cuda.corr_fwd(fm0, fm1, d, 1)
+    close(out, ref.cpu().numpy(), np.float32)
+    live = torch.from_numpy(corr_live_mask(H, W, d, 1)).to(cuda)
+    assert not bool(((out != 0) & ~live).any())
+    g0, g1 = pc_mod.pointwise_correlation_backward(go, fm0, fm1, d, 1)
+    r0, r1 = ref_cuda.corr_bwd(go, fm0, fm1, d, 1)
+    close(g0, r0.cpu().numpy(), np.float32)
+    close(g1, r1.cpu().numpy(), np.float32)
+
+
+def test_corr_backward_is_batch_invariant(cuda):
+    """the kernel family behind d2t_corr_bwd_f32 depends on (C, d_max, stride) only (include/d2t_b200.h), so the
+    gradients of an image are bit-identical whether it is processed alone or inside a batch of 8."""
+    for C in (64, 512):   # FP32-pipe family / tensor-core family
+        fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(8, C, 38, 63, 8, seed=19, dtype=np.float32))
+        g0, g1 = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
+        for b in (0, 5):
+            h0, h1 = pc_mod.pointwise_correlation_backward(go[b:b + 1].contiguous(), fm0[b:b + 1].contiguous(),
+                                                           fm1[b:b + 1].contiguous(), 8, 1)
+            assert torch.equal(g0[b:b + 1], h0) and torch.equal(g1[b:b + 1], h1)
+
+
+def test_corr_nonfinite_inputs(cuda):
+    """a NaN / Inf in one key pixel: the forward and the FP32-pipe backward poison exactly the windows that contain it,
+    like the reference; the tensor-core backward is documented to spread it over the affected 8x16 tiles only
+    (include/d2t_b200.h) -- positions of other tiles stay finite and correct."""
+    B, C, H, W, d = 1, 128, 38, 63, 8
+    fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(B, C, H, W, d, seed=23, dtype=np.float32))
+    bad = fm1.clone()
+    bad[0, 3, 20, 40] = float("inf")
+    out = pc_mod.pointwise_correlation_forward(fm0, bad, d, 1)
+    clean = pc_mod.pointwise_correlation_forward(fm0, fm1, d, 1)
+    nonfinite = ~torch.isfinite(out)
+    # exactly the (i, j, ci, cj) with i-d+ci == 20 and j-d+cj == 40
+    want = torch.zeros_like(nonfinite)
+    for i in range(max(0, 20 - d + 1), min(H, 20 + d + 1)):
+        for j in range(max(0, 40 - d + 1), min(W, 40 + d + 1)):
+            want[0, i, j, 20 - i + d, 40 - j + d] = True
+    assert torch.equal(nonfinite, want)
+    assert torch.equal(out[~want], clean[~want])
+    from detect_to_track_b200 import _lib
+    lib = _lib.lib()
+    g0, g1 = torch.empty_like(fm0), torch.empty_like(fm1)
+    rc = lib.d2t_corr_bwd_f32_simt(go.data_ptr(), fm0.data_ptr(), bad.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, C, H, W, d, 1,
+                                   None, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    nf0 = ~torch.isfinite(g0)
+    assert bool(nf0[0, 3].any()) and not bool(nf0[0, :3].any()) and not bool(nf0[0, 4:].any())   # only channel 3 of grad_FM0
+    assert bool(torch.isfinite(g1).all())                                                         # grad_FM1 does not read FM1
+    # tensor-core family: rows 12..27 / cols 32..48 can see pixel (20, 40); tiles are 8 rows x 16 cols
+    t0, t1 = pc_mod.pointwise_correlation_backward(go, fm0, bad, d, 1)
+    nf = ~torch.isfinite(t0)
+    assert not bool(nf[0, :, :8].any()) and not bool(nf[0, :, 32:].any()) and not bool(nf[0, :, :, :16].any())
+    assert bool(torch.isfinite(t1).all())
 
 
 @pytest.mark.parametrize("B,C,H,W,d,stride", [(2, 2, 11, 10, 3, 2), (2, 64, 32, 32, 4, 1), (1, 48, 38, 63, 8, 1)])
@@ -75,20 +173,6 @@ def test_corr_vs_reference_kernels(cuda, B, C, H, W, d, stride):
     close(g1, r1.cpu().numpy(), np.float32)
 
 
-def test_roipool_row_owner_backward_experiment(cuda, monkeypatch):
-    """pool_rows.cu (D2T_ROIPOOL_ROWS=1): lanes own pixel rows; same results as the default kernel within rounding,
-    bitwise reproducible, edge-case RoIs included."""
-    C, H, W, k = 45, 38, 63, 7
-    rois = np.concatenate([cases.rois_random(150, 21), cases.rois_edge_cases(H, W)], 0)
-    fm, go = cases.pool_inputs(C, H, W, (len(rois), C, k, k), seed=22)
-    want = oracle.roipool_bwd(go, rois, H, W)
-    monkeypatch.setenv("D2T_ROIPOOL_ROWS", "1")
-    a = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
-    b = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
-    close(a, want, np.float32)
-    assert torch.equal(a, b)
-
-
 @pytest.mark.parametrize("d_max", [3])
 @pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("input_b", [1, 2])
@@ -101,29 +185,6 @@ def test_pointwise_correlation_gradients(cuda, d_max, stride, input_b, input_c, 
     fm0 = torch.rand(*fm_shape).double().cuda().requires_grad_(True)
     fm1 = torch.rand(*fm_shape).double().cuda().requires_grad_(True)
     assert gradcheck(pc, (fm0, fm1))
-
-
-@pytest.mark.parametrize("B,C,H,W", [(1, 96, 38, 63), (3, 40, 20, 21), (1, 16, 70, 66), (2, 2048, 38, 63)])
-def test_corr_fwd_tensor_core_variant(cuda, B, C, H, W):
-    """experimental tcgen05 / 3xTF32 forward (d2t_corr_fwd_f32_tc): stated looser tolerance
-    |err| <= 1e-5 * sum_c |fm0*fm1| (measured 4e-6, tools/umma_test.cu), dead entries exactly zero."""
-    from detect_to_track_b200 import _lib
-    d = 8
-    g = torch.Generator(device="cpu").manual_seed(77)
-    fm0 = torch.randn(B, C, H, W, generator=g).to(cuda)
-    fm1 = torch.randn(B, C, H, W, generator=g).to(cuda)
-    lib = _lib.lib()
-    out = torch.empty((B, H, W, 17, 17), device=cuda)
-    n = lib.d2t_corr_fwd_workspace_bytes(B, C, H, W, d, 1, 4)
-    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=cuda)
-    rc = lib.d2t_corr_fwd_f32_tc(fm0.data_ptr(), fm1.data_ptr(), out.data_ptr(), B, C, H, W, d, 1, ws.data_ptr(), n,
-                                 torch.cuda.current_stream().cuda_stream)
-    assert rc == 0, _lib.last_error()
-    ref = pc_mod.pointwise_correlation_forward(fm0.double(), fm1.double(), d, 1)        # float64 generic kernel
-    mag = pc_mod.pointwise_correlation_forward(fm0.double().abs(), fm1.double().abs(), d, 1)
-    err = (out.double() - ref).abs()
-    assert bool((err <= 1e-5 * mag + 1e-30).all()), float((err / (mag + 1e-30)).max())
-    assert bool((out[ref == 0] == 0).all())
 
 
 @pytest.mark.parametrize("B,C,H,W", [(1, 96, 38, 63), (3, 40, 20, 21), (1, 16, 70, 66), (2, 300, 9, 17), (2, 2048, 38, 63)])
@@ -194,22 +255,21 @@ def test_tensor_core_kernels_stay_inside_their_buffers(cuda, B, C, H, W):
     assert intact(wsb, n_ws) and intact(g0b, fm0.numel()) and intact(g1b, fm1.numel())
     assert bool(torch.isfinite(g0).all()) and bool(torch.isfinite(g1).all())
 
+    # SIMT forward with its stream-K partial workspace
     n_fws = lib.d2t_corr_fwd_workspace_bytes(B, C, H, W, d, 1, 4) // 4
     fwb, fws = guarded(max(n_fws, 1))
     ob, o = guarded(B * H * W * 289)
-    rc = lib.d2t_corr_fwd_f32_tc(fm0.data_ptr(), fm1.data_ptr(), o.data_ptr(), B, C, H, W, d, 1, fws.data_ptr(), n_fws * 4, stream)
+    rc = lib.d2t_corr_fwd_f32(fm0.data_ptr(), fm1.data_ptr(), o.data_ptr(), B, C, H, W, d, 1, fws.data_ptr(), n_fws * 4, stream)
     assert rc == 0, _lib.last_error()
     torch.cuda.synchronize()
     assert intact(fwb, max(n_fws, 1)) and intact(ob, B * H * W * 289)
     assert not bool((o == sentinel).any())  # every output element is written (no memset needed)
 
 
-@pytest.mark.parametrize("variant", ["", "vec", "col", "tc", "v3"])
 @pytest.mark.parametrize("C,H,W,R", [(29, 38, 63, 97), (200, 17, 64, 300), (3, 38, 20, 5)])
-def test_roipool_backward_variants_stay_inside_their_buffers(cuda, monkeypatch, variant, C, H, W, R):
-    """every float32 ROIPool backward kernel with its output embedded in a sentinel-filled buffer and grad_out at the very
-    end of its allocation: guard zones untouched, every output element written (ragged channel tiles, partial RoI
-    groups / chunks, a channel count above one 192-channel tensor-core tile)."""
+def test_roipool_backward_stays_inside_its_buffers(cuda, C, H, W, R):
+    """the float32 ROIPool backward with its output embedded in a sentinel-filled buffer and grad_out at the very end of
+    its allocation: guard zones untouched, every output element written (ragged channel tiles, partial RoI groups)."""
     from detect_to_track_b200 import _lib
     lib = _lib.lib()
     k, guard, sentinel = 7, 4096, 1234.5
@@ -224,8 +284,6 @@ def test_roipool_backward_variants_stay_inside_their_buffers(cuda, monkeypatch, 
     n = C * H * W
     buf = torch.full((n + 2 * guard,), sentinel, device=cuda)
     gin = buf[guard:guard + n]
-    if variant:
-        monkeypatch.setenv("D2T_ROIPOOL_BWD", variant)
     rc = lib.d2t_roipool_bwd_f32(go.data_ptr(), rois.data_ptr(), gin.data_ptr(), R, C, H, W, k, None, 0,
                                  torch.cuda.current_stream().cuda_stream)
     assert rc == 0, _lib.last_error()
@@ -270,15 +328,34 @@ def test_pooling_on_maps_larger_than_the_packed_edge_range(cuda):
     close(ps_mod.ps_roipool_backward(dev(sgo, cuda), dev(rois, cuda), W, H), oracle.psroipool_bwd(sgo, rois, W, H), np.float32)
 
 
-def test_corr_bwd_dispatch_env(cuda, monkeypatch):
-    """D2T_CORR_BWD selects the kernel family behind d2t_corr_bwd_f32; both agree within the FP32 tolerance."""
-    fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 72, 38, 63, 8, seed=15, dtype=np.float32))
-    monkeypatch.setenv("D2T_CORR_BWD", "simt")
-    a = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
-    monkeypatch.setenv("D2T_CORR_BWD", "umma")
-    b = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
-    close(b[0], a[0].cpu().numpy(), np.float32)
-    close(b[1], a[1].cpu().numpy(), np.float32)
+def test_corr_bwd_explicit_families_agree(cuda):
+    """d2t_corr_bwd_f32_simt (FP32 FMAs) and d2t_corr_bwd_f32_tc (tcgen05, 3xTF32) agree within the FP32 tolerance, and
+    the default entry point picks the family the header documents (C >= 128 -> tensor cores, bit-identical to _tc)."""
+    from detect_to_track_b200 import _lib
+    lib = _lib.lib()
+    for C in (72, 200):
+        B, H, W, d = 2, 38, 63, 8
+        fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(B, C, H, W, d, seed=15, dtype=np.float32))
+        stream = torch.cuda.current_stream().cuda_stream
+        n = lib.d2t_corr_bwd_tc_workspace_bytes(B, C, H, W, d, 1)
+        ws = torch.empty(n, dtype=torch.uint8, device=cuda)
+        res = {}
+        for fam, args in (("simt", (None, 0)), ("tc", (ws.data_ptr(), n))):
+            g0, g1 = torch.empty_like(fm0), torch.empty_like(fm1)
+            rc = getattr(lib, f"d2t_corr_bwd_f32_{fam}")(go.data_ptr(), fm0.data_ptr(), fm1.data_ptr(), g0.data_ptr(), g1.data_ptr(),
+                                                         B, C, H, W, d, 1, *args, stream)
+            assert rc == 0, _lib.last_error()
+            res[fam] = (g0, g1)
+        close(res["tc"][0], res["simt"][0].cpu().numpy(), np.float32)
+        close(res["tc"][1], res["simt"][1].cpu().numpy(), np.float32)
+        dflt = pc_mod.pointwise_correlation_backward(go, fm0, fm1, d, 1)
+        fam = "tc" if C >= 128 else "simt"
+        assert torch.equal(dflt[0], res[fam][0]) and torch.equal(dflt[1], res[fam][1])
+    # a missing workspace is an error, never a silent change of kernel family
+    g0, g1 = torch.empty_like(fm0), torch.empty_like(fm1)
+    rc = lib.d2t_corr_bwd_f32(go.data_ptr(), fm0.data_ptr(), fm1.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, C, H, W, d, 1,
+                              None, 0, stream)
+    assert rc == 3
 
 
 def test_corr_backward_is_deterministic(cuda):
@@ -364,12 +441,9 @@ def test_roipool_vec_kernels_shapes(cuda, C, H, W, R):
     assert torch.equal(gin, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
 
 
-@pytest.mark.parametrize("variant", ["", "vec", "col", "tc", "v3"])
 @pytest.mark.parametrize("C,H,W,R", [(29, 38, 63, 300), (5, 38, 64, 1100), (18, 16, 20, 9), (1, 1, 1, 3), (7, 50, 70, 41)])
-def test_roipool_backward_variants(cuda, monkeypatch, variant, C, H, W, R):
-    """float32, r_hw = 7 backward kernels: the default (pool_vec2.cu: raw cp.async staging, per-row RoI lists, update
-    classes), the previous generation (D2T_ROIPOOL_BWD=vec, pool_vec.cu) and the column-owner experiment
-    (D2T_ROIPOOL_BWD=col, pool_col.cu; H <= 38, W <= 64, else it falls through to the default).  Each against the
+def test_roipool_backward_shapes(cuda, C, H, W, R):
+    """float32, r_hw = 7 backward (pool_vec2.cu: raw cp.async staging, per-row RoI lists, update classes) against the
     oracle and bitwise reproducible; channel counts that are not a multiple of 4, RoI counts that are not a multiple
     of the group size and exceed every table, RoIs whose bins are thinner than a pixel (update classes 1 and 2)."""
     k = 7
@@ -378,8 +452,6 @@ def test_roipool_backward_variants(cuda, monkeypatch, variant, C, H, W, R):
     rois = np.concatenate([rois, tiny], 0)
     _, go = cases.pool_inputs(C, H, W, (rois.shape[0], C, k, k), 35, np.float32)
     want = oracle.roipool_bwd(go, rois, H, W)
-    if variant:
-        monkeypatch.setenv("D2T_ROIPOOL_BWD", variant)
     a = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
     close(a, want, np.float32)
     assert torch.equal(a, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
@@ -436,6 +508,26 @@ def test_roipool_full_size_track_head(cuda):
     np.testing.assert_array_equal(rp_mod.roipool_forward(fm, rois, k, exact=True)[:, sel].cpu().numpy(), want)
     wg = oracle.roipool_bwd(go[:, sel].cpu().numpy().copy(), rois_np, H, W)
     close(gin[sel], wg, np.float32)
+
+
+def test_roipool_full_size_track_head_vs_reference_kernels(cuda):
+    """BASELINE config 4 at full size, the WHOLE tensors (not sampled channels) against the reference's own kernels
+    (oracle/_ref) on the same device: 300 x 1891 x 7 x 7 forward (NaN pattern of empty bins included, exact variant
+    bit-identical) and the 1891 x 38 x 63 backward."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    C, H, W, k, R = 1891, 38, 63, 7, 300
+    g = torch.Generator(device="cpu").manual_seed(1238)
+    fm = torch.randn(C, H, W, generator=g).to(cuda)
+    go = torch.randn(R, C, k, k, generator=g).to(cuda)
+    rois = dev(cases.rois_random(R, 1238), cuda)
+    ref = ref_cuda.roipool_fwd(fm, rois, k)
+    out = rp_mod.roipool_forward(fm, rois, k)
+    assert torch.equal(torch.isnan(out), torch.isnan(ref))
+    close(out, ref.cpu().numpy(), np.float32, equal_nan=True)
+    ex = rp_mod.roipool_forward(fm, rois, k, exact=True)
+    assert torch.equal(torch.nan_to_num(ex, nan=12345.0), torch.nan_to_num(ref, nan=12345.0))
+    close(rp_mod.roipool_backward(go, rois, H, W), ref_cuda.roipool_bwd(go, rois, H, W).cpu().numpy(), np.float32)
 
 
 # ------------------------------------------------------------------ PSROIPool
