@@ -59,8 +59,9 @@ class RFCN(nn.Module):
 class CorrelationTracker(nn.Module):
     """correlation tracker (correlation_tracker.py:13-87)."""
 
-    def __init__(self, d_max: int, r_hw: int, reg_channels: int, stride: int = 1) -> None:
+    def __init__(self, d_max: int, r_hw: int, reg_channels: int, stride: int = 1, fused: bool = False) -> None:
         super().__init__()
+        self.fused = fused
         self.point_corr = PointwiseCorrelation(d_max, stride)
         self.pool = ROIPool(r_hw)
         self.fc_channels = (3 * pow(2 * d_max + 1, 2) + 2 * reg_channels) * pow(r_hw, 2)
