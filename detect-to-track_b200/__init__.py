@@ -9,11 +9,12 @@ include/d2t_b200.h.  No Triton, no CPU fallback.
 from .pointwise_correlation import PointwiseCorrelation, PointwiseCorrelationFunction
 from .roipool import ROIPool, ROIPoolFunction
 from .ps_roipool import PSROIPool, PSROIPoolFunction, PSROIPoolBatched, PSROIPoolBatchedFunction
+from .track_head import TrackHeadFunction
 from .models import RFCN, CorrelationTracker
 
 __all__ = [
     "PointwiseCorrelation", "PointwiseCorrelationFunction",
     "ROIPool", "ROIPoolFunction",
     "PSROIPool", "PSROIPoolFunction", "PSROIPoolBatched", "PSROIPoolBatchedFunction",
-    "RFCN", "CorrelationTracker",
+    "TrackHeadFunction", "RFCN", "CorrelationTracker",
 ]

@@ -61,6 +61,10 @@ SIGNATURES = {
     "d2t_psroipool_bwd_batched_workspace_bytes": (_c_size_t, _WS7),
     "d2t_psroipool_fwd_batched_f32": (_c_int, _PSPOOL_B),
     "d2t_psroipool_bwd_batched_f32": (_c_int, _PSPOOL_B),
+    "d2t_trackhead_fwd_workspace_bytes": (_c_size_t, _WS6),
+    "d2t_trackhead_bwd_workspace_bytes": (_c_size_t, _WS6),
+    "d2t_trackhead_fwd_f32": (_c_int, [_P] * 5 + [_c_int] * 6 + [_P, _c_size_t, _P]),
+    "d2t_trackhead_bwd_f32": (_c_int, [_P] * 7 + [_c_int] * 6 + [_P, _c_size_t, _P]),
     "d2t_pool_bins_f32": (_c_int, [_P, _P] + [_c_int] * 5 + [_P]),
     "d2t_pool_bins_f64": (_c_int, [_P, _P] + [_c_int] * 5 + [_P]),
 }

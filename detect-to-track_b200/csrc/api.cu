@@ -108,6 +108,14 @@ int corr_tile_bwd_launch(const float*, const float*, const float*, float*, float
 int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
                               cudaStream_t);
 
+// fused track head (track_head.cu)
+size_t trackhead_fwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
+size_t trackhead_bwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
+int trackhead_fwd_launch(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*,
+                         size_t, cudaStream_t);
+int trackhead_bwd_launch(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int,
+                         int, void*, size_t, cudaStream_t);
+
 static int check_corr(const void* a, const void* b, const void* c, int B, int C, int H, int W, int d, int stride,
                       const char* who) {
     D2T_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, "%s: negative dimension (B=%d C=%d H=%d W=%d)", who, B, C, H, W);
@@ -300,6 +308,24 @@ int d2t_psroipool_bwd_batched_f32(const float* grad_out, const float* rois, floa
         if (rc) return rc;
     }
     return D2T_OK;
+}
+
+// ---- fused track head: ROIPool -> Linear ---------------------------------------------
+size_t d2t_trackhead_fwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int n_out) {
+    return trackhead_fwd_ws_bytes(R, C, H, W, r_hw, n_out);
+}
+size_t d2t_trackhead_bwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int n_out) {
+    return trackhead_bwd_ws_bytes(R, C, H, W, r_hw, n_out);
+}
+int d2t_trackhead_fwd_f32(const float* fm, const float* rois, const float* weight, const float* bias, float* out, int R, int C,
+                          int H, int W, int r_hw, int n_out, void* ws, size_t ws_bytes, void* stream) {
+    return trackhead_fwd_launch(fm, rois, weight, bias, out, R, C, H, W, r_hw, n_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d2t_trackhead_bwd_f32(const float* grad_out, const float* fm, const float* rois, const float* weight, float* grad_fm,
+                          float* grad_weight, float* grad_bias, int R, int C, int H, int W, int r_hw, int n_out, void* ws,
+                          size_t ws_bytes, void* stream) {
+    return trackhead_bwd_launch(grad_out, fm, rois, weight, grad_fm, grad_weight, grad_bias, R, C, H, W, r_hw, n_out, ws, ws_bytes,
+                                (cudaStream_t)stream);
 }
 
 // ---- bin edges -----------------------------------------------------------------------

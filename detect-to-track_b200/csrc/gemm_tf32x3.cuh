@@ -1,0 +1,32 @@
+// gemm_tf32x3.cuh -- internal interface of the TMA + tcgen05 3xTF32 GEMM (gemm_tf32x3.cu).
+#pragma once
+#include "common.cuh"
+
+namespace d2t {
+
+enum { GEMM_EPI_ROW = 0, GEMM_EPI_COL = 1 };
+
+// One K-major operand: rows x K FP32, K contiguous, row pitch `ld` floats (multiple of 4; base 16-byte aligned),
+// pre-split into hi = tf32_rn(v) and lo = v - hi planes of identical layout.
+struct GemmOperand {
+    const float* hi;
+    const float* lo;
+    int rows;
+    int ld;
+};
+
+struct GemmArgs {
+    int M, N, K;
+    int kblocks, splits;
+    int ldo, epilogue, slab_rows;
+};
+
+// out = A (M x K) * B^T (N x K).  splits > 1: split s writes its partial sum to the slab starting at row
+// s * slab_rows (ROW) / element s * slab_rows * ldo (COL).  bn: N tile (64, 208 or 256).
+int gemm_tf32x3(const GemmOperand& A, const GemmOperand& B, float* out, int M, int N, int K, int ldo, int epilogue, int splits,
+                int slab_rows, int bn, cudaStream_t st);
+
+// round-to-nearest split used by every producer of GEMM operands: hi keeps tf32's 10 explicit mantissa bits
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+}  // namespace d2t

@@ -1,0 +1,414 @@
+// track_head.cu -- the D&T track-regression head, ROIPool -> view -> Linear(C*k*k, n_out), as ONE fused operator
+// (forward + backward) that never materialises the pooled (R, C, k, k) tensor.  sm_100a.
+//
+// Reference composition (correlation_tracker.py:82-85):
+//     pooled = ROIPool(k)(track_feats, rois)            (R, C, k, k)   111 MB at C = 1891, R = 300, k = 7
+//     t_hat  = Linear(C*k*k, n_out)(pooled.view(R, -1))  (R, n_out)
+// Both steps are linear in track_feats and the pooling weights do not depend on the channel, so the contraction over
+// channels can be done FIRST, on the un-pooled map:
+//     Z[p, (o,ij)]   = sum_c X[c, p] * W[o, c*kk + ij]                      GEMM  P x (n_out*kk) x C      (forward 1)
+//     t_hat[r, o]    = b[o] + sum_ij (1/n_rij) sum_{p in bin_rij} Z[p,(o,ij)]   position-sensitive pooling of Z (forward 2)
+// and the backward is its transpose:
+//     gZ[p, (o,ij)]  = sum_r g[r, o] * [p in bin_rij] / n_rij                (a 196-channel, R-RoI scatter, done as a gather)
+//     gX[c, p]       = sum_(o,ij) gZ[p,(o,ij)] * W[o, c*kk + ij]             GEMM  P x C x (n_out*kk)
+//     gW[o, c*kk+ij] = sum_p gZ[p,(o,ij)] * X[c, p]                          GEMM  C x (n_out*kk) x P
+//     gb[o]          = sum_r g[r, o]
+// 1.77 GFLOP per GEMM at the BASELINE track-head size instead of 129 MB of HBM traffic per direction plus a
+// (300 x 92659) x (92659 x 4) library GEMM.  Bins, clamped RoI start and the empty-bin NaN (0/0) follow ROIPool
+// (roipool_cuda.cu:26-61): an empty bin makes every output of that RoI NaN, exactly like pooled -> Linear would.
+//
+// The GEMMs run on tcgen05 in 3xTF32 (gemm_tf32x3.cu) from K-major hi/lo planes written by the layout kernels below;
+// all reductions have a fixed order (split-K slabs summed ascending, RoI lists ascending): bitwise reproducible.
+#include "gemm_tf32x3.cuh"
+
+namespace d2t {
+
+namespace {
+
+constexpr int kThMaxN = 256;   // n_out * r_hw^2 must fit one UMMA N tile
+
+struct ThDims {
+    int R, C, H, W, k, nO;
+    int P, KK, N1;          // pixels, bins, n_out * bins
+    int ldc, ldp, ldn;      // pitches (floats, multiples of 4) of K = C, K = P and K = N1 operands / N1-wide outputs
+    int bn;                 // N tile for the N = N1 GEMMs
+    int s1, s3;             // split-K factors of forward GEMM / weight-gradient GEMM
+};
+
+static int th_dims(int R, int C, int H, int W, int k, int nO, ThDims* d) {
+    D2T_REQUIRE(R >= 0 && C > 0 && H > 0 && W > 0 && k > 0 && nO > 0, "trackhead: bad shape R=%d C=%d H=%d W=%d r_hw=%d n_out=%d", R,
+                C, H, W, k, nO);
+    D2T_REQUIRE(nO * k * k <= kThMaxN, "trackhead: n_out * r_hw^2 must be <= %d", kThMaxN);
+    D2T_REQUIRE(H < 32768 && W < 32768 && (long long)C * H * W < (1ll << 31), "trackhead: map too large");
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    d->R = R; d->C = C; d->H = H; d->W = W; d->k = k; d->nO = nO;
+    d->P = H * W; d->KK = k * k; d->N1 = nO * k * k;
+    d->ldc = (int)align_up(C, 4); d->ldp = (int)align_up(d->P, 4); d->ldn = (int)align_up(d->N1, 4);
+    d->bn = d->N1 <= 64 ? 64 : d->N1 <= 208 ? 208 : 256;
+    auto splits = [&](int tiles, int K) {
+        const int kb = ceil_div(K, 32);
+        int s = di.sm_count / (tiles > 0 ? tiles : 1);
+        if (s > kb) s = kb;
+        return s < 1 ? 1 : s;
+    };
+    d->s1 = splits(ceil_div(d->P, 128), C);
+    d->s3 = splits(ceil_div(C, 128), d->P);
+    return D2T_OK;
+}
+
+// workspace carving (all offsets multiples of 256 bytes)
+struct ThFwdWs {
+    float *xt_hi, *xt_lo, *wt_hi, *wt_lo, *zpart, *z;
+    size_t total;
+};
+static ThFwdWs th_fwd_ws(const ThDims& d, void* base) {
+    ThFwdWs w;
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+        off = align_up(off + floats * sizeof(float), 256);
+        return p;
+    };
+    w.xt_hi = take((size_t)d.P * d.ldc); w.xt_lo = take((size_t)d.P * d.ldc);
+    w.wt_hi = take((size_t)d.N1 * d.ldc); w.wt_lo = take((size_t)d.N1 * d.ldc);
+    w.zpart = take((size_t)d.s1 * d.P * d.ldn);
+    w.z = take((size_t)d.P * d.ldn);
+    w.total = off;
+    return w;
+}
+struct ThBwdWs {
+    float *gz_hi, *gz_lo, *gzt_hi, *gzt_lo, *xc_hi, *xc_lo, *wc_hi, *wc_lo, *gwpart;
+    size_t total;
+};
+static ThBwdWs th_bwd_ws(const ThDims& d, void* base) {
+    ThBwdWs w;
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+        off = align_up(off + floats * sizeof(float), 256);
+        return p;
+    };
+    w.gz_hi = take((size_t)d.P * d.ldn); w.gz_lo = take((size_t)d.P * d.ldn);
+    w.gzt_hi = take((size_t)d.N1 * d.ldp); w.gzt_lo = take((size_t)d.N1 * d.ldp);
+    w.xc_hi = take((size_t)d.C * d.ldp); w.xc_lo = take((size_t)d.C * d.ldp);
+    w.wc_hi = take((size_t)d.C * d.ldn); w.wc_lo = take((size_t)d.C * d.ldn);
+    w.gwpart = take((size_t)d.s3 * d.C * d.ldn);
+    w.total = off;
+    return w;
+}
+
+// ---- layout kernels ---------------------------------------------------------------------------------------------
+// X (C, P) -> XT hi / lo (P, ldc): 32 x 32 tiles through shared memory, both sides coalesced
+__global__ void __launch_bounds__(256)
+th_split_transpose_kernel(const float* __restrict__ x, float* __restrict__ thi, float* __restrict__ tlo, int C, int P, int ldc) {
+    __shared__ float tile[32][33];
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, p = p0 + tx;
+        tile[r][tx] = (c < C && p < P) ? __ldg(x + (size_t)c * P + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int p = p0 + r, c = c0 + tx;
+        if (p < P && c < C) {
+            const float v = tile[tx][r];
+            const float h = tf32_rn(v);
+            thi[(size_t)p * ldc + c] = h;
+            tlo[(size_t)p * ldc + c] = v - h;
+        }
+    }
+}
+
+// X (C, P) -> Xc hi / lo (C, ldp): same order, aligned pitch
+__global__ void __launch_bounds__(256)
+th_split_copy_kernel(const float* __restrict__ x, float* __restrict__ chi, float* __restrict__ clo, int C, int P, int ldp) {
+    const int c = blockIdx.y;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const float v = __ldg(x + (size_t)c * P + p);
+        const float h = tf32_rn(v);
+        chi[(size_t)c * ldp + p] = h;
+        clo[(size_t)c * ldp + p] = v - h;
+    }
+}
+
+// W (nO, C*KK) -> Wt hi / lo ((o,ij), ldc)  [K = c]   (transposed == 0)
+//              -> Wc hi / lo (c, ldn)       [K = (o,ij)]   (transposed == 1)
+__global__ void __launch_bounds__(256)
+th_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int C, int KK, int nO, int ld,
+                      int by_channel) {
+    const int total = nO * C * KK;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int o, c, ij;
+        size_t dst;
+        if (by_channel) {          // e = (c, o, ij): writes contiguous
+            c = e / (nO * KK);
+            const int n = e - c * (nO * KK);
+            o = n / KK; ij = n - o * KK;
+            dst = (size_t)c * ld + n;
+        } else {                   // e = (o, ij, c): writes contiguous
+            const int n = e / C;
+            c = e - n * C;
+            o = n / KK; ij = n - o * KK;
+            dst = (size_t)n * ld + c;
+        }
+        const float v = __ldg(w + (size_t)o * C * KK + (size_t)c * KK + ij);
+        const float h = tf32_rn(v);
+        hi[dst] = h;
+        lo[dst] = v - h;
+    }
+}
+
+// Z[p][n] = sum_s Zpart[s][p][n], ascending s
+__global__ void __launch_bounds__(256)
+th_reduce_slabs_kernel(const float4* __restrict__ part, float4* __restrict__ z, int n4, int splits) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += gridDim.x * blockDim.x) {
+        float4 s = part[e];
+        for (int k = 1; k < splits; ++k) {
+            const float4 v = part[(size_t)k * n4 + e];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        z[e] = s;
+    }
+}
+
+// ---- forward 2: position-sensitive pooling of Z over ROIPool bins ----------------------------------------------------
+// one CTA per RoI; thread n = (o, ij) sums Z[., n] over its bin rows-then-columns and divides by the bin size (0/0 = NaN
+// for an empty bin, like roipool_cuda.cu:61); thread o then adds the kk bin means of its output in ascending bin order.
+__global__ void __launch_bounds__(kThMaxN)
+th_pool_kernel(const float* __restrict__ z, const float* __restrict__ rois, const float* __restrict__ bias, float* __restrict__ out,
+               int H, int W, int k, int nO, int ldn) {
+    __shared__ float part[kThMaxN];
+    const int r = blockIdx.x, n = threadIdx.x, KK = k * k, N1 = nO * KK;
+    if (n < N1) {
+        const int ij = n % KK, i = ij / k, j = ij - i * k;
+        const float* roi = rois + (size_t)r * 4;
+        int i0, i1, j0, j1;
+        bin_edge<float, true>(roi[0], roi[2], i, k, H, i0, i1);
+        bin_edge<float, true>(roi[1], roi[3], j, k, W, j0, j1);
+        float acc = 0.f;
+        for (int pi = i0; pi < i1; ++pi)
+            for (int pj = j0; pj < j1; ++pj) acc += __ldg(z + (size_t)(pi * W + pj) * ldn + n);
+        const int numel = (i1 - i0) * (j1 - j0);
+        acc /= numel;
+        part[n] = acc;
+    }
+    __syncthreads();
+    if (n < nO) {
+        float s = bias ? bias[n] : 0.f;
+        for (int ij = 0; ij < KK; ++ij) s += part[n * KK + ij];
+        out[(size_t)r * nO + n] = s;
+    }
+}
+
+// ---- backward 1: gZ (both layouts, hi/lo) ------------------------------------------------------------------------------
+// one CTA per (pixel row y, bin row i).  Phase 1: every RoI's bin-row-i edges; warp 0 compacts, in ascending RoI order,
+// the RoIs whose bin row covers y.  Phase 2: column edges and scaled gradients g[r, o] / n_rij of the listed RoIs.
+// Phase 3: thread (x, j) adds, in list order, the entries whose column bin j covers x -- a gather: fixed order, no atomics.
+constexpr int kGzThreads = 256;
+constexpr int kGzMaxO = 8;
+__global__ void __launch_bounds__(kGzThreads)
+th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float* __restrict__ gz_hi, float* __restrict__ gz_lo,
+             float* __restrict__ gzt_hi, float* __restrict__ gzt_lo, int R, int H, int W, int k, int nO, int ldn, int ldp) {
+    extern __shared__ unsigned char th_smem[];
+    // list[R] (int) | rowext[R] (int: I1 - I0 or 0) | cj[R*k] (short2 J0, J1) | val[R*k*nO] (float)
+    int* list = reinterpret_cast<int*>(th_smem);
+    int* rowext = list + R;
+    short2* cj = reinterpret_cast<short2*>(rowext + R);
+    float* val = reinterpret_cast<float*>(cj + (size_t)R * k);
+    __shared__ int nlist;
+    const int y = blockIdx.x / k, i = blockIdx.x - y * k;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int KK = k * k;
+    for (int r = tid; r < R; r += kGzThreads) {
+        const float* roi = rois + (size_t)r * 4;
+        int i0, i1;
+        bin_edge<float, true>(roi[0], roi[2], i, k, H, i0, i1);
+        rowext[r] = (i0 <= y && y < i1) ? (i1 - i0) : 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int cnt = 0;
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            const int r = r0 + lane;
+            const bool in = r < R && rowext[r] > 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) list[cnt + __popc(bal & ((1u << lane) - 1))] = r;
+            cnt += __popc(bal);
+        }
+        if (lane == 0) nlist = cnt;
+    }
+    __syncthreads();
+    const int nl = nlist;
+    for (int e = tid; e < nl * k; e += kGzThreads) {
+        const int l = e / k, j = e - l * k;
+        const int r = list[l];
+        const float* roi = rois + (size_t)r * 4;
+        int j0, j1;
+        bin_edge<float, true>(roi[1], roi[3], j, k, W, j0, j1);
+        cj[e] = make_short2((short)j0, (short)j1);
+        const int numel = rowext[r] * (j1 - j0);
+        for (int o = 0; o < nO; ++o) val[(size_t)e * nO + o] = numel > 0 ? __ldg(g + (size_t)r * nO + o) / numel : 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < W * k; e += kGzThreads) {
+        const int j = e / W, x = e - j * W;   // x fastest: the transposed-layout stores are coalesced
+        float acc[kGzMaxO];
+#pragma unroll
+        for (int o = 0; o < kGzMaxO; ++o) acc[o] = 0.f;
+        for (int l = 0; l < nl; ++l) {
+            const short2 c = cj[l * k + j];
+            if (x >= c.x && x < c.y) {
+                const float* v = val + (size_t)(l * k + j) * nO;
+#pragma unroll
+                for (int o = 0; o < kGzMaxO; ++o)
+                    if (o < nO) acc[o] += v[o];
+            }
+        }
+        const int p = y * W + x;
+#pragma unroll
+        for (int o = 0; o < kGzMaxO; ++o) {
+            if (o < nO) {
+                const int n = o * KK + i * k + j;
+                const float h = tf32_rn(acc[o]), lo = acc[o] - h;
+                gz_hi[(size_t)p * ldn + n] = h;
+                gz_lo[(size_t)p * ldn + n] = lo;
+                gzt_hi[(size_t)n * ldp + p] = h;
+                gzt_lo[(size_t)n * ldp + p] = lo;
+            }
+        }
+    }
+}
+
+// ---- backward 3: gW[o][c*KK + ij] = sum_s gWpart[s][c][o*KK + ij];  gb[o] = sum_r g[r][o] -------------------------------
+__global__ void __launch_bounds__(256)
+th_reduce_w_kernel(const float* __restrict__ part, const float* __restrict__ g, float* __restrict__ gw, float* __restrict__ gb,
+                   int R, int C, int KK, int nO, int ldn, int splits) {
+    const int N1 = nO * KK;
+    const size_t slab = (size_t)C * ldn;
+    if (gw) {
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < C * N1; e += gridDim.x * blockDim.x) {
+            const int c = e / N1, n = e - c * N1;
+            const int o = n / KK, ij = n - o * KK;
+            float s = 0.f;
+            for (int k = 0; k < splits; ++k) s += part[(size_t)k * slab + (size_t)c * ldn + n];
+            gw[(size_t)o * C * KK + (size_t)c * KK + ij] = s;
+        }
+    }
+    if (gb && blockIdx.x == 0 && threadIdx.x < nO) {
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) s += g[(size_t)r * nO + threadIdx.x];
+        gb[threadIdx.x] = s;
+    }
+}
+
+static int grid_for(size_t n, int block, int cap) {
+    size_t g = (n + block - 1) / block;
+    if (g > (size_t)cap) g = cap;
+    return g < 1 ? 1 : (int)g;
+}
+
+}  // namespace
+
+size_t trackhead_fwd_ws_bytes(int R, int C, int H, int W, int k, int nO) {
+    ThDims d;
+    if (th_dims(R, C, H, W, k, nO, &d)) return 0;
+    return th_fwd_ws(d, nullptr).total;
+}
+size_t trackhead_bwd_ws_bytes(int R, int C, int H, int W, int k, int nO) {
+    ThDims d;
+    if (th_dims(R, C, H, W, k, nO, &d)) return 0;
+    return th_bwd_ws(d, nullptr).total;
+}
+
+int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight, const float* bias, float* out, int R, int C,
+                         int H, int W, int k, int nO, void* wsp, size_t ws_bytes, cudaStream_t st) {
+    ThDims d;
+    int rc = th_dims(R, C, H, W, k, nO, &d);
+    if (rc) return rc;
+    if (R == 0) return D2T_OK;
+    D2T_REQUIRE(fm && rois && weight && out, "trackhead_fwd: null pointer");
+    const ThFwdWs w = th_fwd_ws(d, wsp);
+    if (wsp == nullptr || ws_bytes < w.total) {
+        set_error("trackhead_fwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
+        return D2T_ERR_WORKSPACE;
+    }
+    DeviceInfo di;
+    if ((rc = device_info(&di))) return rc;
+    const int cap = di.sm_count * 8;
+    th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wt_hi, w.wt_lo, C, d.KK, nO, d.ldc, 0);
+    D2T_CUDA_TRY(cudaGetLastError());
+    th_split_transpose_kernel<<<dim3(ceil_div(d.P, 32), ceil_div(C, 32)), 256, 0, st>>>(fm, w.xt_hi, w.xt_lo, C, d.P, d.ldc);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch(2);
+    GemmOperand A{w.xt_hi, w.xt_lo, d.P, d.ldc}, B{w.wt_hi, w.wt_lo, d.N1, d.ldc};
+    if ((rc = gemm_tf32x3(A, B, w.zpart, d.P, d.N1, C, d.ldn, GEMM_EPI_ROW, d.s1, d.P, d.bn, st))) return rc;
+    const float* z = w.zpart;
+    if (d.s1 > 1) {
+        const int n4 = d.P * d.ldn / 4;
+        th_reduce_slabs_kernel<<<grid_for(n4, 256, cap), 256, 0, st>>>(reinterpret_cast<const float4*>(w.zpart),
+                                                                       reinterpret_cast<float4*>(w.z), n4, d.s1);
+        D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
+        z = w.z;
+    }
+    th_pool_kernel<<<R, kThMaxN, 0, st>>>(z, rois, bias, out, H, W, k, nO, d.ldn);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
+int trackhead_bwd_launch(const float* go, const float* fm, const float* rois, const float* weight, float* gfm, float* gw, float* gb,
+                         int R, int C, int H, int W, int k, int nO, void* wsp, size_t ws_bytes, cudaStream_t st) {
+    ThDims d;
+    int rc = th_dims(R, C, H, W, k, nO, &d);
+    if (rc) return rc;
+    D2T_REQUIRE(nO <= kGzMaxO, "trackhead_bwd: n_out must be <= %d", kGzMaxO);
+    DeviceInfo di;
+    if ((rc = device_info(&di))) return rc;
+    const int cap = di.sm_count * 8;
+    if (R == 0) {   // no RoIs: every gradient is zero
+        if (gfm) D2T_CUDA_TRY(cudaMemsetAsync(gfm, 0, (size_t)C * d.P * sizeof(float), st));
+        if (gw) D2T_CUDA_TRY(cudaMemsetAsync(gw, 0, (size_t)nO * C * d.KK * sizeof(float), st));
+        if (gb) D2T_CUDA_TRY(cudaMemsetAsync(gb, 0, (size_t)nO * sizeof(float), st));
+        return D2T_OK;
+    }
+    D2T_REQUIRE(go && fm && rois && weight, "trackhead_bwd: null pointer");
+    const ThBwdWs w = th_bwd_ws(d, wsp);
+    if (wsp == nullptr || ws_bytes < w.total) {
+        set_error("trackhead_bwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
+        return D2T_ERR_WORKSPACE;
+    }
+    const size_t gzSmem = (size_t)R * 8 + (size_t)R * k * 4 + (size_t)R * k * nO * 4;
+    D2T_REQUIRE(gzSmem <= (size_t)di.max_smem_optin - 1024, "trackhead_bwd: too many RoIs for one call (%d)", R);
+    D2T_SMEM_OPTIN(th_gz_kernel, gzSmem);
+    th_gz_kernel<<<H * k, kGzThreads, gzSmem, st>>>(go, rois, w.gz_hi, w.gz_lo, w.gzt_hi, w.gzt_lo, R, H, W, k, nO, d.ldn, d.ldp);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    if (gfm) {
+        th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wc_hi, w.wc_lo, C, d.KK, nO, d.ldn, 1);
+        D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
+        GemmOperand A{w.gz_hi, w.gz_lo, d.P, d.ldn}, B{w.wc_hi, w.wc_lo, C, d.ldn};
+        if ((rc = gemm_tf32x3(A, B, gfm, d.P, C, d.N1, d.P, GEMM_EPI_COL, 1, 0, 256, st))) return rc;
+    }
+    if (gw) {
+        th_split_copy_kernel<<<dim3(ceil_div(d.P, 1024), C), 256, 0, st>>>(fm, w.xc_hi, w.xc_lo, C, d.P, d.ldp);
+        D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
+        GemmOperand A{w.xc_hi, w.xc_lo, C, d.ldp}, B{w.gzt_hi, w.gzt_lo, d.N1, d.ldp};
+        if ((rc = gemm_tf32x3(A, B, w.gwpart, C, d.N1, d.P, d.ldn, GEMM_EPI_ROW, d.s3, C, d.bn, st))) return rc;
+    }
+    if (gw || gb) {
+        th_reduce_w_kernel<<<grid_for((size_t)C * d.N1, 256, cap), 256, 0, st>>>(w.gwpart, go, gw, gb, R, C, d.KK, nO, d.ldn, d.s3);
+        D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
+    }
+    return D2T_OK;
+}
+
+}  // namespace d2t

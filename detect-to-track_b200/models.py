@@ -15,6 +15,7 @@ from torch import Tensor, nn
 from .pointwise_correlation import PointwiseCorrelation
 from .ps_roipool import PSROIPool
 from .roipool import ROIPool
+from .track_head import TrackHeadFunction
 
 
 class _RFCNHead(nn.Module):
@@ -57,7 +58,8 @@ class RFCN(nn.Module):
 
 
 class CorrelationTracker(nn.Module):
-    """correlation tracker (correlation_tracker.py:13-87)."""
+    """correlation tracker (correlation_tracker.py:13-87).  `fused=True` (extension, default off) replaces
+    pool -> view -> reg_fc by the fused track head; parameters and state_dict are unchanged."""
 
     def __init__(self, d_max: int, r_hw: int, reg_channels: int, stride: int = 1, fused: bool = False) -> None:
         super().__init__()
@@ -82,6 +84,8 @@ class CorrelationTracker(nn.Module):
     def forward(self, fm_pyr_0, fm_pyr_1, reg_fm_0: Tensor, reg_fm_1: Tensor, rois: Tensor) -> Tensor:
         corr_feats = self.correlation_features(fm_pyr_0, fm_pyr_1)
         track_feats = torch.cat([reg_fm_0, reg_fm_1, *corr_feats])
+        if self.fused:  # ROIPool -> view -> Linear as one operator; same parameters, same result (track_head.py)
+            return TrackHeadFunction.apply(track_feats, rois, self.reg_fc.weight, self.reg_fc.bias, self.pool.r_hw)
         pooled_feats = self.pool(track_feats, rois)
         pooled_feats = pooled_feats.view(pooled_feats.size(0), self.fc_channels)
         return self.reg_fc(pooled_feats)

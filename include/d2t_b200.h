@@ -169,6 +169,26 @@ D2T_API size_t d2t_psroipool_bwd_batched_workspace_bytes(int N, int R, int n_tar
 D2T_API int d2t_psroipool_bwd_batched_f32(const float* grad_out, const float* rois, float* grad_fm, int N, int R,
                           int n_targets, int H, int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Fused track head: ROIPool -> view -> Linear (float32) -----------------------
+ * Extension beside the API-parity ops: the reference's track-regression head (correlation_tracker.py:82-85)
+ *     t_hat = Linear(C*r_hw^2, n_out)( ROIPool(r_hw)(fm, rois).view(R, -1) )
+ * computed without materialising the pooled (R, C, r_hw, r_hw) tensor (111 MB at the D&T size): the channel
+ * contraction runs first, on the un-pooled map, as a tcgen05 3xTF32 GEMM fed by TMA, followed by a position-
+ * sensitive pooling of its n_out*r_hw^2-channel result; the backward is the transpose (csrc/track_head.cu).
+ *   fm : (C, H, W);  rois : (R, 4);  weight : (n_out, C*r_hw^2) row-major as torch.nn.Linear;  bias : (n_out) or NULL
+ *   out / grad_out : (R, n_out);  grad_fm : (C, H, W);  grad_weight : like weight;  grad_bias : (n_out)
+ * Any of grad_fm / grad_weight / grad_bias may be NULL (not computed).  Requires n_out * r_hw^2 <= 256, n_out <= 8.
+ * Same bins, clamped RoI start and empty-bin NaN as d2t_roipool_fwd_f32; values agree with the composition to FP32
+ * rounding (3xTF32: |err| <= 2e-6 * sum |a||b| per contraction).  Bitwise reproducible.
+ */
+D2T_API size_t d2t_trackhead_fwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int n_out);
+D2T_API int d2t_trackhead_fwd_f32(const float* fm, const float* rois, const float* weight, const float* bias, float* out,
+                          int R, int C, int H, int W, int r_hw, int n_out, void* ws, size_t ws_bytes, void* stream);
+D2T_API size_t d2t_trackhead_bwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int n_out);
+D2T_API int d2t_trackhead_bwd_f32(const float* grad_out, const float* fm, const float* rois, const float* weight,
+                          float* grad_fm, float* grad_weight, float* grad_bias, int R, int C, int H, int W, int r_hw,
+                          int n_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- integer bin edges (parity instrumentation) ----------------------------
  * edges : (R, r_hw, 4) int32 = (I0, I1, J0, J1) of row-bin / column-bin b,
  * computed on the device by the same code the pooling kernels use.

@@ -63,7 +63,7 @@ def test_rfcn_matches_the_reference_wiring(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fused", [False])
+@pytest.mark.parametrize("fused", [False, True])
 def test_correlation_tracker_matches_the_reference_wiring(cuda, fused):
     import make_golden_models as mg
     import detect_to_track_b200 as d2t

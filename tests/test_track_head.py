@@ -1,0 +1,116 @@
+"""GPU parity tests of the fused track head (ROIPool -> view -> Linear, csrc/track_head.cu + gemm_tf32x3.cu) against the
+reference COMPOSITION: the API-parity ROIPool (bit-identical `exact` kernel; at full size also the reference's own CUDA
+kernel, oracle/_ref) followed by the Linear layer evaluated in float64.  Tolerance as for every float32 op: rtol 1e-4,
+atol 1e-5 * max|ref| (the GEMMs are 3xTF32 on tcgen05, stated |err| <= 2e-6 * sum|a||b|)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import ref_cuda
+from detect_to_track_b200 import roipool as rp_mod, track_head as th
+
+pytestmark = pytest.mark.gpu
+
+
+def close(got, want, what):
+    got, want = got.detach().double().cpu().numpy(), want.detach().double().cpu().numpy()
+    scale = float(np.nanmax(np.abs(want))) or 1.0
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * scale, equal_nan=True, err_msg=what)
+
+
+def composition(fm, rois, weight, bias, k, go, pooled=None):
+    """reference composition with the Linear layer in float64; returns t_hat, grad_fm, grad_weight, grad_bias"""
+    R, C = rois.size(0), fm.size(0)
+    if pooled is None:
+        pooled = rp_mod.roipool_forward(fm, rois, k, exact=True)
+    flat = pooled.view(R, -1).double()
+    t_hat = flat @ weight.double().t() + bias.double()
+    g_pooled = (go.double() @ weight.double()).float().view(R, C, k, k).contiguous()
+    g_fm = rp_mod.roipool_backward(g_pooled, rois, fm.size(1), fm.size(2))
+    g_w = go.double().t() @ torch.nan_to_num(flat, nan=0.0)
+    return t_hat, g_fm, g_w, go.double().sum(0)
+
+
+def inside(rois):
+    half = rois[:, 2:] / 2
+    rois[:, :2] = np.minimum(np.maximum(rois[:, :2], half), 1.0 - half)
+    return rois
+
+
+@pytest.mark.parametrize("C,H,W,R,k,n_out", [(37, 20, 21, 40, 7, 4), (130, 38, 63, 77, 7, 4), (8, 9, 10, 5, 3, 2),
+                                             (300, 12, 70, 33, 5, 8), (1, 1, 1, 2, 7, 4)])
+def test_track_head_matches_the_composition(cuda, C, H, W, R, k, n_out):
+    g = torch.Generator(device="cpu").manual_seed(1000 + C)
+    fm = torch.randn(C, H, W, generator=g).to(cuda)
+    rois = torch.from_numpy(inside(cases.rois_random(R, 77))).to(cuda)
+    weight = (torch.randn(n_out, C * k * k, generator=g) / (C * k * k) ** 0.5).to(cuda)
+    bias = torch.randn(n_out, generator=g).to(cuda)
+    go = torch.randn(R, n_out, generator=g).to(cuda)
+    want = composition(fm, rois, weight, bias, k, go)
+    out = th.track_head_forward(fm, rois, weight, bias, k)
+    close(out, want[0], "t_hat")
+    got = th.track_head_backward(go, fm, rois, weight, k)
+    for a, b, nm in zip(got, want[1:], ("grad_fm", "grad_weight", "grad_bias")):
+        close(a, b, nm)
+    again = th.track_head_backward(go, fm, rois, weight, k)
+    assert torch.equal(out, th.track_head_forward(fm, rois, weight, bias, k))
+    assert all(torch.equal(a, b) for a, b in zip(got, again))          # bitwise reproducible
+
+
+def test_track_head_full_size_vs_reference_kernels(cuda):
+    """BASELINE config 4 (C = 1891, 38x63, 300 RoIs, k = 7, Linear(92659, 4)): the fused head against the reference's own
+    ROIPool kernels (oracle/_ref) + float64 Linear, on the WHOLE tensors, including RoIs with empty bins (NaN rows)."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    C, H, W, R, k, n_out = 1891, 38, 63, 300, 7, 4
+    g = torch.Generator(device="cpu").manual_seed(1238)
+    fm = torch.randn(C, H, W, generator=g).to(cuda)
+    rois = torch.from_numpy(cases.rois_random(R, 1238)).to(cuda)
+    weight = (torch.randn(n_out, C * k * k, generator=g) / (C * k * k) ** 0.5).to(cuda)
+    bias = torch.randn(n_out, generator=g).to(cuda)
+    go = torch.randn(R, n_out, generator=g).to(cuda)
+    pooled = ref_cuda.roipool_fwd(fm, rois, k)
+    flat = pooled.view(R, -1).double()
+    want = flat @ weight.double().t() + bias.double()
+    out = th.track_head_forward(fm, rois, weight, bias, k)
+    assert 0 < int(torch.isnan(want).any(1).sum()) < R                 # some RoIs cross the border: empty bins -> NaN (F7)
+    assert torch.equal(torch.isnan(out), torch.isnan(want))
+    close(out, want, "t_hat")
+    g_pooled = (go.double() @ weight.double()).float().view(R, C, k, k).contiguous()
+    want_fm = ref_cuda.roipool_bwd(g_pooled, rois, H, W)
+    g_fm, g_w, g_b = th.track_head_backward(go, fm, rois, weight, k)
+    close(g_fm, want_fm, "grad_fm")
+    close(g_w, go.double().t() @ torch.nan_to_num(flat, nan=0.0), "grad_weight")   # empty bins carry no gradient
+    close(g_b, go.double().sum(0), "grad_bias")
+
+
+def test_track_head_autograd_and_optional_grads(cuda):
+    C, H, W, R, k, n_out = 21, 14, 15, 12, 7, 4
+    g = torch.Generator(device="cpu").manual_seed(5)
+    fm = torch.randn(C, H, W, generator=g).to(cuda).requires_grad_(True)
+    rois = torch.from_numpy(inside(cases.rois_random(R, 78))).to(cuda)
+    lin = torch.nn.Linear(C * k * k, n_out).to(cuda)
+    out = th.TrackHeadFunction.apply(fm, rois, lin.weight, lin.bias, k)
+    wt = torch.randn(out.shape, generator=g).to(cuda)
+    (out * wt).sum().backward()
+    fm2 = fm.detach().clone().requires_grad_(True)
+    lin2 = torch.nn.Linear(C * k * k, n_out).to(cuda)
+    lin2.load_state_dict(lin.state_dict())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = lin2(rp_mod.ROIPoolFunction.apply(fm2, rois, k).view(R, -1))
+    (ref * wt).sum().backward()
+    close(out, ref, "t_hat")
+    close(fm.grad, fm2.grad, "grad_fm")
+    close(lin.weight.grad, lin2.weight.grad, "grad_weight")
+    close(lin.bias.grad, lin2.bias.grad, "grad_bias")
+    # no bias, frozen weights: only grad_fm is computed
+    fm3 = fm.detach().clone().requires_grad_(True)
+    o3 = th.TrackHeadFunction.apply(fm3, rois, lin.weight.detach(), None, k)
+    o3.sum().backward()
+    assert fm3.grad is not None
+    # no RoIs
+    empty = torch.zeros(0, 4, device=cuda)
+    assert tuple(th.track_head_forward(fm.detach(), empty, lin.weight.detach(), None, k).shape) == (0, n_out)
+    gz = th.track_head_backward(torch.zeros(0, n_out, device=cuda), fm.detach(), empty, lin.weight.detach(), k)
+    assert all(not bool(t.any()) for t in gz)

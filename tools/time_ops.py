@@ -105,6 +105,26 @@ def main():
             report("  REF roipool fwd", timeit(lambda: ref.roipool_fwd(fm, rois, k), 4, flush), None, nb)
             report("  REF roipool bwd", timeit(lambda: ref.roipool_bwd(go, rois, H, W), 4, flush), None, nb)
 
+    if not args.only or "trackhead" in args.only:
+        from detect_to_track_b200 import track_head as th
+        C, H, W, k, R, n_out = 1891, 38, 63, 7, 300, 4
+        rois = torch.from_numpy(cases.rois_random(R, 1238)).to(dev)
+        fm = torch.randn(C, H, W, generator=g).to(dev)
+        weight = (torch.randn(n_out, C * k * k, generator=g) / 300).to(dev)
+        bias = torch.zeros(n_out, device=dev)
+        go = torch.randn(R, n_out, generator=g).to(dev)
+        report("trackhead fused fwd C=1891 R=300", timeit(lambda: th.track_head_forward(fm, rois, weight, bias, k), args.iters, flush))
+        report("trackhead fused bwd (fm+W+b grads)", timeit(lambda: th.track_head_backward(go, fm, rois, weight, k), args.iters, flush))
+        report("trackhead fused bwd (fm grad only)", timeit(lambda: th.track_head_backward(go, fm, rois, weight, k, True, False, False), args.iters, flush))
+        lin = torch.nn.Linear(C * k * k, n_out).to(dev)
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+        def unfused():
+            x = fm.detach().requires_grad_(True)
+            o = lin(rp.ROIPoolFunction.apply(x, rois, k).view(R, -1))
+            o.backward(go)
+        report("trackhead UNFUSED fwd+bwd (ROIPool+Linear, autograd)", timeit(unfused, max(3, args.iters // 2), flush))
+
     if not args.only or "psroi" in args.only:
         H, W, k, R = 38, 63, 7, 300
         rois = torch.from_numpy(cases.rois_random(R, 1237)).to(dev)
