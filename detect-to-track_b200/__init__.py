@@ -6,7 +6,7 @@ identical Module / Function names, constructor and forward signatures, output
 layouts and numerical quirks.  Kernels: csrc/*.cu behind the C ABI of
 include/d2t_b200.h.  No Triton, no CPU fallback.
 """
-from .pointwise_correlation import PointwiseCorrelation, PointwiseCorrelationFunction
+from .pointwise_correlation import PointwiseCorrelation, PointwiseCorrelationFunction, TrackFeaturesFunction
 from .roipool import ROIPool, ROIPoolFunction
 from .ps_roipool import PSROIPool, PSROIPoolFunction, PSROIPoolBatched, PSROIPoolBatchedFunction
 from .track_head import TrackHeadFunction
@@ -16,5 +16,5 @@ __all__ = [
     "PointwiseCorrelation", "PointwiseCorrelationFunction",
     "ROIPool", "ROIPoolFunction",
     "PSROIPool", "PSROIPoolFunction", "PSROIPoolBatched", "PSROIPoolBatchedFunction",
-    "TrackHeadFunction", "RFCN", "CorrelationTracker",
+    "TrackHeadFunction", "TrackFeaturesFunction", "RFCN", "CorrelationTracker",
 ]

@@ -73,7 +73,7 @@ int ensure_dyn_smem(const void* func, size_t bytes) {
 
 // launchers implemented in the other translation units
 template <typename T>
-int corr_fwd_generic_launch(const T*, const T*, T*, int, int, int, int, int, int, cudaStream_t);
+int corr_fwd_generic_launch(const T*, const T*, T*, int, int, int, int, int, int, CorrOutStrides, cudaStream_t);
 template <typename T>
 int corr_bwd_generic_launch(const T*, const T*, const T*, T*, T*, int, int, int, int, int, int, cudaStream_t);
 template <typename T>
@@ -102,7 +102,8 @@ bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
 bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride);
 size_t corr_tile_fwd_ws_bytes(int B, int C, int H, int W, int d);
 size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d);
-int corr_tile_fwd_launch(const float*, const float*, float*, int, int, int, int, int, void*, size_t, cudaStream_t);
+int corr_tile_fwd_launch(const float*, const float*, float*, int, int, int, int, int, const CorrOutStrides*, void*, size_t,
+                         cudaStream_t);
 int corr_tile_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int, void*,
                          size_t, cudaStream_t);
 int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
@@ -146,13 +147,22 @@ size_t d2t_corr_bwd_workspace_bytes(int B, int C, int H, int W, int d_max, int s
     return 0;
 }
 
-int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
-                     void* ws, size_t ws_bytes, void* stream) {
-    int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, "d2t_corr_fwd_f32");
+static CorrOutStrides dense_strides(int H, int W, int d) {
+    const long long kk = (long long)(2 * d + 1) * (2 * d + 1);
+    return CorrOutStrides{(long long)H * W * kk, kk, 1};
+}
+static int corr_fwd_f32_any(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
+                            CorrOutStrides os, void* ws, size_t ws_bytes, void* stream, const char* who) {
+    int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, who);
     if (rc) return rc;
     if (corr_tile_supported(B, C, H, W, d_max, stride))
-        return corr_tile_fwd_launch(fm0, fm1, out, B, C, H, W, d_max, ws, ws_bytes, (cudaStream_t)stream);
-    return corr_fwd_generic_launch<float>(fm0, fm1, out, B, C, H, W, d_max, stride, (cudaStream_t)stream);
+        return corr_tile_fwd_launch(fm0, fm1, out, B, C, H, W, d_max, &os, ws, ws_bytes, (cudaStream_t)stream);
+    return corr_fwd_generic_launch<float>(fm0, fm1, out, B, C, H, W, d_max, stride, os, (cudaStream_t)stream);
+}
+int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
+                     void* ws, size_t ws_bytes, void* stream) {
+    return corr_fwd_f32_any(fm0, fm1, out, B, C, H, W, d_max, stride, dense_strides(H, W, d_max), ws, ws_bytes, stream,
+                            "d2t_corr_fwd_f32");
 }
 int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
                      int stride, void* ws, size_t ws_bytes, void* stream) {
@@ -160,7 +170,27 @@ int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, i
     (void)ws_bytes;
     int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, "d2t_corr_fwd_f64");
     if (rc) return rc;
-    return corr_fwd_generic_launch<double>(fm0, fm1, out, B, C, H, W, d_max, stride, (cudaStream_t)stream);
+    return corr_fwd_generic_launch<double>(fm0, fm1, out, B, C, H, W, d_max, stride, dense_strides(H, W, d_max),
+                                           (cudaStream_t)stream);
+}
+// strided output: element (b, pos, t) goes to out[b*batch_stride + pos*pos_stride + t*disp_stride] (elements)
+int d2t_corr_fwd_strided_f32(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
+                             long long batch_stride, long long pos_stride, long long disp_stride, void* ws, size_t ws_bytes,
+                             void* stream) {
+    D2T_REQUIRE(pos_stride > 0 && disp_stride > 0 && batch_stride >= 0, "d2t_corr_fwd_strided_f32: strides must be positive");
+    return corr_fwd_f32_any(fm0, fm1, out, B, C, H, W, d_max, stride, CorrOutStrides{batch_stride, pos_stride, disp_stride}, ws,
+                            ws_bytes, stream, "d2t_corr_fwd_strided_f32");
+}
+int d2t_corr_fwd_strided_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max, int stride,
+                             long long batch_stride, long long pos_stride, long long disp_stride, void* ws, size_t ws_bytes,
+                             void* stream) {
+    (void)ws;
+    (void)ws_bytes;
+    D2T_REQUIRE(pos_stride > 0 && disp_stride > 0 && batch_stride >= 0, "d2t_corr_fwd_strided_f64: strides must be positive");
+    int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, "d2t_corr_fwd_strided_f64");
+    if (rc) return rc;
+    return corr_fwd_generic_launch<double>(fm0, fm1, out, B, C, H, W, d_max, stride,
+                                           CorrOutStrides{batch_stride, pos_stride, disp_stride}, (cudaStream_t)stream);
 }
 int d2t_corr_bwd_f32(const float* grad_out, const float* fm0, const float* fm1, float* grad_fm0, float* grad_fm1, int B,
                      int C, int H, int W, int d_max, int stride, void* ws, size_t ws_bytes, void* stream) {

@@ -75,6 +75,14 @@ __device__ __forceinline__ void bin_edge(T r, T len, int b, int k, int n, int& e
     e1 = static_cast<int>(ceil(clamp01(centre + binLen / 2) * n));
 }
 
+// ---- correlation output addressing ----------------------------------------------------------------------------
+// element (b, pos = i*W + j, t = ci*(2d+1) + cj) of the correlation output lives at out[b*sb + pos*sp + t*st].
+// The reference layout (B, H, W, 2d+1, 2d+1) is {H*W*kk, kk, 1}; {*, 1, H*W} is the channel-major ((2d+1)^2, H, W) map
+// the tracker concatenates (correlation_tracker.py:64-80), written in place by d2t_corr_fwd_strided_*.
+struct CorrOutStrides {
+    long long sb, sp, st;
+};
+
 // ---- correlation liveness -----------------------------------
 // key index p is sampled from query index i iff
 //   lo <= p < min(i+d, n)  and  (p - lo) % stride == 0   with lo = max(0, i-d)

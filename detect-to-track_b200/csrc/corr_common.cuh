@@ -37,7 +37,8 @@ struct CorrPlan {
     // forward: `rounds` whole tiles per CTA (tile = round * G + cta, all CTAs walk the channels in step, so the halos
     // that neighbouring tiles share are fetched from L2, not HBM), then the `left` remaining tiles stream-K split
     int rounds, left, ipcL;
-    int dbg;                // experiment switches (0 in production)
+    int dbg;                // backward: chunks per channel group
+    CorrOutStrides os;      // forward: output addressing (see common.cuh)
 };
 
 template <int D>
@@ -47,6 +48,7 @@ static inline int make_plan(int B, int C, int H, int W, int CK, CorrPlan* p) {
     int rc = device_info(&di);
     if (rc) return rc;
     p->B = B; p->C = C; p->H = H; p->W = W; p->dbg = 0;
+    p->os.sb = (long long)H * W * Cfg::KK; p->os.sp = Cfg::KK; p->os.st = 1;
     p->tilesX = ceil_div(W, Cfg::QCOLS);
     p->tilesY = ceil_div(H, Cfg::QROWS);
     p->T = B * p->tilesX * p->tilesY;

@@ -15,7 +15,7 @@ constexpr int kThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 corr_fwd_generic_kernel(const T* __restrict__ fm0, const T* __restrict__ fm1, T* __restrict__ out, int B, int C,
-                        int H, int W, int d, int stride) {
+                        int H, int W, int d, int stride, CorrOutStrides os) {
     const int k = 2 * d + 1;
     const long long total = (long long)B * H * W * k * k;
     const size_t plane = (size_t)H * W;
@@ -36,7 +36,7 @@ corr_fwd_generic_kernel(const T* __restrict__ fm0, const T* __restrict__ fm1, T*
             const T* key = fm1 + (size_t)b * C * plane + (size_t)di * W + dj;
             for (int c = 0; c < C; ++c) acc += __ldg(q + c * plane) * __ldg(key + c * plane);
         }
-        out[idx] = acc;
+        out[(long long)b * os.sb + ((long long)i * W + j) * os.sp + (long long)(ci * k + cj) * os.st] = acc;
     }
 }
 
@@ -92,7 +92,7 @@ corr_bwd_generic_kernel(const T* __restrict__ go, const T* __restrict__ fm0, con
 
 template <typename T>
 int corr_fwd_generic_launch(const T* fm0, const T* fm1, T* out, int B, int C, int H, int W, int d, int stride,
-                            cudaStream_t st) {
+                            CorrOutStrides os, cudaStream_t st) {
     const long long total = (long long)B * H * W * (2 * d + 1) * (2 * d + 1);
     if (total == 0) return D2T_OK;
     DeviceInfo di;
@@ -101,7 +101,7 @@ int corr_fwd_generic_launch(const T* fm0, const T* fm1, T* out, int B, int C, in
     long long blocks = (total + kThreads - 1) / kThreads;
     const long long cap = (long long)di.sm_count * 32;
     if (blocks > cap) blocks = cap;
-    corr_fwd_generic_kernel<T><<<(int)blocks, kThreads, 0, st>>>(fm0, fm1, out, B, C, H, W, d, stride);
+    corr_fwd_generic_kernel<T><<<(int)blocks, kThreads, 0, st>>>(fm0, fm1, out, B, C, H, W, d, stride, os);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;
@@ -125,9 +125,9 @@ int corr_bwd_generic_launch(const T* go, const T* fm0, const T* fm1, T* g0, T* g
 }
 
 template int corr_fwd_generic_launch<float>(const float*, const float*, float*, int, int, int, int, int, int,
-                                            cudaStream_t);
+                                            CorrOutStrides, cudaStream_t);
 template int corr_fwd_generic_launch<double>(const double*, const double*, double*, int, int, int, int, int, int,
-                                             cudaStream_t);
+                                             CorrOutStrides, cudaStream_t);
 template int corr_bwd_generic_launch<float>(const float*, const float*, const float*, float*, float*, int, int, int, int,
                                             int, int, cudaStream_t);
 template int corr_bwd_generic_launch<double>(const double*, const double*, const double*, double*, double*, int, int,

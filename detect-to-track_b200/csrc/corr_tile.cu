@@ -264,15 +264,28 @@ corr_fwd_tile_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         __syncthreads();
 
         const bool whole = (chunkBeg == 0 && chunkEnd == p.NI);
-        if (whole) {
+        const bool dense = (p.os.st == 1 && p.os.sp == KK);   // the reference layout: a tile row is one contiguous run
+        if (whole && dense) {
             const int ncols = min(Cfg::QCOLS, W - j0);
             const int run = ncols * KK;
 #pragma unroll 1
             for (int r = 0; r < Cfg::QROWS; ++r) {
                 if (i0 + r >= H) break;
-                float* dst = out + (((size_t)b * H + (i0 + r)) * W + j0) * KK;
+                float* dst = out + (size_t)b * p.os.sb + ((size_t)(i0 + r) * W + j0) * KK;
                 const float* src = tileS + r * Cfg::QCOLS * KK;
                 for (int e = tid; e < run; e += kCorrThreads) dst[e] = src[e];
+            }
+        } else if (whole) {
+            // strided output (e.g. channel-major into the tracker's concatenated map): column fastest, so a warp writes
+            // two 16-pixel runs and reads tileS at bank (col + t) % 32 (KK = 1 mod 32): conflict-free
+            const int ncols = min(Cfg::QCOLS, W - j0), nrows = min(Cfg::QROWS, H - i0);
+            float* base = out + (size_t)b * p.os.sb;
+            for (int e = tid; e < KK * nrows * Cfg::QCOLS; e += kCorrThreads) {
+                const int col = e % Cfg::QCOLS, rt = e / Cfg::QCOLS;
+                const int rr = rt % nrows, t = rt / nrows;
+                if (col < ncols)
+                    base[((long long)(i0 + rr) * W + j0 + col) * p.os.sp + (long long)t * p.os.st] =
+                        tileS[(rr * Cfg::QCOLS + col) * KK + t];
             }
         } else {
             // fixed slot per (cta, left-over tile): slot = cta + lt (unique because lt is monotone in cta)
@@ -301,14 +314,26 @@ corr_fwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ 
     const int j0 = (trem % p.tilesX) * Cfg::QCOLS;
     const int ncols = min(Cfg::QCOLS, p.W - j0);
     const int run = ncols * KK;
+    const bool dense = (p.os.st == 1 && p.os.sp == KK);
     for (int r = blockIdx.y; r < Cfg::QROWS; r += gridDim.y) {
         if (i0 + r >= p.H) break;
-        float* dst = out + (((size_t)b * p.H + (i0 + r)) * p.W + j0) * KK;
         const float* src = partial + (size_t)r * Cfg::QCOLS * KK;
-        for (int e = threadIdx.x; e < run; e += blockDim.x) {
-            float s = 0.f;
-            for (int g = gFirst; g <= gLast; ++g) s += src[(size_t)(g + lt) * Cfg::TILE_FLOATS + e];
-            dst[e] = s;
+        if (dense) {
+            float* dst = out + (size_t)b * p.os.sb + ((size_t)(i0 + r) * p.W + j0) * KK;
+            for (int e = threadIdx.x; e < run; e += blockDim.x) {
+                float s = 0.f;
+                for (int g = gFirst; g <= gLast; ++g) s += src[(size_t)(g + lt) * Cfg::TILE_FLOATS + e];
+                dst[e] = s;
+            }
+        } else {
+            float* base = out + (size_t)b * p.os.sb + ((long long)(i0 + r) * p.W + j0) * p.os.sp;
+            for (int e = threadIdx.x; e < KK * Cfg::QCOLS; e += blockDim.x) {
+                const int col = e % Cfg::QCOLS, t = e / Cfg::QCOLS;
+                if (col >= ncols) continue;
+                float s = 0.f;
+                for (int g = gFirst; g <= gLast; ++g) s += src[(size_t)(g + lt) * Cfg::TILE_FLOATS + col * KK + t];
+                base[(long long)col * p.os.sp + (long long)t * p.os.st] = s;
+            }
         }
     }
 }
@@ -562,13 +587,14 @@ size_t corr_tile_bwd_ws_bytes(int B, int C, int H, int W, int d) {
 }
 
 template <int D>
-static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, void* ws,
-                      size_t ws_bytes, cudaStream_t st) {
+static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, const CorrOutStrides* os,
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
     using Cfg = FwdCfg<D>;
     constexpr int CK = kFwdCK;
     CorrPlan p;
     int rc = make_plan<D>(B, C, H, W, CK, &p);
     if (rc) return rc;
+    if (os) p.os = *os;
     // Whole-tile rounds (all CTAs in step, halos shared through L2) were measured SLOWER than one contiguous
     // (tile, chunk) range per CTA at B = 8 (c5: 587 vs ~510 us): with every CTA on the same channel planes at the
     // same time the memory system is hit in bursts.  So the schedule is the staggered stream-K walk.
@@ -597,10 +623,10 @@ static int fwd_launch(const float* fm0, const float* fm1, float* out, int B, int
     return D2T_OK;
 }
 
-int corr_tile_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
-    return d == 8 ? fwd_launch<8>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st)
-                  : fwd_launch<4>(fm0, fm1, out, B, C, H, W, ws, ws_bytes, st);
+int corr_tile_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d,
+                         const CorrOutStrides* os, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return d == 8 ? fwd_launch<8>(fm0, fm1, out, B, C, H, W, os, ws, ws_bytes, st)
+                  : fwd_launch<4>(fm0, fm1, out, B, C, H, W, os, ws, ws_bytes, st);
 }
 
 int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int,

@@ -136,8 +136,10 @@ th_split_copy_kernel(const float* __restrict__ x, float* __restrict__ chi, float
     }
 }
 
-// W (nO, C*KK) -> Wt hi / lo ((o,ij), ldc)  [K = c]   (transposed == 0)
-//              -> Wc hi / lo (c, ldn)       [K = (o,ij)]   (transposed == 1)
+// The n_out * kk "position-sensitive channels" are numbered n = ij * nO + o (outputs of one bin adjacent), so that the
+// pooling and gZ kernels move the nO values of a bin with one vector access.
+// W (nO, C*KK) -> Wt hi / lo (n, ldc)   [K = c]   (by_channel == 0)
+//              -> Wc hi / lo (c, ldn)   [K = n]   (by_channel == 1)
 __global__ void __launch_bounds__(256)
 th_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int C, int KK, int nO, int ld,
                       int by_channel) {
@@ -145,15 +147,15 @@ th_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ hi, float
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         int o, c, ij;
         size_t dst;
-        if (by_channel) {          // e = (c, o, ij): writes contiguous
+        if (by_channel) {          // e = (c, n): writes contiguous
             c = e / (nO * KK);
             const int n = e - c * (nO * KK);
-            o = n / KK; ij = n - o * KK;
+            ij = n / nO; o = n - ij * nO;
             dst = (size_t)c * ld + n;
-        } else {                   // e = (o, ij, c): writes contiguous
+        } else {                   // e = (n, c): writes contiguous
             const int n = e / C;
             c = e - n * C;
-            o = n / KK; ij = n - o * KK;
+            ij = n / nO; o = n - ij * nO;
             dst = (size_t)n * ld + c;
         }
         const float v = __ldg(w + (size_t)o * C * KK + (size_t)c * KK + ij);
@@ -177,31 +179,52 @@ th_reduce_slabs_kernel(const float4* __restrict__ part, float4* __restrict__ z, 
 }
 
 // ---- forward 2: position-sensitive pooling of Z over ROIPool bins ----------------------------------------------------
-// one CTA per RoI; thread n = (o, ij) sums Z[., n] over its bin rows-then-columns and divides by the bin size (0/0 = NaN
-// for an empty bin, like roipool_cuda.cu:61); thread o then adds the kk bin means of its output in ascending bin order.
-__global__ void __launch_bounds__(kThMaxN)
+// one CTA per kPoolRois RoIs; thread (roi, ij) sums the nO adjacent values Z[., ij*nO .. ij*nO+nO-1] over its bin
+// rows-then-columns (one 16-byte load per pixel for nO = 4) and divides by the bin size (0/0 = NaN for an empty bin, like
+// roipool_cuda.cu:61); thread (roi, o) then adds the kk bin means of its output in ascending bin order.
+constexpr int kPoolThreads2 = 256;
+template <int NO>
+__global__ void __launch_bounds__(kPoolThreads2)
 th_pool_kernel(const float* __restrict__ z, const float* __restrict__ rois, const float* __restrict__ bias, float* __restrict__ out,
-               int H, int W, int k, int nO, int ldn) {
-    __shared__ float part[kThMaxN];
-    const int r = blockIdx.x, n = threadIdx.x, KK = k * k, N1 = nO * KK;
-    if (n < N1) {
-        const int ij = n % KK, i = ij / k, j = ij - i * k;
+               int R, int H, int W, int k, int ldn, int roisPerCta) {
+    extern __shared__ float th_part[];   // [roisPerCta][KK][NO]
+    const int KK = k * k;
+    const int rl = threadIdx.x / KK, ij = threadIdx.x - rl * KK;
+    const int r = blockIdx.x * roisPerCta + rl;
+    if (rl < roisPerCta && r < R) {
+        const int i = ij / k, j = ij - i * k;
         const float* roi = rois + (size_t)r * 4;
         int i0, i1, j0, j1;
         bin_edge<float, true>(roi[0], roi[2], i, k, H, i0, i1);
         bin_edge<float, true>(roi[1], roi[3], j, k, W, j0, j1);
-        float acc = 0.f;
+        float acc[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = 0.f;
+        const float* zb = z + (size_t)ij * NO;
         for (int pi = i0; pi < i1; ++pi)
-            for (int pj = j0; pj < j1; ++pj) acc += __ldg(z + (size_t)(pi * W + pj) * ldn + n);
+            for (int pj = j0; pj < j1; ++pj) {
+                const float* src = zb + (size_t)(pi * W + pj) * ldn;
+                if (NO == 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                } else {
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) acc[o] += __ldg(src + o);
+                }
+            }
         const int numel = (i1 - i0) * (j1 - j0);
-        acc /= numel;
-        part[n] = acc;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) th_part[(rl * KK + ij) * NO + o] = acc[o] / numel;
     }
     __syncthreads();
-    if (n < nO) {
-        float s = bias ? bias[n] : 0.f;
-        for (int ij = 0; ij < KK; ++ij) s += part[n * KK + ij];
-        out[(size_t)r * nO + n] = s;
+    if (threadIdx.x < roisPerCta * NO) {
+        const int rl2 = threadIdx.x / NO, o = threadIdx.x - rl2 * NO;
+        const int r2 = blockIdx.x * roisPerCta + rl2;
+        if (r2 < R) {
+            float s = bias ? bias[o] : 0.f;
+            for (int b = 0; b < KK; ++b) s += th_part[(rl2 * KK + b) * NO + o];
+            out[(size_t)r2 * NO + o] = s;
+        }
     }
 }
 
@@ -223,7 +246,6 @@ th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float*
     __shared__ int nlist;
     const int y = blockIdx.x / k, i = blockIdx.x - y * k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int KK = k * k;
     for (int r = tid; r < R; r += kGzThreads) {
         const float* roi = rois + (size_t)r * 4;
         int i0, i1;
@@ -270,21 +292,32 @@ th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float*
             }
         }
         const int p = y * W + x;
+        const int nb = (i * k + j) * nO;
+        float hi[kGzMaxO], lo[kGzMaxO];
+#pragma unroll
+        for (int o = 0; o < kGzMaxO; ++o) {
+            hi[o] = tf32_rn(acc[o]);
+            lo[o] = acc[o] - hi[o];
+        }
+        if (nO == 4) {   // ldn and nb are multiples of 4: one 16-byte store per plane
+            *reinterpret_cast<float4*>(gz_hi + (size_t)p * ldn + nb) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(gz_lo + (size_t)p * ldn + nb) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
 #pragma unroll
         for (int o = 0; o < kGzMaxO; ++o) {
             if (o < nO) {
-                const int n = o * KK + i * k + j;
-                const float h = tf32_rn(acc[o]), lo = acc[o] - h;
-                gz_hi[(size_t)p * ldn + n] = h;
-                gz_lo[(size_t)p * ldn + n] = lo;
-                gzt_hi[(size_t)n * ldp + p] = h;
-                gzt_lo[(size_t)n * ldp + p] = lo;
+                if (nO != 4) {
+                    gz_hi[(size_t)p * ldn + nb + o] = hi[o];
+                    gz_lo[(size_t)p * ldn + nb + o] = lo[o];
+                }
+                gzt_hi[(size_t)(nb + o) * ldp + p] = hi[o];
+                gzt_lo[(size_t)(nb + o) * ldp + p] = lo[o];
             }
         }
     }
 }
 
-// ---- backward 3: gW[o][c*KK + ij] = sum_s gWpart[s][c][o*KK + ij];  gb[o] = sum_r g[r][o] -------------------------------
+// ---- backward 3: gW[o][c*KK + ij] = sum_s gWpart[s][c][ij*nO + o];  gb[o] = sum_r g[r][o] -----------------------------
 __global__ void __launch_bounds__(256)
 th_reduce_w_kernel(const float* __restrict__ part, const float* __restrict__ g, float* __restrict__ gw, float* __restrict__ gb,
                    int R, int C, int KK, int nO, int ldn, int splits) {
@@ -293,16 +326,23 @@ th_reduce_w_kernel(const float* __restrict__ part, const float* __restrict__ g, 
     if (gw) {
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < C * N1; e += gridDim.x * blockDim.x) {
             const int c = e / N1, n = e - c * N1;
-            const int o = n / KK, ij = n - o * KK;
+            const int ij = n / nO, o = n - ij * nO;
             float s = 0.f;
             for (int k = 0; k < splits; ++k) s += part[(size_t)k * slab + (size_t)c * ldn + n];
             gw[(size_t)o * C * KK + (size_t)c * KK + ij] = s;
         }
     }
-    if (gb && blockIdx.x == 0 && threadIdx.x < nO) {
-        float s = 0.f;
-        for (int r = 0; r < R; ++r) s += g[(size_t)r * nO + threadIdx.x];
-        gb[threadIdx.x] = s;
+    // bias gradient: the last block, one warp per output; lanes take RoIs r = lane, lane + 32, ... (ascending), then a
+    // fixed-shape shuffle tree: deterministic
+    if (gb && blockIdx.x == gridDim.x - 1) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int o = warp; o < nO; o += blockDim.x >> 5) {
+            float s = 0.f;
+            for (int r = lane; r < R; r += 32) s += __ldg(g + (size_t)r * nO + o);
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+            if (lane == 0) gb[o] = s;
+        }
     }
 }
 
@@ -331,6 +371,7 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
     int rc = th_dims(R, C, H, W, k, nO, &d);
     if (rc) return rc;
     if (R == 0) return D2T_OK;
+    D2T_REQUIRE(nO <= 8, "trackhead_fwd: n_out must be <= 8");
     D2T_REQUIRE(fm && rois && weight && out, "trackhead_fwd: null pointer");
     const ThFwdWs w = th_fwd_ws(d, wsp);
     if (wsp == nullptr || ws_bytes < w.total) {
@@ -356,7 +397,23 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
         note_launch();
         z = w.z;
     }
-    th_pool_kernel<<<R, kThMaxN, 0, st>>>(z, rois, bias, out, H, W, k, nO, d.ldn);
+    {
+        const int rpc = kPoolThreads2 / d.KK > 0 ? kPoolThreads2 / d.KK : 1;   // RoIs per CTA (5 for k = 7)
+        D2T_REQUIRE(d.KK <= kPoolThreads2, "trackhead_fwd: r_hw^2 must be <= %d", kPoolThreads2);
+        const size_t psm = (size_t)rpc * d.KK * nO * sizeof(float);
+        const int grid = ceil_div(R, rpc);
+        switch (nO) {
+            case 1: th_pool_kernel<1><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 2: th_pool_kernel<2><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 3: th_pool_kernel<3><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 4: th_pool_kernel<4><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 5: th_pool_kernel<5><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 6: th_pool_kernel<6><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 7: th_pool_kernel<7><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 8: th_pool_kernel<8><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            default: set_error("trackhead_fwd: n_out must be <= 8"); return D2T_ERR_BAD_ARG;
+        }
+    }
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;

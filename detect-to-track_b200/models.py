@@ -12,7 +12,7 @@ from typing import Dict, Tuple
 import torch
 from torch import Tensor, nn
 
-from .pointwise_correlation import PointwiseCorrelation
+from .pointwise_correlation import PointwiseCorrelation, TrackFeaturesFunction
 from .ps_roipool import PSROIPool
 from .roipool import ROIPool
 from .track_head import TrackHeadFunction
@@ -82,10 +82,16 @@ class CorrelationTracker(nn.Module):
         ]
 
     def forward(self, fm_pyr_0, fm_pyr_1, reg_fm_0: Tensor, reg_fm_1: Tensor, rois: Tensor) -> Tensor:
+        if self.fused:
+            # same function, two fusions: the correlations write channel-major maps
+            # straight into the concatenated buffer, and ROIPool -> view -> Linear is one operator (track_head.py)
+            down = lambda t: nn.functional.interpolate(t[None, :, :, :], scale_factor=1 / 2).contiguous()
+            track_feats = TrackFeaturesFunction.apply(
+                reg_fm_0, reg_fm_1, down(fm_pyr_0["c3"]), down(fm_pyr_1["c3"]), fm_pyr_0["c4"][None], fm_pyr_1["c4"][None],
+                fm_pyr_0["c5"][None], fm_pyr_1["c5"][None], self.point_corr.d_max, self.point_corr.stride)
+            return TrackHeadFunction.apply(track_feats, rois, self.reg_fc.weight, self.reg_fc.bias, self.pool.r_hw)
         corr_feats = self.correlation_features(fm_pyr_0, fm_pyr_1)
         track_feats = torch.cat([reg_fm_0, reg_fm_1, *corr_feats])
-        if self.fused:  # ROIPool -> view -> Linear as one operator; same parameters, same result (track_head.py)
-            return TrackHeadFunction.apply(track_feats, rois, self.reg_fc.weight, self.reg_fc.bias, self.pool.r_hw)
         pooled_feats = self.pool(track_feats, rois)
         pooled_feats = pooled_feats.view(pooled_feats.size(0), self.fc_channels)
         return self.reg_fc(pooled_feats)

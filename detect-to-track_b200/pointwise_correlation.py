@@ -39,6 +39,73 @@ def pointwise_correlation_forward(FM0: Tensor, FM1: Tensor, d_max: int, stride: 
     return out
 
 
+def pointwise_correlation_forward_channel_major(FM0: Tensor, FM1: Tensor, d_max: int, stride: int, out: Tensor) -> Tensor:
+    """Tracker glue fusion (correlation_tracker.py:64-80): the correlation of ONE frame pair (B = 1) written directly as
+    the channel-major ((2d+1)^2, H, W) map into `out`, a contiguous slice of the tracker's concatenated feature buffer.
+    Bit-identical to `pointwise_correlation_forward(...).squeeze(0).view(H, W, -1).permute(2, 0, 1)`; no permute copy,
+    no torch.cat."""
+    _lib.check_input(FM0, "FM0")
+    _lib.check_input(FM1, "FM1")
+    _lib.check_input(out, "out")
+    if FM0.shape != FM1.shape or FM0.dim() != 4 or FM0.size(0) != 1:
+        raise RuntimeError(f"FM0 and FM1 must both be (1, C, H, W); got {tuple(FM0.shape)} and {tuple(FM1.shape)}")
+    sfx = _lib.suffix(FM0.dtype)
+    _, C, H, W = FM0.shape
+    k = 2 * d_max + 1
+    if tuple(out.shape) != (k * k, H, W) or out.dtype != FM0.dtype or out.device != FM0.device:
+        raise RuntimeError(f"out must be a contiguous {(k * k, H, W)} {FM0.dtype} tensor on {FM0.device}")
+    lib = _lib.lib()
+    with torch.cuda.device(FM0.device):
+        nbytes = lib.d2t_corr_fwd_workspace_bytes(1, C, H, W, d_max, stride, FM0.element_size())
+        ws, ws_ptr, ws_n = _lib.workspace(nbytes, FM0.device)
+        rc = getattr(lib, f"d2t_corr_fwd_strided_{sfx}")(
+            FM0.data_ptr(), FM1.data_ptr(), out.data_ptr(), 1, C, H, W, d_max, stride, 0, 1, H * W,
+            ws_ptr, ws_n, _lib.stream_ptr(FM0.device))
+        _lib.check(rc, "pointwise_correlation_forward_channel_major")
+    return out
+
+
+class TrackFeaturesFunction(Function):
+    """track_feats = cat([reg_fm_0, reg_fm_1, corr(c3), corr(c4), corr(c5)]) as the reference builds it
+    (correlation_tracker.py:64-80), with the three correlations written channel-major straight into their slices of
+    the output: no (1, H, W, k, k) -> (k^2, H, W) permute copies and no torch.cat.  Extension used by
+    `CorrelationTracker(fused=True)`; gradients flow to all eight inputs."""
+
+    @staticmethod
+    def forward(ctx, reg_fm_0: Tensor, reg_fm_1: Tensor, c3_0: Tensor, c3_1: Tensor, c4_0: Tensor, c4_1: Tensor,
+                c5_0: Tensor, c5_1: Tensor, d_max: int, stride: int) -> Tensor:
+        pairs = [(c3_0, c3_1), (c4_0, c4_1), (c5_0, c5_1)]
+        ctx.save_for_backward(c3_0, c3_1, c4_0, c4_1, c5_0, c5_1)
+        ctx.cfg = (d_max, stride, reg_fm_0.size(0), reg_fm_1.size(0))
+        kk = (2 * d_max + 1) ** 2
+        Cr0, Cr1 = reg_fm_0.size(0), reg_fm_1.size(0)
+        H, W = reg_fm_0.shape[-2:]
+        out = torch.empty((Cr0 + Cr1 + 3 * kk, H, W), dtype=reg_fm_0.dtype, device=reg_fm_0.device)
+        out[:Cr0].copy_(reg_fm_0)
+        out[Cr0:Cr0 + Cr1].copy_(reg_fm_1)
+        base = Cr0 + Cr1
+        for n, (a, b) in enumerate(pairs):
+            pointwise_correlation_forward_channel_major(a.contiguous(), b.contiguous(), d_max, stride,
+                                                        out[base + n * kk: base + (n + 1) * kk])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad: Tensor):
+        d_max, stride, Cr0, Cr1 = ctx.cfg
+        saved = ctx.saved_tensors
+        k = 2 * d_max + 1
+        kk = k * k
+        H, W = grad.shape[-2:]
+        grads = [grad[:Cr0], grad[Cr0:Cr0 + Cr1]]
+        base = Cr0 + Cr1
+        for n in range(3):
+            a, b = saved[2 * n], saved[2 * n + 1]
+            go = grad[base + n * kk: base + (n + 1) * kk].permute(1, 2, 0).contiguous().view(1, H, W, k, k)
+            g0, g1 = pointwise_correlation_backward(go, a.contiguous(), b.contiguous(), d_max, stride)
+            grads += [g0, g1]
+        return (*grads, None, None)
+
+
 def pointwise_correlation_backward(
     grad_out: Tensor, FM0: Tensor, FM1: Tensor, d_max: int, stride: int
 ) -> Tuple[Tensor, Tensor]:

@@ -84,6 +84,19 @@ D2T_API int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int
 D2T_API int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
                      int stride, void* ws, size_t ws_bytes, void* stream);
 
+/* Strided output (tracker glue fusion, correlation_tracker.py:64-80): element (b, pos = i*W + j, t = ci*(2d+1) + cj)
+ * is written to out[b*batch_stride + pos*pos_stride + t*disp_stride] (strides in elements).  {H*W*kk, kk, 1} is the
+ * reference layout; {anything, 1, H*W} writes the ((2d+1)^2, H, W) channel-major map the tracker feeds to ROIPool
+ * straight into a slice of its concatenated feature buffer -- bit-identical to
+ * out.squeeze(0).view(H, W, -1).permute(2, 0, 1) of d2t_corr_fwd_*, without the permute copy and the torch.cat.
+ * Same workspace as d2t_corr_fwd_*. */
+D2T_API int d2t_corr_fwd_strided_f32(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max,
+                             int stride, long long batch_stride, long long pos_stride, long long disp_stride, void* ws,
+                             size_t ws_bytes, void* stream);
+D2T_API int d2t_corr_fwd_strided_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
+                             int stride, long long batch_stride, long long pos_stride, long long disp_stride, void* ws,
+                             size_t ws_bytes, void* stream);
+
 /* grad_out : (B, H, W, 2d+1, 2d+1);  grad_fm0, grad_fm1 : (B, C, H, W)
  *
  * Kernel family of d2t_corr_bwd_f32 -- a function of (C, d_max, stride) only, never of B, H or W, so the gradients of

@@ -358,6 +358,42 @@ def test_corr_bwd_explicit_families_agree(cuda):
     assert rc == 3
 
 
+@pytest.mark.parametrize("C,H,W,d,stride,dtype", [(96, 38, 63, 8, 1, np.float32), (2048, 38, 63, 8, 1, np.float32),
+                                                 (24, 12, 13, 4, 1, np.float32), (5, 9, 14, 2, 3, np.float32),
+                                                 (3, 10, 11, 3, 2, np.float64)])
+def test_corr_channel_major_output_is_bit_identical_to_the_permute(cuda, C, H, W, d, stride, dtype):
+    """tracker glue fusion (correlation_tracker.py:64-80): d2t_corr_fwd_strided_* writing ((2d+1)^2, H, W) into a slice of a
+    larger buffer == permute(2, 0, 1) of the reference-layout output, bit for bit; the rest of the buffer is untouched
+    (whole tiles, stream-K split tiles at C = 2048, the generic kernel for other (d, stride), float64)."""
+    fm0, fm1, _ = (dev(a, cuda) for a in cases.corr_inputs(1, C, H, W, d, seed=31, dtype=dtype))
+    kk = (2 * d + 1) ** 2
+    buf = torch.full((7 + kk + 5, H, W), 777.0, dtype=fm0.dtype, device=cuda)
+    pc_mod.pointwise_correlation_forward_channel_major(fm0, fm1, d, stride, buf[7:7 + kk])
+    want = pc_mod.pointwise_correlation_forward(fm0, fm1, d, stride).squeeze(0).view(H, W, -1).permute(2, 0, 1)
+    assert torch.equal(buf[7:7 + kk], want)
+    assert bool((buf[:7] == 777.0).all()) and bool((buf[7 + kk:] == 777.0).all())
+
+
+def test_track_features_function_matches_cat_of_permutes(cuda):
+    """TrackFeaturesFunction == torch.cat([reg0, reg1, corr maps permuted]) of the reference wiring: values bit-identical,
+    gradients of all eight inputs equal to autograd through the reference composition."""
+    H, W, d, Cr = 20, 21, 3, 6
+    g = torch.Generator(device="cpu").manual_seed(9)
+    mk = lambda *s: torch.randn(*s, generator=g).to(cuda).requires_grad_(True)
+    ins = [mk(Cr, H, W), mk(Cr, H, W), mk(1, 8, H, W), mk(1, 8, H, W), mk(1, 12, H, W), mk(1, 12, H, W), mk(1, 16, H, W), mk(1, 16, H, W)]
+    out = d2t.TrackFeaturesFunction.apply(*ins, d, 1)
+    wt = torch.randn(out.shape, generator=g).to(cuda)
+    (out * wt).sum().backward()
+    ins2 = [t.detach().clone().requires_grad_(True) for t in ins]
+    pc = d2t.PointwiseCorrelation(d, 1)
+    feats = [pc(ins2[2 + 2 * n], ins2[3 + 2 * n]).squeeze(0).view(H, W, -1).permute(2, 0, 1) for n in range(3)]
+    ref = torch.cat([ins2[0], ins2[1], *feats])
+    (ref * wt).sum().backward()
+    assert torch.equal(out, ref)
+    for a, b in zip(ins, ins2):
+        assert torch.equal(a.grad, b.grad)
+
+
 def test_corr_backward_is_deterministic(cuda):
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(2, 64, 38, 63, 8, seed=13, dtype=np.float32))
     a = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
