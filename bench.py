@@ -13,15 +13,23 @@ One STEP = the whole hot path, forward + backward, for 8 frame pairs on one GPU
 Pairs shard over GPUs with no data-path collective: weak scaling, value =
 pairs processed by all ranks / max-over-ranks device time.
 
-`value`   : inputs resident in HBM, ops called through the Python mirror of the reference API
-            (which calls the C ABI); CUDA events; working set per step (> 2 GB) exceeds L2.
-`e2e`     : the same work driven from HOST buffers through the public nn.Module API wired as the
-            reference wires it (CorrelationTracker + R-FCN heads): every step copies that step's
-            inputs from pinned host memory and reads the scalar loss back.
-`roofline`: the dominant kernel (correlation backward, c5) timed live with CUDA events.
+`value`      : inputs resident in HBM, the API-parity ops called through the Python mirror of the reference API
+               (which calls the C ABI); CUDA events; working set per step (> 2 GB) exceeds L2.
+`fused`      : the same step with config 4 (track head) run by the fused ROIPool->Linear operator (csrc/track_head.cu),
+               which also does the Linear(92659, 4) the API-parity step leaves to the caller.
+`e2e`        : the same work driven from HOST buffers through the public nn.Module API wired as the
+               reference wires it (CorrelationTracker + R-FCN heads): every step copies that step's
+               inputs from pinned host memory and reads the scalar loss back.
+`roofline`   : the dominant kernel of the `value` step (ROIPool backward), timed live with CUDA events;
+               `roofline_other`: every other default kernel family.
+`per_config` : BASELINE.json configs 1-4 one by one (device time, achieved rate, fraction of roofline, CPU port time).
+`reference_gpu`: the reference's OWN CUDA kernels (oracle/_ref, compiled unmodified from /root/reference) timed on this
+               GPU through the reference's per-call API (B = 1 / one frame), beside our ops on the same inputs.
+`train_step` : BASELINE config 5, the full D&T R-FCN ResNet-101 training step on synthetic 608x1008 frame pairs,
+               DistributedDataParallel over the pair shards (detect_to_track_b200/train_step.py).
 `cpu_baseline` / `--impl reference`: the reference has NO CPU implementation of these ops
-            (CUDA-only, README); the CPU arm is the C restatement in oracle/ (kind "port"), OpenMP
-            over all host cores, on a bounded sample (one frame pair per step).
+               (CUDA-only, README); the CPU arm is the C restatement in oracle/ (kind "port"), OpenMP
+               over all host cores, on a bounded sample (one frame pair per step).
 """
 from __future__ import annotations
 
@@ -50,6 +58,12 @@ METRIC = "corr+PSROI fwd+bwd frame-pairs/s"
 WORKLOAD = ("D&T op hot path fwd+bwd per frame pair: PointwiseCorrelation d=8 on c3/c4/c5 (512/1024/2048 ch, 38x63, "
             "from 608x1008 frames) + PSROIPool 7x7 cls(31)+reg(4) x 2 frames, 300 RoIs + ROIPool 7x7 track head "
             "(1891 ch, 300 RoIs); 8 pairs per GPU")
+
+
+def base_config():
+    """the keys both arms report under `config` (same workload, same shapes)"""
+    return {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "rois": R, "d_max": D, "r_hw": K,
+            "l2": "per-step working set > 2 GB, far above the 126 MB L2 (no explicit flush needed)"}
 
 
 def live_pairs(n_h, n_w, d):
@@ -154,16 +168,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # bounded: one frame pair per step (1/8 of the GPU step), a few seconds each
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
-    steps = min(steps, 30)
+    # bounded: each step is ONE frame pair of the workload (1/8 of the GPU arm's step), ~0.3 s on 16 host threads, so
+    # the driver's --steps / --warmup are honoured as given
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     pps, sec, cores = time_cpu(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": 1,
-                   "note": "the reference ops are CUDA-only; this arm is the CPU restatement oracle/d2t_oracle.c (OpenMP)"},
+        "config": base_config(),
+        "arm": {"sample": "1 frame pair per step (the GPU arm runs 8 per step per GPU); same per-pair workload",
+                "note": "the reference ops are CUDA-only; this arm is the CPU restatement oracle/d2t_oracle.c (OpenMP)"},
         "cpu_baseline": {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                          "sample": "1 frame pair per step (all 3 correlations, 4 PSROIPool, 1 ROIPool; fwd+bwd)"},
         "e2e": {"value": pps, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -171,6 +186,224 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# --------------------------------------------------------------------------------------------- per-config + reference kernels
+def _time_call(torch, fn, flush, iters=15, warm=3):
+    """median device time (s) of one call: CUDA events on the current stream, L2 flushed before every timed call"""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def run_per_config(torch, dev, hbm, fp32_peak, tf32_peak, cpu=True):
+    """BASELINE.json configs 1-4, each on its own: device time of forward and backward (CUDA events, L2 flushed between
+    calls), algorithmic work, achieved rate against the roof that bounds it, and the CPU port's
+    time for the same call (config 3 / 4: one pair, scaled) -- runs after all timed regions."""
+    import cases
+    from detect_to_track_b200 import pointwise_correlation as pc, roipool as rp, ps_roipool as ps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    oracle = None
+    if cpu:
+        import oracle as _o
+        _o.set_threads(os.cpu_count() or 1)
+        oracle = _o
+    rows = []
+
+    def cpu_time(fn):
+        if oracle is None:
+            return None
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        return time.perf_counter() - t0
+
+    def corr(name, B, C, Hh, Ww, d, cpu_b=None):
+        fm0 = (torch.randn(B, C, Hh, Ww, generator=g).relu_() / 16).to(dev)
+        fm1 = (torch.randn(B, C, Hh, Ww, generator=g).relu_() / 16).to(dev)
+        go = torch.randn(B, Hh, Ww, 2 * d + 1, 2 * d + 1, generator=g).to(dev)
+        v = lambda n: sum(len(range(max(0, i - d), min(i + d, n))) for i in range(n))
+        Pn = B * v(Hh) * v(Ww)
+        kk = (2 * d + 1) ** 2
+        tf = _time_call(torch, lambda: pc.pointwise_correlation_forward(fm0, fm1, d, 1), flush)
+        tb = _time_call(torch, lambda: pc.pointwise_correlation_backward(go, fm0, fm1, d, 1), flush)
+        tensor_bwd = d == 8 and C >= 128
+        row = {"config": name, "us_fwd": tf * 1e6, "us_bwd": tb * 1e6,
+               "fwd": {"bound": "fp32", "achieved": 2.0 * C * Pn / tf * 1e-12, "peak": fp32_peak, "unit": "TFLOP/s",
+                       "frac": 2.0 * C * Pn / tf * 1e-12 / fp32_peak,
+                       "hbm_gbs": (2 * B * C * Hh * Ww + B * Hh * Ww * kk) * 4 / tf * 1e-9},
+               "bwd": {"bound": "tensor" if tensor_bwd else "fp32", "achieved": 4.0 * C * Pn / tb * 1e-12,
+                       "peak": tf32_peak if tensor_bwd else fp32_peak, "unit": "TFLOP/s",
+                       "frac": 4.0 * C * Pn / tb * 1e-12 / (tf32_peak if tensor_bwd else fp32_peak),
+                       "hbm_gbs": (4 * B * C * Hh * Ww + B * Hh * Ww * kk) * 4 / tb * 1e-9}}
+        if oracle is not None:
+            nb = cpu_b or B
+            a0, a1, ag = (t[:nb].cpu().numpy() for t in (fm0, fm1, go))
+            s = cpu_time(lambda: (oracle.corr_fwd(a0, a1, d, 1), oracle.corr_bwd(ag, a0, a1, d, 1)))
+            row["cpu_port_us_fwd_bwd"] = s * 1e6 * B / nb
+            row["cpu_sample"] = f"{nb} of {B} batch elements, scaled"
+        rows.append(row)
+
+    corr("1: PointwiseCorrelation fwd+bwd, 2 pairs, C=256, 32x32, d=4", 2, 256, 32, 32, 4)
+    for nm, C in CORR_C:
+        corr(f"3: correlation d=8 {nm} C={C} 38x63, batch 8 pairs", PAIRS_PER_GPU, C, H, W, D, cpu_b=1)
+
+    rois = torch.from_numpy(cases.rois_random(R, 1237)).to(dev)
+    for nm, nT, live in (("cls (31 targets)", N_CLS, 608), ("reg (4 targets)", N_REG, 117)):
+        fm = torch.randn(nT * K * K, H, W, generator=g).to(dev)
+        go = torch.randn(R, nT, K, K, generator=g).to(dev)
+        fb = (live * H * W + R * nT * K * K) * 4 + R * 16
+        bb = (nT * K * K * H * W + R * nT * K * K) * 4 + R * 16
+        tf = _time_call(torch, lambda: ps.ps_roipool_forward(fm, rois, nT, K), flush)
+        tb = _time_call(torch, lambda: ps.ps_roipool_backward(go, rois, H, W), flush)
+        row = {"config": f"2: PSROIPool 7x7 {nm}, 300 RoIs, ONE frame per call (the reference API)", "us_fwd": tf * 1e6,
+               "us_bwd": tb * 1e6,
+               "fwd": {"bound": "hbm", "achieved": fb / tf * 1e-9, "peak": hbm, "unit": "GB/s", "frac": fb / tf * 1e-9 / hbm},
+               "bwd": {"bound": "hbm", "achieved": bb / tb * 1e-9, "peak": hbm, "unit": "GB/s", "frac": bb / tb * 1e-9 / hbm},
+               "note": "a single-frame call is launch-latency-bound (1.8 MB moved); the batched entry points are in roofline_other"}
+        if oracle is not None:
+            a, ag, ar = fm.cpu().numpy(), go.cpu().numpy(), rois.cpu().numpy()
+            row["cpu_port_us_fwd_bwd"] = cpu_time(lambda: (oracle.psroipool_fwd(a, ar, nT, K), oracle.psroipool_bwd(ag, ar, H, W))) * 1e6
+        rows.append(row)
+
+    rois = torch.from_numpy(cases.rois_random(R, 1238)).to(dev)
+    fm = torch.randn(TRACK_C, H, W, generator=g).to(dev)
+    go = torch.randn(R, TRACK_C, K, K, generator=g).to(dev)
+    nb = (TRACK_C * H * W + R * TRACK_C * K * K) * 4
+    tf = _time_call(torch, lambda: rp.roipool_forward(fm, rois, K), flush)
+    tb = _time_call(torch, lambda: rp.roipool_backward(go, rois, H, W), flush)
+    row = {"config": "4: track-head ROIPool, 1891 channels, 300 RoIs", "us_fwd": tf * 1e6, "us_bwd": tb * 1e6,
+           "fwd": {"bound": "hbm", "achieved": nb / tf * 1e-9, "peak": hbm, "unit": "GB/s", "frac": nb / tf * 1e-9 / hbm},
+           "bwd": {"bound": "hbm", "achieved": nb / tb * 1e-9, "peak": hbm, "unit": "GB/s", "frac": nb / tb * 1e-9 / hbm}}
+    if oracle is not None:
+        a, ag, ar = fm.cpu().numpy(), go.cpu().numpy(), rois.cpu().numpy()
+        row["cpu_port_us_fwd_bwd"] = cpu_time(lambda: (oracle.roipool_fwd(a, ar, K), oracle.roipool_bwd(ag, ar, H, W))) * 1e6
+    rows.append(row)
+    return rows
+
+
+def run_reference_gpu(torch, dev):
+    """the reference's OWN CUDA kernels (oracle/_ref: its three *_cuda.cu files compiled unmodified for sm_100a) on this
+    GPU, through its per-call API -- B = 1 correlation (correlation_tracker.py:68-70), one frame per pooling call --
+    beside this library's ops on the same inputs and the same harness (CUDA events, L2 flushed).  Checker code timed as
+    a second witness; runs after every timed region.  us = forward / backward."""
+    import cases
+    from oracle import ref_cuda
+    from detect_to_track_b200 import pointwise_correlation as pc, roipool as rp, ps_roipool as ps
+    if not ref_cuda.available():
+        return {"unavailable": "oracle/_ref/libd2t_ref_cuda.so not built (needs /root/reference at build time)"}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    rows = []
+
+    def add(name, ours_f, ours_b, ref_f, ref_b, ref_iters=5):
+        o = (_time_call(torch, ours_f, flush), _time_call(torch, ours_b, flush))
+        r = (_time_call(torch, ref_f, flush, iters=ref_iters, warm=1), _time_call(torch, ref_b, flush, iters=ref_iters, warm=1))
+        rows.append({"op": name, "ours_us": [o[0] * 1e6, o[1] * 1e6], "reference_kernel_us": [r[0] * 1e6, r[1] * 1e6],
+                     "speedup": [r[0] / o[0], r[1] / o[1]]})
+
+    for nm, C in CORR_C:
+        fm0 = (torch.randn(1, C, H, W, generator=g).relu_() / 16).to(dev)
+        fm1 = (torch.randn(1, C, H, W, generator=g).relu_() / 16).to(dev)
+        go = torch.randn(1, H, W, 2 * D + 1, 2 * D + 1, generator=g).to(dev)
+        add(f"PointwiseCorrelation {nm} C={C} 38x63 d=8 B=1",
+            lambda: pc.pointwise_correlation_forward(fm0, fm1, D, 1), lambda: pc.pointwise_correlation_backward(go, fm0, fm1, D, 1),
+            lambda: ref_cuda.corr_fwd(fm0, fm1, D, 1), lambda: ref_cuda.corr_bwd(go, fm0, fm1, D, 1), ref_iters=3)
+    rois = torch.from_numpy(cases.rois_random(R, 1237)).to(dev)
+    for nm, nT in (("cls nT=31", N_CLS), ("reg nT=4", N_REG)):
+        fm = torch.randn(nT * K * K, H, W, generator=g).to(dev)
+        go = torch.randn(R, nT, K, K, generator=g).to(dev)
+        add(f"PSROIPool {nm} R=300 one frame",
+            lambda: ps.ps_roipool_forward(fm, rois, nT, K), lambda: ps.ps_roipool_backward(go, rois, H, W),
+            lambda: ref_cuda.psroipool_fwd(fm, rois, nT, K), lambda: ref_cuda.psroipool_bwd(go, rois, H, W))
+    rois = torch.from_numpy(cases.rois_random(R, 1238)).to(dev)
+    fm = torch.randn(TRACK_C, H, W, generator=g).to(dev)
+    go = torch.randn(R, TRACK_C, K, K, generator=g).to(dev)
+    add("ROIPool track head C=1891 R=300",
+        lambda: rp.roipool_forward(fm, rois, K), lambda: rp.roipool_backward(go, rois, H, W),
+        lambda: ref_cuda.roipool_fwd(fm, rois, K), lambda: ref_cuda.roipool_bwd(go, rois, H, W))
+    return {"kind": "reference CUDA kernels (oracle/_ref), legacy default stream, same GPU", "rows": rows}
+
+
+# --------------------------------------------------------------------------------------------- config 5: train step
+def run_train_step(torch, dev, rank, world, barrier, pairs=PAIRS_PER_GPU, steps=3, warmup=2):
+    """BASELINE config 5: full D&T R-FCN ResNet-101 training step (backbone -> RPN -> R-FCN heads -> correlation tracker ->
+    losses -> backward -> SGD) on synthetic 608x1008 frame pairs, `pairs` per GPU per step, DistributedDataParallel over
+    the pair shards (bucketed NCCL all-reduce overlapped with the backward).  Images cross PCIe inside the timed region
+    (pinned host memory, one copy per pair); the scalar loss is read back every step."""
+    import torch.distributed as dist
+    from detect_to_track_b200 import train_step as ts
+    torch.manual_seed(1239)                               # identical initial weights on every rank
+    out = {}
+    for fused in (False, True):
+        model = ts.DetectTrackModule("resnet101", 3, fused_tracker=fused).to(dev)
+        stepm = ts.DetectTrackTrainStep(model)
+        ddp = stepm
+        if world > 1:
+            ddp = torch.nn.parallel.DistributedDataParallel(stepm, device_ids=[dev.index], bucket_cap_mb=25,
+                                                            gradient_as_bucket_view=True)
+        opt = ts.make_optimizer(stepm)
+        host = ts.synthetic_batch(pairs, 608, 1008, R, 30, seed=1239 + rank, pin=True)
+        h2d = sum(v.numel() * v.element_size() for it in host for v in it.values())
+        loss_host = torch.zeros(1).pin_memory()
+
+        def one_step(sync=True):
+            batch = [{k: v.to(dev, non_blocking=True) for k, v in it.items()} for it in host]
+            opt.zero_grad(set_to_none=True)
+            if world > 1 and not sync:
+                with ddp.no_sync():
+                    loss, _ = ddp(batch)
+                    loss.backward()
+            else:
+                loss, _ = ddp(batch)
+                loss.backward()
+            opt.step()
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return float(loss_host[0])
+
+        def timed(sync):
+            for _ in range(warmup):
+                last = one_step(sync)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                last = one_step(sync)
+            e1.record()
+            barrier()
+            if not (last == last):
+                raise RuntimeError("train step produced a NaN loss")
+            return e0.elapsed_time(e1) / steps, last
+
+        ms, last = timed(True)
+        ms_nosync = timed(False)[0] if world > 1 else ms
+        ms, ms_nosync = global_max([ms, ms_nosync], dev)
+        out["fused_tracker" if fused else "reference_composition"] = {
+            "ms_per_step": ms, "pairs_per_s": world * pairs / (ms * 1e-3), "loss": last,
+            "ms_per_step_without_gradient_sync": ms_nosync, "exposed_allreduce_ms": max(0.0, ms - ms_nosync)}
+        out["trainable_parameter_mb"] = ts.trainable_parameter_bytes(stepm) / 1e6
+        out["h2d_bytes_per_step"] = h2d
+        del model, stepm, ddp, opt
+        torch.cuda.empty_cache()
+    out.update({"config": "5: full D&T R-FCN ResNet-101 train step, synthetic 608x1008 frame pairs, random init, "
+                          f"{pairs} pairs per GPU per step, {world} GPU(s)",
+                "unit": "frame-pairs/s", "steps": steps, "warmup": warmup, "dtype": "f32 (cuDNN convolutions may use TF32)",
+                "collective": ("DistributedDataParallel: NCCL all-reduce of layer3+layer4+RPN+R-FCN+tracker gradients in 25 MB "
+                               "buckets, overlapped with the backward") if world > 1 else "none (1 GPU)"})
+    return out
 
 
 # --------------------------------------------------------------------------------------------- multi-rank plumbing
@@ -209,6 +442,10 @@ def build_device_inputs(torch, dev, seed):
         rois = torch.from_numpy(cases.rois_random(R, 1238 + pr)).to(dev)
         inp["track"].append((torch.randn(TRACK_C, H, W, generator=g).to(dev), rois,
                              torch.randn(R, TRACK_C, K, K, generator=g).to(dev)))
+    # fused track head: the Linear(92659, 4) of correlation_tracker.py:33 and the gradient of its (R, 4) output
+    inp["fc_w"] = (torch.randn(4, TRACK_C * K * K, generator=g) / (TRACK_C * K * K) ** 0.5).to(dev)
+    inp["fc_b"] = torch.zeros(4).to(dev)
+    inp["fc_go"] = torch.randn(R, 4, generator=g).to(dev)
     return inp
 
 
@@ -216,7 +453,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from detect_to_track_b200 import _lib
-    from detect_to_track_b200 import pointwise_correlation as pc, roipool as rp, ps_roipool as ps
+    from detect_to_track_b200 import pointwise_correlation as pc, roipool as rp, ps_roipool as ps, track_head as th
     import detect_to_track_b200 as d2t
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,7 +488,7 @@ def run_ours(args):
     n_streams = max(1, args.streams)
     lanes = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
 
-    def step(record_dom=False):
+    def step(record_dom=False, fused=False):
         keep = []
         main = torch.cuda.current_stream(dev)
         use = [main] + lanes if not record_dom else [main]   # per-kernel timing runs on one stream
@@ -264,13 +501,20 @@ def run_ours(args):
                 timed("corr_fwd", rec, lambda: pc.pointwise_correlation_forward(fm0, fm1, D, 1)),
                 timed("corr_bwd", rec, lambda: pc.pointwise_correlation_backward(go, fm0, fm1, D, 1))))
         for nT, fm, rois, go in inp["ps"]:   # all 2*B frames of the shard in one set of launches
-            jobs.append(lambda nT=nT, fm=fm, rois=rois, go=go: (
-                ps.ps_roipool_forward_batched(fm, rois, nT, K), ps.ps_roipool_backward_batched(go, rois, H, W)))
+            key = "ps_cls" if nT == N_CLS else "ps_reg"
+            jobs.append(lambda nT=nT, fm=fm, rois=rois, go=go, key=key: (
+                timed(key + "_fwd", record_dom, lambda: ps.ps_roipool_forward_batched(fm, rois, nT, K)),
+                timed(key + "_bwd", record_dom, lambda: ps.ps_roipool_backward_batched(go, rois, H, W))))
         for n, (fm, rois, go) in enumerate(inp["track"]):
             rec = record_dom and n == 0
-            jobs.append(lambda fm=fm, rois=rois, go=go, rec=rec: (
-                timed("roipool_fwd", rec, lambda: rp.roipool_forward(fm, rois, K)),
-                timed("roipool_bwd", rec, lambda: rp.roipool_backward(go, rois, H, W))))
+            if fused:
+                jobs.append(lambda fm=fm, rois=rois, rec=rec: (
+                    timed("th_fwd", rec, lambda: th.track_head_forward(fm, rois, inp["fc_w"], inp["fc_b"], K)),
+                    timed("th_bwd", rec, lambda: th.track_head_backward(inp["fc_go"], fm, rois, inp["fc_w"], K))))
+            else:
+                jobs.append(lambda fm=fm, rois=rois, go=go, rec=rec: (
+                    timed("roipool_fwd", rec, lambda: rp.roipool_forward(fm, rois, K)),
+                    timed("roipool_bwd", rec, lambda: rp.roipool_backward(go, rois, H, W))))
         for j, job in enumerate(jobs):
             with torch.cuda.stream(use[j % len(use)]):
                 keep.append(job())
@@ -286,52 +530,60 @@ def run_ours(args):
     # ---- device-resident throughput -------------------------------------------------------------
     # The step is 86 op calls / ~190 kernel launches, many of them tiny (PSROIPool); it is captured once into a
     # CUDA graph and replayed, so the timed region measures the kernels, not Python launch overhead.
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    graph, keep_graph = None, None
-    if not args.no_graph:
+    def capture(fused):
+        for _ in range(args.warmup):
+            step(fused=fused)
+        barrier()
+        if args.no_graph:
+            return None, None
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                step()                                   # allocator warm-up on the capture stream
+                step(fused=fused)                        # allocator warm-up on the capture stream
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                keep_graph = step()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                keep = step(fused=fused)
             for _ in range(2):
-                graph.replay()
+                gr.replay()
             torch.cuda.synchronize()
+            return gr, keep
         except Exception as exc:  # pragma: no cover - fall back to eager launches, say so in the JSON
             print(f"[bench] CUDA graph capture failed ({exc!r}); timing eager launches", file=sys.stderr)
-            graph = None
             torch.cuda.synchronize()
-    barrier()
+            return None, None
+
+    def run_timed(gr, fused):
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(args.steps):
+            if gr is not None:
+                gr.replay()
+            else:
+                step(fused=fused)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    graph, keep_graph = capture(False)
+    graph_f, keep_graph_f = capture(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
-    e0, e1 = ev(), ev()
-    e0.record()
-    if graph is not None:
-        for _ in range(args.steps):
-            graph.replay()
-    else:
-        for _ in range(args.steps):
-            step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = run_timed(graph, False)
+    ms_fused = run_timed(graph_f, True)
     # launches per step: counted on an eager step (a replayed graph launches the same kernels)
     l0 = _lib.launch_count()
     step()
     torch.cuda.synchronize()
     launches = (_lib.launch_count() - l0) * args.steps
     # per-kernel times, live: CUDA events around the calls (eager, same process, right after the timed steps)
-    for _ in range(max(3, args.steps)):
+    for _ in range(max(3, min(args.steps, 10))):
         step(record_dom=True)
+        step(record_dom=True, fused=True)
     torch.cuda.synchronize()
     med = lambda key: sorted(a.elapsed_time(b) for a, b in dom[key])[len(dom[key]) // 2] * 1e-3  # seconds
     clocks = sampler.stop() if rank == 0 else None
@@ -340,7 +592,16 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 5))
     e2e_ms, h2d, d2h, e2e_mode = run_e2e(torch, dev, d2t, e2e_steps, barrier, rank, world)
 
-    ms, e2e_ms = global_max([ms, e2e_ms], dev)
+    # ---- BASELINE config 5: full train step (all ranks: it contains the DDP all-reduce) -----------
+    train = None
+    if not args.no_train:
+        try:
+            train = run_train_step(torch, dev, rank, world, barrier)
+        except Exception as exc:  # the op benchmark must not be lost to a problem in the (torchvision-based) model leg
+            print(f"[bench] train_step leg failed: {exc!r}", file=sys.stderr, flush=True)
+            train = {"error": repr(exc)}
+
+    ms, ms_fused, e2e_ms = global_max([ms, ms_fused, e2e_ms], dev)
 
     if rank == 0:
         peaks = {}
@@ -363,26 +624,43 @@ def run_ours(args):
         t_cf, t_cb = med("corr_fwd"), med("corr_bwd")
         corr_bytes = (B * H * W * k2 + 2 * B * C5 * H * W) * 4
         flops = 2.0 * C5 * P
+        # PSROIPool, 16 frames per call (touched channels + outputs + RoIs)
+        NF = 2 * PAIRS_PER_GPU
+        ps_bytes = {"cls": ((608 * H * W + R * N_CLS * K * K) * 4 + R * 16, (N_CLS * K * K * H * W + R * N_CLS * K * K) * 4 + R * 16),
+                    "reg": ((117 * H * W + R * N_REG * K * K) * 4 + R * 16, (N_REG * K * K * H * W + R * N_REG * K * K) * 4 + R * 16)}
+        # fused track head: three 1.77 GFLOP contractions (forward Z, grad_fm, grad_weight)
+        th_flops = 2.0 * (H * W) * (4 * K * K) * TRACK_C
+
+        def hbm_row(kernel, nbytes, t, **kw):
+            return dict({"bound": "hbm", "kernel": kernel, "achieved": nbytes / t * 1e-9, "peak": hbm, "unit": "GB/s",
+                         "frac": nbytes / t * 1e-9 / hbm, "us_per_launch": t * 1e6, "algorithmic_bytes": nbytes}, **kw)
+
         line = {
             "metric": METRIC, "value": job_throughput(world, args.steps, ms), "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "rois": R, "d_max": D, "r_hw": K,
-                       "l2": "per-step working set > 2 GB, far above the 126 MB L2 (no explicit flush needed)",
-                       "launch": ("one CUDA graph replay per step" if graph is not None else "eager launches") +
-                                 f", independent ops on {n_streams} streams",
-                       "parallelism": f"{world} independent pair shards, no data-path collective"},
+            "config": base_config(),
+            "arm": {"launch": ("one CUDA graph replay per step" if graph is not None else "eager launches") +
+                              f", independent ops on {n_streams} streams",
+                    "parallelism": f"{world} independent pair shards, no data-path collective"},
+            "fused": {"value": job_throughput(world, args.steps, ms_fused), "unit": "frame-pairs/s",
+                      "ms_per_step": ms_fused / args.steps,
+                      "what": "same step, but config 4 (track head) runs the fused ROIPool->Linear(92659,4) operator "
+                              "(d2t_trackhead_*_f32): forward + grad_fm + grad_weight + grad_bias, the pooled 111 MB tensor "
+                              "is never formed; `value` keeps the API-parity ROIPool op (and leaves the Linear to the caller)",
+                      "us_fwd": med("th_fwd") * 1e6, "us_bwd": med("th_bwd") * 1e6,
+                      "us_parity_roipool_fwd_bwd": (t_rpf + t_rpb) * 1e6},
             "roofline": {"bound": "hbm", "kernel": "roipool_vec2_bwd_kernel (track head: C=1891, R=300, 38x63)",
                          "achieved": rp_bytes / t_rpb * 1e-9, "peak": hbm, "unit": "GB/s",
                          "frac": rp_bytes / t_rpb * 1e-9 / hbm, "traffic": 115.69e6, "peak_source": which,
                          "us_per_launch": t_rpb * 1e6, "algorithmic_bytes": rp_bytes,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
                                            "(profiles/r1_ncu_pool_v5_summary.txt)",
-                         "note": "largest share of the step (8 launches); bound in practice by warp-serial shared-memory "
-                                 "read-modify-write chains (5 warps per scheduler, 53 % issue), see DESIGN.md section 2.3"},
+                         "note": "largest share of the `value` step (8 launches); bound in practice by warp-serial shared-memory "
+                                 "read-modify-write chains (5 warps per scheduler, 53 % issue), see DESIGN.md section 2.3; "
+                                 "the fused track head (`fused`) removes this kernel from the model path"},
             "roofline_other": [
-                {"bound": "hbm", "kernel": "roipool_vec_fwd_kernel<7>", "achieved": rp_bytes / t_rpf * 1e-9, "peak": hbm,
-                 "unit": "GB/s", "frac": rp_bytes / t_rpf * 1e-9 / hbm, "us_per_launch": t_rpf * 1e6},
+                hbm_row("roipool_vec_fwd_kernel<7>", rp_bytes, t_rpf),
                 {"bound": "tensor", "kernel": "corr_bwd_umma_kernel<0|1> (c5: C=2048, B=8; 3xTF32, 2 launches + flip)",
                  "achieved": 2 * flops / t_cb * 1e-12, "peak": tf32_peak, "unit": "TFLOP/s",
                  "frac": 2 * flops / t_cb * 1e-12 / tf32_peak, "us_per_call": t_cb * 1e6,
@@ -392,13 +670,23 @@ def run_ours(args):
                  "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t_cf * 1e-12 / fp32_peak,
                  "us_per_launch": t_cf * 1e6, "hbm_gbs": corr_bytes / t_cf * 1e-9,
                  "peak_source": "measured FFMA micro-benchmark (profiles/r1_microbench.txt)"},
+                hbm_row("psb_fwd_kernel (+edges), cls head, 16 frames per call", NF * ps_bytes["cls"][0], med("ps_cls_fwd")),
+                hbm_row("psb_bwd_kernel (+edges, scale, rowlists), cls head, 16 frames per call", NF * ps_bytes["cls"][1], med("ps_cls_bwd")),
+                hbm_row("psb_fwd_kernel (+edges), box head, 16 frames per call", NF * ps_bytes["reg"][0], med("ps_reg_fwd")),
+                hbm_row("psb_bwd_kernel (+edges, scale, rowlists), box head, 16 frames per call", NF * ps_bytes["reg"][1], med("ps_reg_bwd")),
+                {"bound": "tensor", "kernel": "fused track head forward (layout + gemm_tf32x3_kernel<208> + reduce + pool; 3xTF32)",
+                 "achieved": th_flops / med("th_fwd") * 1e-12, "peak": tf32_peak, "unit": "TFLOP/s",
+                 "frac": th_flops / med("th_fwd") * 1e-12 / tf32_peak, "us_per_call": med("th_fwd") * 1e6},
+                {"bound": "tensor", "kernel": "fused track head backward (gZ + 2 x gemm_tf32x3_kernel + layout + reduce; 3xTF32)",
+                 "achieved": 2 * th_flops / med("th_bwd") * 1e-12, "peak": tf32_peak, "unit": "TFLOP/s",
+                 "frac": 2 * th_flops / med("th_bwd") * 1e-12 / tf32_peak, "us_per_call": med("th_bwd") * 1e6},
             ],
             "e2e": {"value": job_throughput(world, e2e_steps, e2e_ms), "unit": "frame-pairs/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "launch": e2e_mode,
                     "collective": ("NCCL all-reduce (average) of the tracker's parameter gradients once per step"
                                    if world > 1 else "none (1 GPU)")},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "train_step": train,
         }
         if world == 1 and not args.no_cpu:
             pps, sec, cores = time_cpu(steps=2, warmup=1)
@@ -407,6 +695,10 @@ def run_ours(args):
                                               "oracle/d2t_oracle.c with OpenMP on all host cores"}
         else:
             line["cpu_baseline"] = None
+        if world == 1 and not args.no_per_config:
+            # after every timed region: configs 1-4 one by one, then the reference's own CUDA kernels on this GPU
+            line["per_config"] = run_per_config(torch, dev, hbm, fp32_peak, tf32_peak, cpu=not args.no_cpu)
+            line["reference_gpu"] = run_reference_gpu(torch, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -624,6 +916,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a replayed CUDA graph")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-5 train-step leg")
+    ap.add_argument("--no-per-config", action="store_true", help="skip per_config and reference_gpu")
     ap.add_argument("--streams", type=int, default=3, help="streams the independent ops of a step are issued on")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

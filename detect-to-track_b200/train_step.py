@@ -1,0 +1,201 @@
+"""BASELINE config 5: the full D&T R-FCN training step on synthetic frame pairs, data-parallel over frame-pair shards.
+
+What is restated here and why (SURVEY.md section 2, rows marked "re-stated for config 5"): the reference's trainer
+(`trainer.py:133-281`) needs ImageNet VID, `ml_utils` (absent) and pretrained weights (no network), so the step is
+rebuilt around the SAME module graph with synthetic inputs:
+
+    backbone    torchvision ResNet (`weights=None`), FrozenBatchNorm, layer4 dilated, returns c3/c4/c5, stages below
+                `first_trainable_stage` frozen                                             models/resnet.py:12-39
+    rpn         3x3 conv + two 1x1 convs + softmax over (object, not object)               models/rpn.py:9-52
+    rcnn        `RFCN` of this package (PSROIPool heads)                                   models/rfcn.py:46-84
+    c_tracker   `CorrelationTracker` of this package (PointwiseCorrelation + ROIPool)      models/correlation_tracker.py:13-87
+    losses      focal / masked smooth-L1 / smooth-L1, coefficients [1, 1, 1, 1, 1e-4]      loss.py:13-182, cfg/default.yaml:38
+    optimiser   SGD lr 1e-2, momentum 0.9, weight decay 1e-4                               cfg/default.yaml:40-43
+
+The RoIs and the regression / classification targets are fixed synthetic tensors (the reference decodes RPN outputs on
+the host through `ml_utils`; that glue is out of scope and its semantics are unpinned).  One
+minibatch = `pairs` frame pairs per rank: the losses of all pairs are summed and ONE backward runs, like
+`DetectTrackTrainer._minibatch_loss` / `train` (`trainer.py:258-281`).  Data parallelism: one process per GPU, the
+step module wrapped in `torch.nn.parallel.DistributedDataParallel` (NCCL): bucketed gradient all-reduce overlapped with
+the backward, nothing else crosses GPUs.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict, List, Tuple
+
+import torch
+from torch import Tensor, nn
+from torch.nn.functional import relu, softmax
+
+from .models import RFCN, CorrelationTracker
+
+N_ANCHORS = 15            # 5 areas x 3 aspect ratios (cfg/default.yaml:12-13)
+LOSS_COEFS = (1.0, 1.0, 1.0, 1.0, 1.0e-4)
+
+
+class Normalizer(nn.Module):
+    """per-channel (x - mean) / std with the ImageNet statistics (stands in for ml_utils.torch.modules.Normalizer,
+    resnet.py:34; the source of ml_utils is not available, so its exact constants are unpinned)"""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+
+    def forward(self, x: Tensor) -> Tensor:
+        return (x - self.mean) / self.std
+
+
+def resnet_backbone(backbone_arch: str = "resnet101", first_trainable_stage: int = 3) -> nn.Module:
+    """models/resnet.py:12-39 with `weights=None` (random init: there is no network for checkpoints)."""
+    from torchvision.models import resnet
+    from torchvision.models._utils import IntermediateLayerGetter
+    from torchvision.ops.misc import FrozenBatchNorm2d
+
+    net = resnet.__dict__[backbone_arch](weights=None, norm_layer=FrozenBatchNorm2d,
+                                         replace_stride_with_dilation=(False, False, True))
+    net.eval()
+    for name, prm in net.named_parameters():
+        m = re.search(r"layer(\d)", name)
+        if not (m and int(m.group(1)) >= first_trainable_stage):
+            prm.requires_grad_(False)
+    getter = IntermediateLayerGetter(net, {"layer2": "c3", "layer3": "c4", "layer4": "c5"})
+    return nn.Sequential(Normalizer(), getter)
+
+
+class RPN(nn.Module):
+    """models/rpn.py:9-52."""
+
+    def __init__(self, in_channels: int, n_anchors: int) -> None:
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, 512, kernel_size=3, padding=1)
+        self.cls_fc = nn.Conv2d(512, 2 * n_anchors, kernel_size=1)
+        self.reg_fc = nn.Conv2d(512, 4 * n_anchors, kernel_size=1)
+
+    @staticmethod
+    def _flatten(x: Tensor, per_anchor: int) -> Tensor:
+        x = x.permute(0, 2, 3, 1).contiguous()
+        return x.view(x.size(0), -1, per_anchor)
+
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        x = relu(self.conv(x))
+        o_hat = softmax(self._flatten(self.cls_fc(x), 2), dim=2)
+        b_hat = self._flatten(self.reg_fc(x), 4)
+        return o_hat, b_hat, x
+
+
+class DetectTrackModule(nn.Module):
+    """models/detect_track.py:52-61: container of backbone, rpn, rcnn, c_tracker (same attribute names, so a reference
+    state_dict's keys line up).  `fused_tracker=True` selects the fused track head + glue (extension)."""
+
+    def __init__(self, backbone_arch: str = "resnet101", first_trainable_stage: int = 3, n_anchors: int = N_ANCHORS,
+                 n_classes: int = 30, k: int = 7, d_max: int = 8, r_hw: int = 7, fused_tracker: bool = False) -> None:
+        super().__init__()
+        self.backbone = resnet_backbone(backbone_arch, first_trainable_stage)
+        self.rpn = RPN(1024, n_anchors)
+        self.rcnn = RFCN(2048, n_classes, k)
+        self.c_tracker = CorrelationTracker(d_max, r_hw, self.rpn.conv.out_channels, fused=fused_tracker)
+
+
+# ---- losses (loss.py) ---------------------------------------------------------------------------------------------
+def focal_loss(c_hat: Tensor, c_star: Tensor, alpha: float = 0.25, gamma: float = 2.0) -> Tensor:
+    """loss.py:13-47: c_hat (.., |A|, C) probabilities, c_star (.., |A|) int64 -> (.., |A|)."""
+    one_hot = torch.zeros_like(c_hat).scatter_(-1, c_star.unsqueeze(-1), 1)
+    pt = torch.where(one_hot == 1, 1 - c_hat, c_hat)
+    at = torch.where(one_hot == 1, torch.full_like(c_hat, 1 - alpha), torch.full_like(c_hat, alpha))
+    bce = nn.functional.binary_cross_entropy(c_hat, one_hot, reduction="none")
+    return (pt.pow(gamma) * at * bce).mean(-1)
+
+
+def bbox_loss(b_hat: Tensor, b_star: Tensor, c_star: Tensor) -> Tensor:
+    """loss.py:50-70: smooth L1 averaged over the 4 offsets, zero at negative anchors."""
+    l1 = nn.functional.smooth_l1_loss(b_hat, b_star, reduction="none").mean(-1)
+    return torch.where(c_star == 0, torch.zeros_like(l1), l1)
+
+
+# ---- synthetic minibatch ------------------------------------------------------------------------------------------
+def synthetic_rois(n: int, generator: torch.Generator) -> Tensor:
+    """fractional ijhw boxes that stay inside the frame (centres U(0.1, 0.9), sizes U(0.05, 0.6), clipped): a RoI crossing
+    the bottom / right border has empty ROIPool bins, which are NaN in the reference"""
+    c = torch.rand(n, 2, generator=generator) * 0.8 + 0.1
+    s = torch.rand(n, 2, generator=generator) * 0.55 + 0.05
+    half = s / 2
+    c = torch.minimum(torch.maximum(c, half), 1.0 - half)
+    return torch.cat([c, s], 1)
+
+
+def synthetic_batch(pairs: int, height: int, width: int, n_rois: int, n_classes: int, seed: int, device=None,
+                    pin: bool = False) -> List[Dict[str, Tensor]]:
+    """`pairs` frame pairs: images (2, 3, H, W) in [0, 1], RPN targets over |A| = 15 * (H/16) * (W/16) anchors, RoIs and
+    R-CNN targets per frame, track RoIs and track targets.  Host tensors (optionally pinned) unless `device` is given."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    fh, fw = height // 16, width // 16
+    A = N_ANCHORS * fh * fw
+    batch = []
+    for _ in range(pairs):
+        item = {
+            "x": torch.rand(2, 3, height, width, generator=g),
+            "lw_rpn": torch.rand(2, A, generator=g),
+            "c_star_rpn": (torch.rand(2, A, generator=g) < 0.05).long(),
+            "b_star_rpn": torch.randn(2, A, 4, generator=g) * 0.1,
+            "rois": torch.stack([synthetic_rois(n_rois, g) for _ in range(2)]),
+            "c_star_rcnn": torch.randint(0, n_classes + 1, (2 * n_rois,), generator=g),
+            "b_star_rcnn": torch.randn(2 * n_rois, 4, generator=g) * 0.1,
+            "track_rois": synthetic_rois(n_rois, g),
+            "t_star": torch.randn(n_rois, 4, generator=g) * 0.1,
+        }
+        if pin:
+            item = {k: v.pin_memory() for k, v in item.items()}
+        if device is not None:
+            item = {k: v.to(device) for k, v in item.items()}
+        batch.append(item)
+    return batch
+
+
+class DetectTrackTrainStep(nn.Module):
+    """forward(minibatch) -> (total loss, the five loss terms): `_forward_loss` of the reference trainer per pair
+    (trainer.py:133-256) with the host-side label encoders / region filters replaced by the synthetic targets, summed over
+    the minibatch (trainer.py:258-266).  Wrapping THIS module in DistributedDataParallel gives the data-parallel step."""
+
+    def __init__(self, model: DetectTrackModule, coefs=LOSS_COEFS) -> None:
+        super().__init__()
+        self.model = model
+        self.coefs = coefs
+
+    def pair_losses(self, item: Dict[str, Tensor]) -> Tuple[Tensor, ...]:
+        m = self.model
+        fmaps = m.backbone(item["x"])                                   # c3 (2,512,H/8,W/8), c4 (2,1024,H/16,..), c5 (2,2048,..)
+        o_hat, b_hat, fm_reg = m.rpn(fmaps["c4"])
+        o_loss = (item["lw_rpn"] * focal_loss(o_hat, item["c_star_rpn"])).mean()
+        b_loss_rpn = bbox_loss(b_hat, item["b_star_rpn"], item["c_star_rpn"]).mean()
+        c5_0, c5_1 = fmaps["c5"]
+        c0, b0 = m.rcnn(c5_0, item["rois"][0])
+        c1, b1 = m.rcnn(c5_1, item["rois"][1])
+        c_hat, bb_hat = torch.cat([c0, c1])[None], torch.cat([b0, b1])[None]
+        c_star = item["c_star_rcnn"][None]
+        c_loss = focal_loss(c_hat, c_star).mean()
+        b_loss_rcnn = bbox_loss(bb_hat, item["b_star_rcnn"][None], c_star).mean()
+        pyr0 = {k: fmaps[k][0] for k in ("c3", "c4", "c5")}
+        pyr1 = {k: fmaps[k][1] for k in ("c3", "c4", "c5")}
+        t_hat = m.c_tracker(pyr0, pyr1, fm_reg[0], fm_reg[1], item["track_rois"])
+        t_loss = nn.functional.smooth_l1_loss(t_hat, item["t_star"], reduction="none").mean()
+        return o_loss, b_loss_rpn, c_loss, b_loss_rcnn, t_loss
+
+    def forward(self, minibatch: List[Dict[str, Tensor]]) -> Tuple[Tensor, Tensor]:
+        terms = None
+        for item in minibatch:
+            cur = torch.stack(self.pair_losses(item))
+            terms = cur if terms is None else terms + cur
+        coefs = torch.as_tensor(self.coefs, dtype=terms.dtype, device=terms.device)
+        return (terms * coefs).sum(), terms.detach()
+
+
+def make_optimizer(step_module: nn.Module) -> torch.optim.Optimizer:
+    """cfg/default.yaml:40-43"""
+    params = [p for p in step_module.parameters() if p.requires_grad]
+    return torch.optim.SGD(params, lr=1e-2, momentum=0.9, weight_decay=1e-4)
+
+
+def trainable_parameter_bytes(step_module: nn.Module) -> int:
+    return sum(p.numel() * p.element_size() for p in step_module.parameters() if p.requires_grad)

@@ -673,19 +673,13 @@ def test_psroipool_batched_module_autograd(cuda):
         d2t.PSROIPoolBatched(nT, k)(fm[:, :-1].contiguous(), rois)
 
 
-def test_psroipool_legacy_kernels_still_match(cuda, monkeypatch):
-    """a NULL workspace keeps the per-output kernels of pool.cu (the float64 path): same results."""
-    from detect_to_track_b200 import _lib
+def test_psroipool_single_frame_and_batched_kernels_agree(cuda):
+    """the single-frame entry point runs the per-output kernel, the batched one the channel-owner kernels: bit-identical"""
     nT, H, W, k = 4, 38, 63, 7
     rois = _roipool_rois(H, W, np.float32, R=60)
-    fm, go = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 37, np.float32)
-    tf, tr, tg = dev(fm, cuda), dev(rois, cuda), dev(go, cuda)
-    lib = _lib.lib()
-    out = torch.empty((rois.shape[0], nT, k, k), device=cuda)
-    rc = lib.d2t_psroipool_fwd_f32(tf.data_ptr(), tr.data_ptr(), out.data_ptr(), rois.shape[0], nT, H, W, k, 0, None, 0,
-                                   torch.cuda.current_stream().cuda_stream)
-    assert rc == 0, _lib.last_error()
-    assert torch.equal(out, ps_mod.ps_roipool_forward(tf, tr, nT, k))
+    fm, _ = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 37, np.float32)
+    tf, tr = dev(fm, cuda), dev(rois, cuda)
+    assert torch.equal(ps_mod.ps_roipool_forward(tf, tr, nT, k), ps_mod.ps_roipool_forward_batched(tf[None], tr[None], nT, k)[0])
 
 
 # ------------------------------------------------------------------ error behaviour + autograd wiring
