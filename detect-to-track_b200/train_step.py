@@ -56,6 +56,15 @@ def resnet_backbone(backbone_arch: str = "resnet101", first_trainable_stage: int
     net = resnet.__dict__[backbone_arch](weights=None, norm_layer=FrozenBatchNorm2d,
                                          replace_stride_with_dilation=(False, False, True))
     net.eval()
+    # FrozenBatchNorm with its default statistics is the identity, so a randomly initialised 101-layer residual stack
+    # doubles its activation variance block after block and overflows FP32 (the reference never sees this: it loads
+    # pretrained weights and statistics).  Damping the last frozen-BN scale of every residual branch keeps the
+    # synthetic step finite without touching the architecture, the shapes or the work done.
+    for mod in net.modules():
+        if isinstance(mod, resnet.Bottleneck):
+            mod.bn3.weight.fill_(0.25)
+        elif isinstance(mod, resnet.BasicBlock):
+            mod.bn2.weight.fill_(0.25)
     for name, prm in net.named_parameters():
         m = re.search(r"layer(\d)", name)
         if not (m and int(m.group(1)) >= first_trainable_stage):
