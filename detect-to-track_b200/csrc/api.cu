@@ -89,6 +89,7 @@ int pool_bins_launch(const T*, int32_t*, int, int, int, int, int, cudaStream_t);
 size_t psroipool_bwd_ws_bytes(int R, int nT, int H, int W, int k, int elem);
 // batched float32 PSROIPool (pool_ps.cu)
 bool psb_supported(int N, int R, int nT, int H, int W, int k);
+bool psb_bwd_supported(int N, int R, int nT, int H, int W, int k);
 size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd);
 int psb_fwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 int psb_bwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
@@ -267,12 +268,10 @@ int d2t_roipool_bwd_f64(const double* grad_out, const double* rois, double* grad
 }
 
 // ---- PSROIPool -----------------------------------------------------------------------
-static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 size_t d2t_psroipool_fwd_workspace_bytes(int, int, int, int, int, int) { return 0; }
 size_t d2t_psroipool_bwd_workspace_bytes(int R, int n_targets, int H, int W, int r_hw, int elem_size) {
-    size_t n = psroipool_bwd_ws_bytes(R, n_targets, H, W, r_hw, elem_size);
-    if (elem_size == 4 && psb_supported(1, R, n_targets, H, W, r_hw)) n = max_sz(n, psb_ws_bytes(1, R, n_targets, H, W, r_hw, true));
-    return n;
+    if (elem_size == 4 && psb_bwd_supported(1, R, n_targets, H, W, r_hw)) return psb_ws_bytes(1, R, n_targets, H, W, r_hw, true);
+    return psroipool_bwd_ws_bytes(R, n_targets, H, W, r_hw, elem_size);
 }
 
 int d2t_psroipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int n_targets, int H, int W, int r_hw,
@@ -291,7 +290,8 @@ int d2t_psroipool_fwd_f64(const double* fm, const double* rois, double* out, int
 }
 int d2t_psroipool_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int R, int n_targets, int H, int W,
                           int r_hw, int flags, void* ws, size_t ws_bytes, void* stream) {
-    if (ws && psb_supported(1, R, n_targets, H, W, r_hw) && ws_bytes >= psb_ws_bytes(1, R, n_targets, H, W, r_hw, true))
+    D2T_REQUIRE(R >= 0 && n_targets > 0 && H > 0 && W > 0 && r_hw > 0, "d2t_psroipool_bwd_f32: bad shape");
+    if (R > 0 && psb_bwd_supported(1, R, n_targets, H, W, r_hw))   // channel-owner kernels (pool_ps.cu): one launch, usually no workspace
         return psb_bwd_launch(grad_out, rois, grad_fm, 1, R, n_targets, H, W, r_hw, flags, ws, ws_bytes, (cudaStream_t)stream);
     return psroipool_bwd_launch<float>(grad_out, rois, grad_fm, R, n_targets, H, W, r_hw, flags, ws, ws_bytes,
                                        (cudaStream_t)stream);
@@ -308,7 +308,7 @@ size_t d2t_psroipool_fwd_batched_workspace_bytes(int N, int R, int n_targets, in
     return 0;
 }
 size_t d2t_psroipool_bwd_batched_workspace_bytes(int N, int R, int n_targets, int H, int W, int r_hw, int elem_size) {
-    if (elem_size == 4 && psb_supported(N, R, n_targets, H, W, r_hw)) return psb_ws_bytes(N, R, n_targets, H, W, r_hw, true);
+    if (elem_size == 4 && psb_bwd_supported(N, R, n_targets, H, W, r_hw)) return psb_ws_bytes(N, R, n_targets, H, W, r_hw, true);
     return psroipool_bwd_ws_bytes(R, n_targets, H, W, r_hw, elem_size);
 }
 int d2t_psroipool_fwd_batched_f32(const float* fm, const float* rois, float* out, int N, int R, int n_targets, int H, int W,
@@ -330,7 +330,7 @@ int d2t_psroipool_bwd_batched_f32(const float* grad_out, const float* rois, floa
     D2T_REQUIRE(N >= 0 && R >= 0 && n_targets > 0 && H > 0 && W > 0 && r_hw > 0, "d2t_psroipool_bwd_batched_f32: bad shape");
     if (N == 0) return D2T_OK;
     const size_t nCh = (size_t)n_targets * r_hw * r_hw;
-    if (R > 0 && psb_supported(N, R, n_targets, H, W, r_hw))
+    if (R > 0 && psb_bwd_supported(N, R, n_targets, H, W, r_hw))
         return psb_bwd_launch(grad_out, rois, grad_fm, N, R, n_targets, H, W, r_hw, flags, ws, ws_bytes, (cudaStream_t)stream);
     for (int n = 0; n < N; ++n) {
         int rc = psroipool_bwd_launch<float>(grad_out + n * nCh * R, rois + (size_t)n * R * 4, grad_fm + n * nCh * H * W, R,

@@ -136,12 +136,16 @@ roipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __re
 template <typename T>
 __global__ void __launch_bounds__(kSlabThreads)
 roipool_bwd_kernel(const T* __restrict__ go, const T* __restrict__ rois, T* __restrict__ gin, int R, int C, int H,
-                   int W, int k, int CB, int RCH, FastDiv dW) {
+                   int W, int k, int CB, int RCH, FastDiv dW, int bandRows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* acc = reinterpret_cast<T*>(smem_raw);
-    const int HW = H * W;
+    // blockIdx.y selects a band of `bandRows` pixel rows (one band = the whole plane unless the plane is too large for
+    // shared memory): the CTA then owns rows [y0, y0 + HB) of its channels and clips every bin to them
+    const int y0 = blockIdx.y * bandRows;
+    const int HB = min(bandRows, H - y0);
+    const int HW = HB * W;   // pixels of the band
     const int kk = k * k;
-    T* sinv = reinterpret_cast<T*>(smem_raw + align_up_dev((size_t)CB * HW * sizeof(T), 16));
+    T* sinv = reinterpret_cast<T*>(smem_raw + align_up_dev((size_t)CB * bandRows * W * sizeof(T), 16));
     short* sI0 = reinterpret_cast<short*>(reinterpret_cast<unsigned char*>(sinv) + align_up_dev((size_t)RCH * kk * sizeof(T), 16));
     short* sI1 = sI0 + RCH * k;
     short* sJ0 = sI1 + RCH * k;
@@ -189,16 +193,46 @@ roipool_bwd_kernel(const T* __restrict__ go, const T* __restrict__ rois, T* __re
                 const short* I0 = sI0 + rr * k;
                 const short* I1 = sI1 + rr * k;
                 for (int i = 0; i < k; ++i) {
+                    const int r0 = max((int)I0[i], y0), r1 = min((int)I1[i], y0 + HB);
+                    if (r0 >= r1) continue;
                     T u = 0;
                     for (int j = jlo; j <= jhi; ++j) u += __ldg(g + i * k + j) * inv[i * k + j];
-                    for (int pi = I0[i]; pi < I1[i]; ++pi) a[pi * W] += u;
+                    for (int pi = r0; pi < r1; ++pi) a[(pi - y0) * W] += u;
                 }
             }
         }
     }
     __syncthreads();
-    T* dst = gin + (size_t)c0 * HW;
-    for (int idx = threadIdx.x; idx < cb * HW; idx += blockDim.x) dst[idx] = acc[idx];
+    for (int idx = threadIdx.x; idx < cb * HW; idx += blockDim.x) {
+        const int cc = idx / HW, rem = idx - cc * HW;
+        gin[((size_t)(c0 + cc) * H + y0) * W + rem] = acc[idx];
+    }
+}
+
+// ROIPool forward straight from global memory, one thread per output element like the reference kernel
+// (roipool_cuda.cu:6-63): only for planes too large for the shared-memory slab kernels.
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+roipool_fwd_global_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __restrict__ out, long long total, int C,
+                          int H, int W, int k) {
+    const int kk = k * k;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx % kk);
+        const long long rc = idx / kk;
+        const int c = (int)(rc % C), r = (int)(rc / C);
+        const int i = b / k, j = b - i * k;
+        const T* roi = rois + (size_t)r * 4;
+        int i0, i1, j0, j1;
+        bin_edge<T, true>(roi[0], roi[2], i, k, H, i0, i1);
+        bin_edge<T, true>(roi[1], roi[3], j, k, W, j0, j1);
+        const T* p = fm + (size_t)c * H * W;
+        T acc = 0;
+        for (int pi = i0; pi < i1; ++pi)
+            for (int pj = j0; pj < j1; ++pj) acc += __ldg(p + (size_t)pi * W + pj);
+        const int numel = (i1 - i0) * (j1 - j0);
+        acc /= numel;  // 0/0 = NaN like roipool_cuda.cu:61
+        out[idx] = acc;
+    }
 }
 
 // =================================================================================
@@ -247,7 +281,7 @@ psroipool_fwd_kernel(const T* __restrict__ fm, const T* __restrict__ rois, T* __
 struct PsBwdWs {
     short4* edges;    // [R][k]       {I0, I1, J0, J1} of row-bin b / column-bin b
     uint2* list;      // [k*k][H][R]  per (bin b, pixel row y): ascending RoIs whose row-bin covers y and whose
-                      //              column-bin is non-empty, packed {r | J0 << 16 | J1 << 24, r * nT * k*k}
+                      //              column-bin is non-empty, packed {r, J0 | J1 << 16}
     int* cnt;         // [k*k][H]
     int* entCount;    // [nCh]        how many (target, bin) pairs read channel ch
     uint32_t* ent;    // [nCh][nT]    those pairs, ascending target: (t << 16) | bin ; t = 0xFFFF => "all targets"
@@ -346,8 +380,7 @@ psroipool_bwd_prep_kernel(const T* __restrict__ go, PsBwdWs ws, int R, int nT, i
             }
             const unsigned bal = __ballot_sync(0xffffffffu, in);
             if (in)
-                list[n + __popc(bal & ((1u << lane) - 1))] =
-                    make_uint2((unsigned)r | ((unsigned)j0 << 16) | ((unsigned)j1 << 24), (unsigned)(r * nT * kk));
+                list[n + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)r, (unsigned)j0 | ((unsigned)j1 << 16));
             n += __popc(bal);
         }
         if (lane == 0) ws.cnt[l] = n;
@@ -387,8 +420,8 @@ psroipool_bwd_kernel(PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int 
 #pragma unroll 4
             for (int n = 0; n < cnt; ++n) {
                 const uint2 e = __ldg(list + n);
-                const int j0 = (e.x >> 16) & 0xff, j1 = e.x >> 24;
-                const T v = __ldg(g + (e.x & 0xffff));
+                const int j0 = e.y & 0xffff, j1 = e.y >> 16;
+                const T v = __ldg(g + e.x);
                 if (xa >= j0 && xa < j1) acca += v;
                 if (xb >= j0 && xb < j1) accb += v;
             }
@@ -397,8 +430,8 @@ psroipool_bwd_kernel(PsBwdWs ws, T* __restrict__ gin, int R, int nT, int H, int 
 #pragma unroll 4
             for (int n = 0; n < cnt; ++n) {
                 const uint2 e = __ldg(list + n);
-                const int j0 = (e.x >> 16) & 0xff, j1 = e.x >> 24;
-                const T v = __ldg(g + e.y);
+                const int j0 = e.y & 0xffff, j1 = e.y >> 16;
+                const T v = __ldg(g + (size_t)e.x * nT * kk);
                 if (xa >= j0 && xa < j1) acca += v;
                 if (xb >= j0 && xb < j1) accb += v;
             }
@@ -481,22 +514,37 @@ struct SlabPlan {
     int RCH;      // RoIs per edge-table chunk
     size_t smem;  // dynamic shared memory bytes
     int grid;
+    int bandRows; // pixel rows per CTA (H unless the plane does not fit shared memory) and number of bands
+    int bands;
 };
 
 // Choose the channel slab so that the grid is one balanced wave when possible.
 // shared memory = CB planes + per-RoI tables for a chunk of RCH RoIs (4 int16 edge arrays + `per_roi` bytes).
-static int plan_slab(int R, int C, int H, int W, int k, size_t elem, size_t per_roi, SlabPlan* plan) {
+// D2T_ERR_WORKSPACE (without an error message) = the plane does not fit: the caller falls back (forward: global-memory
+// kernel; backward: row bands, allow_bands)
+static int plan_slab(int R, int C, int H, int W, int k, size_t elem, size_t per_roi, SlabPlan* plan, bool allow_bands = false) {
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
     const size_t budget = (size_t)di.max_smem_optin - 1024;
     int RCH = R < 256 ? (R > 0 ? R : 1) : 256;
-    const size_t perCB = (size_t)H * W * elem;
+    size_t perCB = (size_t)H * W * elem;
     auto tables = [&](int rch) { return align_up((size_t)rch * per_roi, 16) + align_up((size_t)4 * rch * k * sizeof(short), 16); };
     while (RCH > 8 && perCB + tables(RCH) > budget) RCH /= 2;
+    plan->bandRows = H;
+    plan->bands = 1;
     if (perCB + tables(RCH) > budget) {
-        set_error("feature map plane %dx%d (%zu B) does not fit the %zu B shared-memory slab", H, W, perCB, budget);
-        return D2T_ERR_BAD_ARG;
+        if (!allow_bands) return D2T_ERR_WORKSPACE;
+        RCH = R < 64 ? (R > 0 ? R : 1) : 64;
+        const size_t rowBytes = (size_t)W * elem;
+        if (rowBytes + tables(RCH) > budget) {
+            set_error("roipool: one %d-pixel row (%zu B) does not fit the %zu B shared-memory slab", W, rowBytes, budget);
+            return D2T_ERR_BAD_ARG;
+        }
+        plan->bandRows = (int)((budget - tables(RCH)) / rowBytes);
+        plan->bands = ceil_div(H, plan->bandRows);
+        plan->bandRows = ceil_div(H, plan->bands);   // balanced bands
+        perCB = (size_t)plan->bandRows * rowBytes;
     }
     int maxCB = (int)((budget - tables(RCH)) / perCB);
     int CB = ceil_div(C, di.sm_count);  // one wave, one CTA per SM
@@ -524,6 +572,17 @@ int roipool_fwd_launch(const T* fm, const T* rois, T* out, int R, int C, int H, 
     if (!force_exact && FastPath<T>::fwd(fm, rois, out, R, C, H, W, k, st, &frc)) return frc;
     SlabPlan p;
     int rc = plan_slab(R, C, H, W, k, sizeof(T), 0, &p);
+    if (rc == D2T_ERR_WORKSPACE) {   // plane larger than shared memory: per-output kernel on global memory (same order => same bits)
+        const long long total = (long long)R * C * k * k;
+        DeviceInfo di;
+        if ((rc = device_info(&di))) return rc;
+        long long grid = (total + kPoolThreads - 1) / kPoolThreads;
+        if (grid > (long long)di.sm_count * 16) grid = (long long)di.sm_count * 16;
+        roipool_fwd_global_kernel<T><<<(int)grid, kPoolThreads, 0, st>>>(fm, rois, out, total, C, H, W, k);
+        D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
+        return D2T_OK;
+    }
     if (rc) return rc;
     D2T_SMEM_OPTIN(roipool_fwd_kernel<T>, p.smem);
     roipool_fwd_kernel<T><<<p.grid, kSlabThreads, p.smem, st>>>(fm, rois, out, R, C, H, W, k, p.CB, p.RCH,
@@ -546,11 +605,11 @@ int roipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int C, int H, 
     int frc = 0;
     if (FastPath<T>::bwd(go, rois, gin, R, C, H, W, k, st, &frc)) return frc;
     SlabPlan p;
-    int rc = plan_slab(R, C, H, W, k, sizeof(T), (size_t)k * k * sizeof(T), &p);
+    int rc = plan_slab(R, C, H, W, k, sizeof(T), (size_t)k * k * sizeof(T), &p, true);
     if (rc) return rc;
     D2T_SMEM_OPTIN(roipool_bwd_kernel<T>, p.smem);
-    roipool_bwd_kernel<T><<<p.grid, kSlabThreads, p.smem, st>>>(go, rois, gin, R, C, H, W, k, p.CB, p.RCH,
-                                                                 make_fastdiv(W));
+    roipool_bwd_kernel<T><<<dim3(p.grid, p.bands), kSlabThreads, p.smem, st>>>(go, rois, gin, R, C, H, W, k, p.CB, p.RCH,
+                                                                                make_fastdiv(W), p.bandRows);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;
@@ -617,7 +676,6 @@ int psroipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int nT, int 
     const int nCh = nT * k * k;
     D2T_REQUIRE(nCh <= 65535, "psroipool_bwd: n_targets*r_hw^2 must be <= 65535");
     D2T_REQUIRE((long long)R * nCh < (1ll << 31), "psroipool_bwd: grad_out too large");
-    D2T_REQUIRE(R <= 65535, "psroipool_bwd: at most 65535 RoIs per call");
     if (R == 0) {
         D2T_CUDA_TRY(cudaMemsetAsync(gin, 0, (size_t)nCh * H * W * sizeof(T), st));
         return D2T_OK;
@@ -632,7 +690,6 @@ int psroipool_bwd_launch(const T* go, const T* rois, T* gin, int R, int nT, int 
     DeviceInfo di;
     int drc = device_info(&di);
     if (drc) return drc;
-    D2T_REQUIRE(W <= 255, "psroipool_bwd: W must be <= 255");
     psroipool_bwd_edges_kernel<T><<<ceil_div(R * k, kPoolThreads), kPoolThreads, 0, st>>>(rois, ws, R, H, W, k);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();

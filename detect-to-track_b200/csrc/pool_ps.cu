@@ -295,6 +295,121 @@ psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlis
 }
 
 // ----------------------------------------------------------------------------------------------------
+// backward, second generation: ONE launch, no workspace.  grid (nCh, N): CTA = (channel, frame), 128 threads.
+// ----------------------------------------------------------------------------------------------------
+// Round 1's backward (psb_edges -> psb_scale -> psb_rowlists -> psb_bwd_kernel, kept below as the fallback for RoI counts
+// whose bitmasks do not fit shared memory) spent its time in latency: four launches, row lists and scaled gradients
+// fetched from global memory in dependent steps, one thread per pixel row doing a 63-step serial scan.  Here a CTA
+// derives everything it needs itself:
+//   per user (target t, bin b = (i, j)) of its channel
+//     A  every thread takes RoIs r = tid, tid + 128, ...: bin-row-i and bin-column-j edges with the reference's
+//        expression (ps_roipool_cuda.cu:42-54), v = grad_out[r, t, b] / cell size, stored as {v, j0 | j1 << 16};
+//        the RoI sets bit r of rowmask[y] for its rows y in [i0, i1) with atomicOr -- an INTEGER atomic, so the result
+//        does not depend on arrival order
+//     B  task (y, sign): walks the set bits of rowmask[y] in ascending RoI order and applies  Dp[y][j0] += v  (sign +)
+//        or  Dm[y][j1] += v  (sign -): one owner per (row, sign), fixed order => bitwise reproducible, no FP atomics
+//        (reference: atomicAdd per bin pixel, ps_roipool_cuda.cu:124-139)
+//   then  grad[y][x] = sum_{x' <= x} (Dp[y][x'] - Dm[y][x'])  by a warp-shuffle scan, written coalesced.
+// Channels nobody reads (911 of 1519 for the class head) are zero-filled by their CTA.
+constexpr int kPsb2Threads = 128;
+__global__ void __launch_bounds__(kPsb2Threads)
+psb2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, float* __restrict__ gin, int R, int nT, int H,
+                int W, int k, int canonical) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int kk = k * k;
+    const int pitch = W + 1;
+    const int MW = (R + 31) >> 5;                                     // mask words per pixel row
+    float* Dp = reinterpret_cast<float*>(smem_raw);                   // [H][pitch]
+    float* Dm = Dp + H * pitch;                                       // [H][pitch]
+    uint32_t* rowmask = reinterpret_cast<uint32_t*>(Dm + H * pitch);  // [H][MW]
+    uint2* vj = reinterpret_cast<uint2*>(rowmask + ((H * MW + 1) & ~1));  // [R] {value bits, j0 | j1 << 16}
+    uint32_t* us = reinterpret_cast<uint32_t*>(vj + R);               // [kk]
+    int* cnt = reinterpret_cast<int*>(us + kk);                       // [8]
+    const int nCh = nT * kk;
+    const int ch = blockIdx.x, n = blockIdx.y;
+    const int HW = H * W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* dst = gin + ((size_t)n * nCh + ch) * HW;
+    const int nU = psb_users(ch, nT, kk, canonical != 0, us, cnt);
+    if (nU == 0) {
+        for (int px = tid; px < HW; px += kPsb2Threads) dst[px] = 0.f;
+        return;
+    }
+    for (int idx = tid; idx < 2 * H * pitch; idx += kPsb2Threads) Dp[idx] = 0.f;   // Dp and Dm are contiguous
+    for (int idx = tid; idx < H * MW; idx += kPsb2Threads) rowmask[idx] = 0u;
+    const float* roiBase = rois + (size_t)n * R * 4;
+    const float* goBase = go + (size_t)n * R * nCh;
+    for (int u = 0; u < nU; ++u) {
+        const uint32_t pk = us[u];
+        const int t = pk >> 16, b = pk & 0xffff;
+        const int i = b / k, j = b - i * k;
+        __syncthreads();   // masks cleared / previous user's walk finished
+        for (int r = tid; r < R; r += kPsb2Threads) {
+            const float* roi = roiBase + (size_t)r * 4;
+            int i0, i1, j0, j1;
+            bin_edge<float, false>(__ldg(roi), __ldg(roi + 2), i, k, H, i0, i1);
+            bin_edge<float, false>(__ldg(roi + 1), __ldg(roi + 3), j, k, W, j0, j1);
+            const int numel = (i1 - i0) * (j1 - j0);
+            float v = 0.f;
+            if (numel > 0) {
+                if (t == 0xFFFF) {   // merged channel 0 of the reference map: bin 0 of every target, ascending target
+                    for (int tt = 0; tt < nT; ++tt) v += __ldg(goBase + ((size_t)r * nT + tt) * kk) / numel;
+                } else {
+                    v = __ldg(goBase + ((size_t)r * nT + t) * kk + b) / numel;   // ps_roipool_cuda.cu:134-137
+                }
+                const uint32_t bit = 1u << (r & 31);
+                for (int y = i0; y < i1; ++y) atomicOr(&rowmask[y * MW + (r >> 5)], bit);
+            }
+            vj[r] = make_uint2(__float_as_uint(v), (uint32_t)j0 | ((uint32_t)j1 << 16));
+        }
+        __syncthreads();
+        for (int task = tid; task < 2 * H; task += kPsb2Threads) {
+            const int y = task >> 1, minus = task & 1;
+            float* row = (minus ? Dm : Dp) + y * pitch;
+            uint32_t* mrow = rowmask + y * MW;
+            for (int wd = 0; wd < MW; ++wd) {
+                uint32_t m = mrow[wd];
+                while (m) {
+                    const int r = (wd << 5) + __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint2 q = vj[r];
+                    const int x = minus ? (int)(q.y >> 16) : (int)(q.y & 0xffff);
+                    row[x] += __uint_as_float(q.x);
+                }
+            }
+        }
+        if (u + 1 < nU) {
+            __syncthreads();
+            for (int idx = tid; idx < H * MW; idx += kPsb2Threads) rowmask[idx] = 0u;
+        }
+    }
+    __syncthreads();
+    // inclusive scan along x, a warp per row, 32 columns per step with a carry
+    for (int y = warp; y < H; y += kPsb2Threads / 32) {
+        const float* rp = Dp + y * pitch;
+        const float* rm = Dm + y * pitch;
+        float carry = 0.f;
+        for (int x0 = 0; x0 < W; x0 += 32) {
+            const int x = x0 + lane;
+            float v = x < W ? rp[x] - rm[x] : 0.f;
+#pragma unroll
+            for (int sh = 1; sh < 32; sh <<= 1) {
+                const float o = __shfl_up_sync(0xffffffffu, v, sh);
+                if (lane >= sh) v += o;
+            }
+            v += carry;
+            if (x < W) dst[y * W + x] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+}
+
+static size_t psb2_smem(int R, int H, int W, int k) {
+    const int MW = (R + 31) >> 5;
+    return (size_t)2 * H * (W + 1) * 4 + (size_t)((H * MW + 1) & ~1) * 4 + (size_t)R * 8 + (size_t)k * k * 4 + 64;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------
 struct PsbLayout {
@@ -330,7 +445,17 @@ bool psb_supported(int N, int R, int nT, int H, int W, int k) {
     return fwdSmem <= cap && bwdSmem <= cap;
 }
 
-size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd) { return psb_layout(N, R, nT, H, W, k, bwd).total; }
+static bool psb2_ok(int R, int H, int W, int k);
+bool psb_bwd_supported(int N, int R, int nT, int H, int W, int k) {
+    if (N <= 0 || R <= 0 || nT <= 0 || k <= 0 || H <= 0 || W <= 0 || N > 65535 || nT >= 0xFFFF) return false;
+    if ((long long)nT * k * k > 0x7fffffffLL / 4 || (long long)R * nT * k * k >= (1ll << 31)) return false;
+    return psb2_ok(R, H, W, k) || psb_supported(N, R, nT, H, W, k);
+}
+
+size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd) {
+    if (bwd && psb2_ok(R, H, W, k)) return 0;   // the one-launch backward needs no workspace
+    return psb_layout(N, R, nT, H, W, k, bwd).total;
+}
 
 static int psb_edges_launch(const float* rois, uint32_t* edges, uint32_t* edgesT, int N, int R, int k, int H, int W,
                             cudaStream_t st) {
@@ -360,8 +485,22 @@ int psb_fwd_launch(const float* fm, const float* rois, float* out, int N, int R,
     return D2T_OK;
 }
 
+// the one-launch backward needs its RoI bitmasks and both difference arrays in shared memory, a few CTAs per SM
+static bool psb2_ok(int R, int H, int W, int k) {
+    return W < 65535 && k * k <= kPsb2Threads && psb2_smem(R, H, W, k) <= 56 * 1024;
+}
+
 int psb_bwd_launch(const float* go, const float* rois, float* gin, int N, int R, int nT, int H, int W, int k, int flags,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (psb2_ok(R, H, W, k)) {
+        const size_t smem2 = psb2_smem(R, H, W, k);
+        D2T_SMEM_OPTIN(psb2_bwd_kernel, smem2);
+        psb2_bwd_kernel<<<dim3(nT * k * k, N), kPsb2Threads, smem2, st>>>(go, rois, gin, R, nT, H, W, k,
+                                                                          (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0);
+        D2T_CUDA_TRY(cudaGetLastError());
+        note_launch();
+        return D2T_OK;
+    }
     const PsbLayout L = psb_layout(N, R, nT, H, W, k, true);
     if (!ws || ws_bytes < L.total) {
         set_error("psroipool_bwd (batched): workspace too small (%zu < %zu bytes)", ws_bytes, L.total);

@@ -328,6 +328,40 @@ def test_pooling_on_maps_larger_than_the_packed_edge_range(cuda):
     close(ps_mod.ps_roipool_backward(dev(sgo, cuda), dev(rois, cuda), W, H), oracle.psroipool_bwd(sgo, rois, W, H), np.float32)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_psroipool_backward_on_wide_maps(cuda, dtype):
+    """W above 255: the packed edge fields of every PSROIPool backward path are 16 bits wide now --
+    float32 takes the one-launch channel-owner kernel while the plane fits shared memory and the per-pixel gather
+    kernels beyond that, float64 always the latter."""
+    k, nT = 7, 2
+    for (H, W) in [(12, 300), (40, 700)]:
+        rois = _roipool_rois(H, W, dtype, R=25)
+        _, go = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 43, dtype)
+        got = ps_mod.ps_roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
+        close(got, oracle.psroipool_bwd(go, rois, H, W), dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_roipool_on_planes_larger_than_shared_memory(cuda, dtype):
+    """a 250 x 300 plane (300 KB in float32) does not fit the shared-memory slab of any ROIPool kernel: the
+    forward falls back to the per-output global-memory kernel (bit-identical to the reference order), the backward to
+    row bands of the channel-owner kernel.  Also r_hw = 5 (not the tuned 7)."""
+    C, H, W = 3, 250, 300
+    for k in (7, 5):
+        rois = _roipool_rois(H, W, dtype, R=20)
+        fm, go = cases.pool_inputs(C, H, W, (rois.shape[0], C, k, k), 44, dtype)
+        want = oracle.roipool_fwd(fm, rois, k)
+        out = rp_mod.roipool_forward(dev(fm, cuda), dev(rois, cuda), k, exact=True)
+        if dtype == np.float32:
+            np.testing.assert_array_equal(out.cpu().numpy(), want)
+        else:
+            close(out, want, dtype, scale=float(np.nanmax(np.abs(want))), equal_nan=True)
+        close(rp_mod.roipool_forward(dev(fm, cuda), dev(rois, cuda), k), want, dtype, scale=float(np.nanmax(np.abs(want))), equal_nan=True)
+        gin = rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W)
+        close(gin, oracle.roipool_bwd(go, rois, H, W), dtype)
+        assert torch.equal(gin, rp_mod.roipool_backward(dev(go, cuda), dev(rois, cuda), H, W))
+
+
 def test_corr_bwd_explicit_families_agree(cuda):
     """d2t_corr_bwd_f32_simt (FP32 FMAs) and d2t_corr_bwd_f32_tc (tcgen05, 3xTF32) agree within the FP32 tolerance, and
     the default entry point picks the family the header documents (C >= 128 -> tensor cores, bit-identical to _tc)."""
