@@ -406,6 +406,34 @@ def run_train_step(torch, dev, rank, world, barrier, pairs=PAIRS_PER_GPU, steps=
     return out
 
 
+# --------------------------------------------------------------------------------------------- NUMA placement
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank's host threads to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node and
+    the node's cpulist) BEFORE any pinned buffer is allocated, so that first-touch places the staging memory next to the
+    GPU's PCIe root.  Round 1's e2e leg fed all eight GPUs from whatever node the allocating thread happened to run on and
+    stopped scaling at 4 GPUs (187 GB/s aggregate).  Returns a short description for the JSON line; a no-op when the
+    topology files are missing."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
+        node = int(path.read_text().strip())
+        if node < 0:
+            return "numa_node unknown (-1): not bound"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"node {node}: none of its CPUs is in this process's affinity mask: not bound"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to NUMA node {node} ({len(allowed)} CPUs) of GPU {local_rank}"
+    except Exception as exc:  # topology not exposed in this container
+        return f"not bound ({type(exc).__name__})"
+
+
 # --------------------------------------------------------------------------------------------- multi-rank plumbing
 def global_max(values, device):
     """max over ranks of per-rank device times (the job is as slow as its slowest shard)."""
@@ -463,6 +491,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if not args.no_numa else "disabled (--no-numa)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the extension is missing
@@ -642,7 +671,8 @@ def run_ours(args):
             "config": base_config(),
             "arm": {"launch": ("one CUDA graph replay per step" if graph is not None else "eager launches") +
                               f", independent ops on {n_streams} streams",
-                    "parallelism": f"{world} independent pair shards, no data-path collective"},
+                    "parallelism": f"{world} independent pair shards, no data-path collective",
+                    "host_placement": numa},
             "fused": {"value": job_throughput(world, args.steps, ms_fused), "unit": "frame-pairs/s",
                       "ms_per_step": ms_fused / args.steps,
                       "what": "same step, but config 4 (track head) runs the fused ROIPool->Linear(92659,4) operator "
@@ -916,6 +946,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a replayed CUDA graph")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-train", action="store_true", help="skip the config-5 train-step leg")
     ap.add_argument("--no-per-config", action="store_true", help="skip per_config and reference_gpu")
     ap.add_argument("--streams", type=int, default=3, help="streams the independent ops of a step are issued on")

@@ -8,13 +8,13 @@ include/d2t_b200.h.  No Triton, no CPU fallback.
 """
 from .pointwise_correlation import PointwiseCorrelation, PointwiseCorrelationFunction, TrackFeaturesFunction
 from .roipool import ROIPool, ROIPoolFunction
-from .ps_roipool import PSROIPool, PSROIPoolFunction, PSROIPoolBatched, PSROIPoolBatchedFunction
+from .ps_roipool import PSROIPool, PSROIPoolFunction, PSROIPoolBatched, PSROIPoolBatchedFunction, PSROIPoolVoteFunction
 from .track_head import TrackHeadFunction
 from .models import RFCN, CorrelationTracker
 
 __all__ = [
     "PointwiseCorrelation", "PointwiseCorrelationFunction",
     "ROIPool", "ROIPoolFunction",
-    "PSROIPool", "PSROIPoolFunction", "PSROIPoolBatched", "PSROIPoolBatchedFunction",
+    "PSROIPool", "PSROIPoolFunction", "PSROIPoolBatched", "PSROIPoolBatchedFunction", "PSROIPoolVoteFunction",
     "TrackHeadFunction", "TrackFeaturesFunction", "RFCN", "CorrelationTracker",
 ]

@@ -63,6 +63,9 @@ SIGNATURES = {
     "d2t_psroipool_bwd_batched_workspace_bytes": (_c_size_t, _WS7),
     "d2t_psroipool_fwd_batched_f32": (_c_int, _PSPOOL_B),
     "d2t_psroipool_bwd_batched_f32": (_c_int, _PSPOOL_B),
+    "d2t_psroipool_vote_supported": (_c_int, _WS6),
+    "d2t_psroipool_vote_fwd_f32": (_c_int, [_P, _P, _P] + [_c_int] * 7 + [_P]),
+    "d2t_psroipool_vote_bwd_f32": (_c_int, [_P, _P, _P] + [_c_int] * 7 + [_P]),
     "d2t_trackhead_fwd_workspace_bytes": (_c_size_t, _WS6),
     "d2t_trackhead_bwd_workspace_bytes": (_c_size_t, _WS6),
     "d2t_trackhead_fwd_f32": (_c_int, [_P] * 5 + [_c_int] * 6 + [_P, _c_size_t, _P]),

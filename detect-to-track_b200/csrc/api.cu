@@ -110,6 +110,10 @@ int corr_tile_bwd_launch(const float*, const float*, const float*, float*, float
 int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
                               cudaStream_t);
 
+// PSROIPool + vote (pool_ps.cu)
+bool psb_vote_supported(int N, int R, int nT, int H, int W, int k);
+int psb_vote_fwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int psb_vote_bwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 // fused track head (track_head.cu)
 size_t trackhead_fwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
 size_t trackhead_bwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
@@ -338,6 +342,31 @@ int d2t_psroipool_bwd_batched_f32(const float* grad_out, const float* rois, floa
         if (rc) return rc;
     }
     return D2T_OK;
+}
+
+// ---- PSROIPool + vote (mean over the k x k bins), N frames --------------------------------
+int d2t_psroipool_vote_supported(int N, int R, int n_targets, int H, int W, int r_hw) {
+    return psb_vote_supported(N, R, n_targets, H, W, r_hw) ? 1 : 0;
+}
+int d2t_psroipool_vote_fwd_f32(const float* fm, const float* rois, float* out, int N, int R, int n_targets, int H, int W,
+                               int r_hw, int flags, void* stream) {
+    D2T_REQUIRE(N >= 0 && R >= 0 && n_targets > 0 && H > 0 && W > 0 && r_hw > 0, "d2t_psroipool_vote_fwd_f32: bad shape");
+    if (N == 0 || R == 0) return D2T_OK;
+    D2T_REQUIRE(fm && rois && out, "d2t_psroipool_vote_fwd_f32: null pointer");
+    D2T_REQUIRE(psb_vote_supported(N, R, n_targets, H, W, r_hw), "d2t_psroipool_vote_fwd_f32: shape not supported (see d2t_psroipool_vote_supported)");
+    return psb_vote_fwd_launch(fm, rois, out, N, R, n_targets, H, W, r_hw, flags, (cudaStream_t)stream);
+}
+int d2t_psroipool_vote_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int N, int R, int n_targets, int H,
+                               int W, int r_hw, int flags, void* stream) {
+    D2T_REQUIRE(N >= 0 && R >= 0 && n_targets > 0 && H > 0 && W > 0 && r_hw > 0, "d2t_psroipool_vote_bwd_f32: bad shape");
+    if (N == 0) return D2T_OK;
+    if (R == 0) {
+        D2T_CUDA_TRY(cudaMemsetAsync(grad_fm, 0, (size_t)N * n_targets * r_hw * r_hw * H * W * sizeof(float), (cudaStream_t)stream));
+        return D2T_OK;
+    }
+    D2T_REQUIRE(grad_out && rois && grad_fm, "d2t_psroipool_vote_bwd_f32: null pointer");
+    D2T_REQUIRE(psb_vote_supported(N, R, n_targets, H, W, r_hw), "d2t_psroipool_vote_bwd_f32: shape not supported (see d2t_psroipool_vote_supported)");
+    return psb_vote_bwd_launch(grad_out, rois, grad_fm, N, R, n_targets, H, W, r_hw, flags, (cudaStream_t)stream);
 }
 
 // ---- fused track head: ROIPool -> Linear ---------------------------------------------

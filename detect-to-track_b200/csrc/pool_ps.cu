@@ -312,16 +312,19 @@ psb_bwd_kernel(const float* __restrict__ vt, const uint16_t* __restrict__ rowlis
 //   then  grad[y][x] = sum_{x' <= x} (Dp[y][x'] - Dm[y][x'])  by a warp-shuffle scan, written coalesced.
 // Channels nobody reads (911 of 1519 for the class head) are zero-filled by their CTA.
 constexpr int kPsb2Threads = 128;
+constexpr int kPsb2UB = 8;   // users whose gradients are prefetched together (one global-memory latency per batch)
 __global__ void __launch_bounds__(kPsb2Threads)
 psb2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, float* __restrict__ gin, int R, int nT, int H,
-                int W, int k, int canonical) {
+                int W, int k, int canonical, int vote) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int kk = k * k;
     const int pitch = W + 1;
     const int MW = (R + 31) >> 5;                                     // mask words per pixel row
-    float* Dp = reinterpret_cast<float*>(smem_raw);                   // [H][pitch]
+    float4* roiS = reinterpret_cast<float4*>(smem_raw);               // [R] the frame's RoIs
+    float* Dp = reinterpret_cast<float*>(roiS + R);                   // [H][pitch]
     float* Dm = Dp + H * pitch;                                       // [H][pitch]
-    uint32_t* rowmask = reinterpret_cast<uint32_t*>(Dm + H * pitch);  // [H][MW]
+    float* gv = Dm + H * pitch;                                       // [kPsb2UB][R] raw gradients of a batch of users
+    uint32_t* rowmask = reinterpret_cast<uint32_t*>(gv + kPsb2UB * R);    // [H][MW]
     uint2* vj = reinterpret_cast<uint2*>(rowmask + ((H * MW + 1) & ~1));  // [R] {value bits, j0 | j1 << 16}
     uint32_t* us = reinterpret_cast<uint32_t*>(vj + R);               // [kk]
     int* cnt = reinterpret_cast<int*>(us + kk);                       // [8]
@@ -335,52 +338,73 @@ psb2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, fl
         for (int px = tid; px < HW; px += kPsb2Threads) dst[px] = 0.f;
         return;
     }
+    const float4* roiG = reinterpret_cast<const float4*>(rois) + (size_t)n * R;
+    for (int r = tid; r < R; r += kPsb2Threads) roiS[r] = __ldg(roiG + r);
     for (int idx = tid; idx < 2 * H * pitch; idx += kPsb2Threads) Dp[idx] = 0.f;   // Dp and Dm are contiguous
     for (int idx = tid; idx < H * MW; idx += kPsb2Threads) rowmask[idx] = 0u;
-    const float* roiBase = rois + (size_t)n * R * 4;
-    const float* goBase = go + (size_t)n * R * nCh;
-    for (int u = 0; u < nU; ++u) {
-        const uint32_t pk = us[u];
-        const int t = pk >> 16, b = pk & 0xffff;
-        const int i = b / k, j = b - i * k;
-        __syncthreads();   // masks cleared / previous user's walk finished
-        for (int r = tid; r < R; r += kPsb2Threads) {
-            const float* roi = roiBase + (size_t)r * 4;
-            int i0, i1, j0, j1;
-            bin_edge<float, false>(__ldg(roi), __ldg(roi + 2), i, k, H, i0, i1);
-            bin_edge<float, false>(__ldg(roi + 1), __ldg(roi + 3), j, k, W, j0, j1);
-            const int numel = (i1 - i0) * (j1 - j0);
-            float v = 0.f;
-            if (numel > 0) {
-                if (t == 0xFFFF) {   // merged channel 0 of the reference map: bin 0 of every target, ascending target
-                    for (int tt = 0; tt < nT; ++tt) v += __ldg(goBase + ((size_t)r * nT + tt) * kk) / numel;
-                } else {
-                    v = __ldg(goBase + ((size_t)r * nT + t) * kk + b) / numel;   // ps_roipool_cuda.cu:134-137
-                }
-                const uint32_t bit = 1u << (r & 31);
-                for (int y = i0; y < i1; ++y) atomicOr(&rowmask[y * MW + (r >> 5)], bit);
+    // vote != 0: `go` is the gradient of the VOTE (N, R, nT) -- the mean over the k x k bins (rfcn.py:41) -- so every bin of
+    // (r, t) receives go[r, t] / kk; otherwise it is the gradient of the pooled tensor (N, R, nT, k, k)
+    const float* goBase = go + (size_t)n * R * (vote ? nT : nCh);
+    const int gstride = vote ? 1 : kk;
+    const float gscale = vote ? 1.f / (float)kk : 1.f;
+    for (int u0 = 0; u0 < nU; u0 += kPsb2UB) {
+        const int nb = min(kPsb2UB, nU - u0);
+        __syncthreads();   // gv of the previous batch is no longer read
+        // all global loads of the batch are issued back to back: one memory latency, not one per user
+        for (int e = tid; e < nb * R; e += kPsb2Threads) {
+            const int uu = e / R, r = e - uu * R;
+            const uint32_t pk = us[u0 + uu];
+            const int t = pk >> 16, b = pk & 0xffff;
+            float g = 0.f;
+            if (t == 0xFFFF) {   // merged channel 0 of the reference map: bin 0 of every target, ascending target
+#pragma unroll 4
+                for (int tt = 0; tt < nT; ++tt) g += __ldg(goBase + ((size_t)r * nT + tt) * gstride);
+            } else {
+                g = __ldg(goBase + ((size_t)r * nT + t) * gstride + (vote ? 0 : b));
             }
-            vj[r] = make_uint2(__float_as_uint(v), (uint32_t)j0 | ((uint32_t)j1 << 16));
+            gv[uu * R + r] = g * gscale;
         }
-        __syncthreads();
-        for (int task = tid; task < 2 * H; task += kPsb2Threads) {
-            const int y = task >> 1, minus = task & 1;
-            float* row = (minus ? Dm : Dp) + y * pitch;
-            uint32_t* mrow = rowmask + y * MW;
-            for (int wd = 0; wd < MW; ++wd) {
-                uint32_t m = mrow[wd];
-                while (m) {
-                    const int r = (wd << 5) + __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint2 q = vj[r];
-                    const int x = minus ? (int)(q.y >> 16) : (int)(q.y & 0xffff);
-                    row[x] += __uint_as_float(q.x);
+        for (int uu = 0; uu < nb; ++uu) {
+            const uint32_t pk = us[u0 + uu];
+            const int b = pk & 0xffff;
+            const int i = b / k, j = b - i * k;
+            __syncthreads();   // gv visible; masks cleared; previous user's walk finished
+            for (int r = tid; r < R; r += kPsb2Threads) {
+                const float4 roi = roiS[r];
+                int i0, i1, j0, j1;
+                bin_edge<float, false>(roi.x, roi.z, i, k, H, i0, i1);
+                bin_edge<float, false>(roi.y, roi.w, j, k, W, j0, j1);
+                const int numel = (i1 - i0) * (j1 - j0);
+                float v = 0.f;
+                if (numel > 0) {
+                    v = gv[uu * R + r] / numel;   // ps_roipool_cuda.cu:134-137 (the merged channel 0 divides the target sum)
+                    const uint32_t bit = 1u << (r & 31);
+                    for (int y = i0; y < i1; ++y) atomicOr(&rowmask[y * MW + (r >> 5)], bit);
                 }
+                vj[r] = make_uint2(__float_as_uint(v), (uint32_t)j0 | ((uint32_t)j1 << 16));
             }
-        }
-        if (u + 1 < nU) {
             __syncthreads();
-            for (int idx = tid; idx < H * MW; idx += kPsb2Threads) rowmask[idx] = 0u;
+            // rows are dealt to the warps round-robin (y = 4 * lane + warp), so that all four schedulers walk masks
+            for (int y = 4 * lane + warp; y < H; y += kPsb2Threads) {
+                float* rowp = Dp + y * pitch;
+                float* rowm = Dm + y * pitch;
+                const uint32_t* mrow = rowmask + y * MW;
+                for (int wd = 0; wd < MW; ++wd) {
+                    uint32_t m = mrow[wd];
+                    while (m) {
+                        const int r = (wd << 5) + __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint2 q = vj[r];
+                        const float v = __uint_as_float(q.x);
+                        rowp[q.y & 0xffff] += v;   // two independent read-modify-writes per hit
+                        rowm[q.y >> 16] += v;
+                    }
+                }
+            }
+            if (u0 + uu + 1 < nU) {
+                __syncthreads();
+                for (int idx = tid; idx < H * MW; idx += kPsb2Threads) rowmask[idx] = 0u;
+            }
         }
     }
     __syncthreads();
@@ -406,7 +430,8 @@ psb2_bwd_kernel(const float* __restrict__ go, const float* __restrict__ rois, fl
 
 static size_t psb2_smem(int R, int H, int W, int k) {
     const int MW = (R + 31) >> 5;
-    return (size_t)2 * H * (W + 1) * 4 + (size_t)((H * MW + 1) & ~1) * 4 + (size_t)R * 8 + (size_t)k * k * 4 + 64;
+    return (size_t)R * 16 + (size_t)2 * H * (W + 1) * 4 + (size_t)kPsb2UB * R * 4 + (size_t)((H * MW + 1) & ~1) * 4 +
+           (size_t)R * 8 + (size_t)k * k * 4 + 64;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -446,6 +471,14 @@ bool psb_supported(int N, int R, int nT, int H, int W, int k) {
 }
 
 static bool psb2_ok(int R, int H, int W, int k);
+// Which backward runs: the one-launch kernel for a single frame (latency matters: 87 us against 116 us for the four
+// round-1 launches at the class-head size) and for maps the round-1 kernels cannot pack (H or W above 255); a BATCH of
+// frames fills the chip and is throughput-bound, where the round-1 row-list kernels execute fewer instructions
+// (254 us against 400 us for 16 frames; profiles/r2_ncu_psb2_summary.txt).
+static bool psb2_use(int N, int R, int nT, int H, int W, int k) {
+    return psb2_ok(R, H, W, k) && (N == 1 || !psb_supported(N, R, nT, H, W, k));
+}
+
 bool psb_bwd_supported(int N, int R, int nT, int H, int W, int k) {
     if (N <= 0 || R <= 0 || nT <= 0 || k <= 0 || H <= 0 || W <= 0 || N > 65535 || nT >= 0xFFFF) return false;
     if ((long long)nT * k * k > 0x7fffffffLL / 4 || (long long)R * nT * k * k >= (1ll << 31)) return false;
@@ -453,7 +486,7 @@ bool psb_bwd_supported(int N, int R, int nT, int H, int W, int k) {
 }
 
 size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd) {
-    if (bwd && psb2_ok(R, H, W, k)) return 0;   // the one-launch backward needs no workspace
+    if (bwd && psb2_use(N, R, nT, H, W, k)) return 0;   // the one-launch backward needs no workspace
     return psb_layout(N, R, nT, H, W, k, bwd).total;
 }
 
@@ -485,6 +518,77 @@ int psb_fwd_launch(const float* fm, const float* rois, float* out, int N, int R,
     return D2T_OK;
 }
 
+// ----------------------------------------------------------------------------------------------------
+// PSROIPool + vote (rfcn.py:40-41: pooled.mean(-1).mean(-1)) in one pass: out[n, r, t] = mean over the k x k bins of the
+// bin means.  One warp per (frame, RoI, target); a lane takes bins b = lane, lane + 32, ..., sums each bin rows-then-
+// columns from its channel plane (L2-resident) and the warp adds the bin means with a fixed-shape shuffle tree.  The
+// (R, nT, k, k) tensor and the two reduction kernels of the composition never exist.
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+psb_vote_fwd_kernel(const float* __restrict__ fm, const float* __restrict__ rois, float* __restrict__ out, int N, int R, int nT,
+                    int H, int W, int k, int canonical) {
+    const int kk = k * k, nCh = nT * kk;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)N * R * nT;
+    for (long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < total;
+         wid += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int t = (int)(wid % nT);
+        const long long nr = wid / nT;       // n * R + r
+        const int n = (int)(nr / R);
+        const float* roi = rois + nr * 4;
+        const float r0 = __ldg(roi), r1 = __ldg(roi + 1), r2 = __ldg(roi + 2), r3 = __ldg(roi + 3);
+        const float* base = fm + (size_t)n * nCh * H * W;
+        float s = 0.f;
+        for (int b = lane; b < kk; b += 32) {
+            const int i = b / k, j = b - i * k;
+            int i0, i1, j0, j1;
+            bin_edge<float, false>(r0, r2, i, k, H, i0, i1);
+            bin_edge<float, false>(r1, r3, j, k, W, j0, j1);
+            const float* ch = base + (size_t)(canonical ? t * kk + b : (t + 1) * b) * H * W;
+            float acc = 0.f;
+            for (int pi = i0; pi < i1; ++pi)
+                for (int pj = j0; pj < j1; ++pj) acc += __ldg(ch + pi * W + pj);
+            const int numel = (i1 - i0) * (j1 - j0);
+            if (numel > 0) acc /= numel;   // empty cell -> 0 (ps_roipool_cuda.cu:67-69)
+            s += acc;
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+        if (lane == 0) out[wid] = s / (float)kk;
+    }
+}
+
+bool psb_vote_supported(int N, int R, int nT, int H, int W, int k) {
+    if (N <= 0 || R <= 0 || nT <= 0 || k <= 0 || H <= 0 || W <= 0 || N > 65535 || nT >= 0xFFFF) return false;
+    if ((long long)R * nT * k * k >= (1ll << 31) || (long long)nT * k * k * H * W >= (1ll << 31)) return false;
+    return psb2_ok(R, H, W, k);
+}
+
+int psb_vote_fwd_launch(const float* fm, const float* rois, float* out, int N, int R, int nT, int H, int W, int k, int flags,
+                        cudaStream_t st) {
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const long long warps = (long long)N * R * nT;
+    long long grid = (warps + 7) / 8;
+    if (grid > (long long)di.sm_count * 32) grid = (long long)di.sm_count * 32;
+    psb_vote_fwd_kernel<<<(int)grid, 256, 0, st>>>(fm, rois, out, N, R, nT, H, W, k, (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
+int psb_vote_bwd_launch(const float* go, const float* rois, float* gin, int N, int R, int nT, int H, int W, int k, int flags,
+                        cudaStream_t st) {
+    const size_t smem2 = psb2_smem(R, H, W, k);
+    D2T_SMEM_OPTIN(psb2_bwd_kernel, smem2);
+    psb2_bwd_kernel<<<dim3(nT * k * k, N), kPsb2Threads, smem2, st>>>(go, rois, gin, R, nT, H, W, k,
+                                                                      (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0, 1);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
 // the one-launch backward needs its RoI bitmasks and both difference arrays in shared memory, a few CTAs per SM
 static bool psb2_ok(int R, int H, int W, int k) {
     return W < 65535 && k * k <= kPsb2Threads && psb2_smem(R, H, W, k) <= 56 * 1024;
@@ -492,11 +596,11 @@ static bool psb2_ok(int R, int H, int W, int k) {
 
 int psb_bwd_launch(const float* go, const float* rois, float* gin, int N, int R, int nT, int H, int W, int k, int flags,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (psb2_ok(R, H, W, k)) {
+    if (psb2_use(N, R, nT, H, W, k)) {
         const size_t smem2 = psb2_smem(R, H, W, k);
         D2T_SMEM_OPTIN(psb2_bwd_kernel, smem2);
         psb2_bwd_kernel<<<dim3(nT * k * k, N), kPsb2Threads, smem2, st>>>(go, rois, gin, R, nT, H, W, k,
-                                                                          (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0);
+                                                                          (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0, 0);
         D2T_CUDA_TRY(cudaGetLastError());
         note_launch();
         return D2T_OK;

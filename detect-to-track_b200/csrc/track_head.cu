@@ -179,52 +179,61 @@ th_reduce_slabs_kernel(const float4* __restrict__ part, float4* __restrict__ z, 
 }
 
 // ---- forward 2: position-sensitive pooling of Z over ROIPool bins ----------------------------------------------------
-// one CTA per kPoolRois RoIs; thread (roi, ij) sums the nO adjacent values Z[., ij*nO .. ij*nO+nO-1] over its bin
-// rows-then-columns (one 16-byte load per pixel for nO = 4) and divides by the bin size (0/0 = NaN for an empty bin, like
-// roipool_cuda.cu:61); thread (roi, o) then adds the kk bin means of its output in ascending bin order.
+// one CTA per RoI, 4 threads per bin: thread (ij, q) sums the nO adjacent values Z[., ij*nO .. ij*nO+nO-1] (one 16-byte
+// load per pixel for nO = 4) over the pixels q, q + 4, ... of its bin (row-major inside the bin), the four partial sums are
+// combined in a fixed order and divided by the bin size (0/0 = NaN for an empty bin, like roipool_cuda.cu:61); thread o
+// then adds the kk bin means of its output in ascending bin order.  All loads of a thread are independent (L2 hits).
 constexpr int kPoolThreads2 = 256;
 template <int NO>
 __global__ void __launch_bounds__(kPoolThreads2)
 th_pool_kernel(const float* __restrict__ z, const float* __restrict__ rois, const float* __restrict__ bias, float* __restrict__ out,
-               int R, int H, int W, int k, int ldn, int roisPerCta) {
-    extern __shared__ float th_part[];   // [roisPerCta][KK][NO]
+               int R, int H, int W, int k, int ldn) {
+    extern __shared__ float th_part[];   // [KK][NO]
     const int KK = k * k;
-    const int rl = threadIdx.x / KK, ij = threadIdx.x - rl * KK;
-    const int r = blockIdx.x * roisPerCta + rl;
-    if (rl < roisPerCta && r < R) {
+    const int r = blockIdx.x;
+    const float* roi = rois + (size_t)r * 4;
+    const float r0 = __ldg(roi), r1 = __ldg(roi + 1), r2 = __ldg(roi + 2), r3 = __ldg(roi + 3);
+    for (int base = 0; base < KK * 4; base += kPoolThreads2) {   // uniform trip count: every lane reaches the shuffles
+        const int item = base + threadIdx.x;
+        const bool valid = item < KK * 4;
+        const int ij = valid ? item >> 2 : 0, q = item & 3;
         const int i = ij / k, j = ij - i * k;
-        const float* roi = rois + (size_t)r * 4;
         int i0, i1, j0, j1;
-        bin_edge<float, true>(roi[0], roi[2], i, k, H, i0, i1);
-        bin_edge<float, true>(roi[1], roi[3], j, k, W, j0, j1);
+        bin_edge<float, true>(r0, r2, i, k, H, i0, i1);
+        bin_edge<float, true>(r1, r3, j, k, W, j0, j1);
+        const int bw = j1 - j0, numel = (i1 - i0) * bw;
+        const int lim = (valid && i1 > i0 && bw > 0) ? numel : 0;
         float acc[NO];
 #pragma unroll
         for (int o = 0; o < NO; ++o) acc[o] = 0.f;
         const float* zb = z + (size_t)ij * NO;
-        for (int pi = i0; pi < i1; ++pi)
-            for (int pj = j0; pj < j1; ++pj) {
-                const float* src = zb + (size_t)(pi * W + pj) * ldn;
-                if (NO == 4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
-                    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
-                } else {
+        for (int e = q; e < lim; e += 4) {
+            const int pi = i0 + e / bw, pj = j0 + e % bw;
+            const float* src = zb + (size_t)(pi * W + pj) * ldn;
+            if (NO == 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+            } else {
 #pragma unroll
-                    for (int o = 0; o < NO; ++o) acc[o] += __ldg(src + o);
-                }
+                for (int o = 0; o < NO; ++o) acc[o] += __ldg(src + o);
             }
-        const int numel = (i1 - i0) * (j1 - j0);
+        }
 #pragma unroll
-        for (int o = 0; o < NO; ++o) th_part[(rl * KK + ij) * NO + o] = acc[o] / numel;
+        for (int o = 0; o < NO; ++o) {   // (q0 + q1) + (q2 + q3): fixed shape
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+        }
+        if (valid && q == 0) {
+#pragma unroll
+            for (int o = 0; o < NO; ++o) th_part[ij * NO + o] = acc[o] / numel;
+        }
     }
     __syncthreads();
-    if (threadIdx.x < roisPerCta * NO) {
-        const int rl2 = threadIdx.x / NO, o = threadIdx.x - rl2 * NO;
-        const int r2 = blockIdx.x * roisPerCta + rl2;
-        if (r2 < R) {
-            float s = bias ? bias[o] : 0.f;
-            for (int b = 0; b < KK; ++b) s += th_part[(rl2 * KK + b) * NO + o];
-            out[(size_t)r2 * NO + o] = s;
-        }
+    if (threadIdx.x < NO) {
+        const int o = threadIdx.x;
+        float s = bias ? bias[o] : 0.f;
+        for (int b = 0; b < KK; ++b) s += th_part[b * NO + o];
+        out[(size_t)r * NO + o] = s;
     }
 }
 
@@ -398,19 +407,16 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
         z = w.z;
     }
     {
-        const int rpc = kPoolThreads2 / d.KK > 0 ? kPoolThreads2 / d.KK : 1;   // RoIs per CTA (5 for k = 7)
-        D2T_REQUIRE(d.KK <= kPoolThreads2, "trackhead_fwd: r_hw^2 must be <= %d", kPoolThreads2);
-        const size_t psm = (size_t)rpc * d.KK * nO * sizeof(float);
-        const int grid = ceil_div(R, rpc);
+        const size_t psm = (size_t)d.KK * nO * sizeof(float);
         switch (nO) {
-            case 1: th_pool_kernel<1><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
-            case 2: th_pool_kernel<2><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
-            case 3: th_pool_kernel<3><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
-            case 4: th_pool_kernel<4><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
-            case 5: th_pool_kernel<5><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
-            case 6: th_pool_kernel<6><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
-            case 7: th_pool_kernel<7><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
-            case 8: th_pool_kernel<8><<<grid, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn, rpc); break;
+            case 1: th_pool_kernel<1><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 2: th_pool_kernel<2><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 3: th_pool_kernel<3><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 4: th_pool_kernel<4><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 5: th_pool_kernel<5><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 6: th_pool_kernel<6><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 7: th_pool_kernel<7><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 8: th_pool_kernel<8><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
             default: set_error("trackhead_fwd: n_out must be <= 8"); return D2T_ERR_BAD_ARG;
         }
     }

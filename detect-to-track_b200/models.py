@@ -13,7 +13,7 @@ import torch
 from torch import Tensor, nn
 
 from .pointwise_correlation import PointwiseCorrelation, TrackFeaturesFunction
-from .ps_roipool import PSROIPool
+from .ps_roipool import PSROIPool, PSROIPoolVoteFunction
 from .roipool import ROIPool
 from .track_head import TrackHeadFunction
 
@@ -21,14 +21,17 @@ from .track_head import TrackHeadFunction
 class _RFCNHead(nn.Module):
     """R-FCN head (rfcn.py:10-43): 1x1 score-map conv -> PSROIPool -> vote (mean over the k x k grid)."""
 
-    def __init__(self, in_channels: int, n_targets: int, k: int) -> None:
+    def __init__(self, in_channels: int, n_targets: int, k: int, fused: bool = False) -> None:
         super().__init__()
         self.sm_conv = nn.Conv2d(in_channels, n_targets * k ** 2, kernel_size=1)
         self.roi_pool = PSROIPool(n_targets, k)
         self.n_targets = n_targets
+        self.fused = fused
 
     def pool_and_vote(self, score_map: Tensor, regions: Tensor) -> Tensor:
         """(n_targets*k^2, H, W), (|R|, 4) -> (|R|, n_targets)   (rfcn.py:40-41)."""
+        if self.fused and score_map.dtype == torch.float32:   # PSROIPool + vote as one operator (SURVEY.md section 8f row 3)
+            return PSROIPoolVoteFunction.apply(score_map, regions, self.n_targets, self.roi_pool.r_hw)
         pooled = self.roi_pool(score_map, regions)
         return pooled.mean(-1).mean(-1)
 
@@ -39,13 +42,13 @@ class _RFCNHead(nn.Module):
 
 
 class RFCN(nn.Module):
-    """R-FCN (rfcn.py:46-84)."""
+    """R-FCN (rfcn.py:46-84).  `fused=True` (extension, default off): the heads pool and vote in one operator."""
 
-    def __init__(self, in_channels: int, n_classes: int, k: int) -> None:
+    def __init__(self, in_channels: int, n_classes: int, k: int, fused: bool = False) -> None:
         super().__init__()
         self.channel_reduce = nn.Conv2d(in_channels, 512, kernel_size=3, dilation=6, padding=6)
-        self.cls_head = _RFCNHead(512, n_classes + 1, k)
-        self.reg_head = _RFCNHead(512, 4, k)
+        self.cls_head = _RFCNHead(512, n_classes + 1, k, fused)
+        self.reg_head = _RFCNHead(512, 4, k, fused)
         self.relu = nn.ReLU(inplace=True)
         self.softmax = nn.Softmax(dim=1)
 

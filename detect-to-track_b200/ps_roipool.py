@@ -115,6 +115,59 @@ def ps_roipool_backward_batched(grad_out: Tensor, rois: Tensor, fm_h: int, fm_w:
     return grad_FM
 
 
+def ps_roipool_vote_supported(N: int, R: int, n_targets: int, H: int, W: int, r_hw: int) -> bool:
+    return bool(_lib.lib().d2t_psroipool_vote_supported(N, R, n_targets, H, W, r_hw))
+
+
+class PSROIPoolVoteFunction(Function):
+    """PSROIPool followed by the R-FCN vote `pooled.mean(-1).mean(-1)` (rfcn.py:40-41) as ONE operator:
+    FM (n_targets*r_hw^2, H, W) [or (N, ...)], rois (|R|, 4) [or (N, |R|, 4)] -> (|R|, n_targets) [or (N, |R|, n_targets)].
+    The pooled (|R|, n_targets, r_hw, r_hw) tensor and the reductions never exist.  float32; shapes the fused kernels do
+    not cover fall back to the composition of the API-parity ops (same result)."""
+
+    @staticmethod
+    def forward(ctx, FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
+        single = FM.dim() == 3
+        FMb, roisb = (FM[None], rois[None]) if single else (FM, rois)
+        if FMb.dim() != 4:
+            raise RuntimeError(f"FM must be (n_targets*r_hw^2, H, W) or (N, n_targets*r_hw^2, H, W); got {tuple(FM.shape)}")
+        _check_batched(FMb, roisb, "FM")
+        N, C, H, W = FMb.shape
+        if C != n_targets * r_hw ** 2:
+            raise ValueError(f"expected {n_targets * r_hw ** 2} feature map channels, recieved feature map of shape {tuple(FM.shape)}")
+        R = roisb.size(1)
+        ctx.save_for_backward(roisb)
+        ctx.cfg = (n_targets, r_hw, H, W, canonical_map, single)
+        ctx.fused = R > 0 and ps_roipool_vote_supported(N, R, n_targets, H, W, r_hw)
+        if not ctx.fused:
+            out = ps_roipool_forward_batched(FMb, roisb, n_targets, r_hw, canonical_map).mean(-1).mean(-1)
+            return out[0] if single else out
+        with torch.cuda.device(FM.device):
+            out = torch.empty((N, R, n_targets), dtype=FM.dtype, device=FM.device)
+            rc = _lib.lib().d2t_psroipool_vote_fwd_f32(FMb.data_ptr(), roisb.data_ptr(), out.data_ptr(), N, R, n_targets, H, W,
+                                                       r_hw, _CANONICAL if canonical_map else 0, _lib.stream_ptr(FM.device))
+            _lib.check(rc, "ps_roipool_vote_forward")
+        return out[0] if single else out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        roisb, = ctx.saved_tensors
+        n_targets, r_hw, H, W, canonical_map, single = ctx.cfg
+        g = (grad_out[None] if single else grad_out).contiguous()
+        N, R = roisb.shape[:2]
+        if not ctx.fused:
+            gp = (g / (r_hw * r_hw))[..., None, None].expand(N, R, n_targets, r_hw, r_hw).contiguous()
+            grad_FM = ps_roipool_backward_batched(gp, roisb, H, W, canonical_map)
+        else:
+            _lib.check_input(g, "gradOut")
+            with torch.cuda.device(g.device):
+                grad_FM = torch.empty((N, n_targets * r_hw * r_hw, H, W), dtype=g.dtype, device=g.device)
+                rc = _lib.lib().d2t_psroipool_vote_bwd_f32(g.data_ptr(), roisb.data_ptr(), grad_FM.data_ptr(), N, R, n_targets, H, W,
+                                                           r_hw, _CANONICAL if canonical_map else 0, _lib.stream_ptr(g.device))
+                _lib.check(rc, "ps_roipool_vote_backward")
+        return (grad_FM[0] if single else grad_FM), None, None, None, None
+
+
 class PSROIPoolBatchedFunction(Function):
     """PSROIPoolFunction over a leading frame dimension (one set of kernel launches for all frames)."""
 

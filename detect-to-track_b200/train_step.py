@@ -96,14 +96,14 @@ class RPN(nn.Module):
 
 class DetectTrackModule(nn.Module):
     """models/detect_track.py:52-61: container of backbone, rpn, rcnn, c_tracker (same attribute names, so a reference
-    state_dict's keys line up).  `fused_tracker=True` selects the fused track head + glue (extension)."""
+    state_dict's keys line up).  `fused_tracker=True` selects the fused operators (track head + glue, PSROIPool + vote; extensions)."""
 
     def __init__(self, backbone_arch: str = "resnet101", first_trainable_stage: int = 3, n_anchors: int = N_ANCHORS,
                  n_classes: int = 30, k: int = 7, d_max: int = 8, r_hw: int = 7, fused_tracker: bool = False) -> None:
         super().__init__()
         self.backbone = resnet_backbone(backbone_arch, first_trainable_stage)
         self.rpn = RPN(1024, n_anchors)
-        self.rcnn = RFCN(2048, n_classes, k)
+        self.rcnn = RFCN(2048, n_classes, k, fused=fused_tracker)
         self.c_tracker = CorrelationTracker(d_max, r_hw, self.rpn.conv.out_channels, fused=fused_tracker)
 
 

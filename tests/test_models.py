@@ -43,13 +43,14 @@ def _state_dict(g):
 
 
 @pytest.mark.gpu
-def test_rfcn_matches_the_reference_wiring(cuda):
+@pytest.mark.parametrize("fused", [False, True])
+def test_rfcn_matches_the_reference_wiring(cuda, fused):
     import make_golden_models as mg
     import detect_to_track_b200 as d2t
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     g = np.load(GOLDEN / "models_rfcn.npz")
-    net = d2t.RFCN(**mg.RFCN_CFG).to(cuda)
+    net = d2t.RFCN(**mg.RFCN_CFG, fused=fused).to(cuda)
     net.load_state_dict(_state_dict(g), strict=True)      # same parameter names and shapes as rfcn.py
     x = torch.from_numpy(g["x"]).to(cuda).requires_grad_(True)
     regions = torch.from_numpy(g["regions"]).to(cuda)

@@ -707,6 +707,34 @@ def test_psroipool_batched_module_autograd(cuda):
         d2t.PSROIPoolBatched(nT, k)(fm[:, :-1].contiguous(), rois)
 
 
+@pytest.mark.parametrize("canonical", [False, True])
+@pytest.mark.parametrize("N,nT,H,W,k,R", [(1, 31, 38, 63, 7, 300), (3, 4, 38, 63, 7, 50), (2, 2, 11, 10, 6, 9), (1, 5, 20, 21, 3, 700)])
+def test_psroipool_vote_matches_pool_then_mean(cuda, N, nT, H, W, k, R, canonical):
+    """PSROIPool + vote as one operator (rfcn.py:40-41) == PSROIPool -> mean(-1).mean(-1) of the API-parity op, values and
+    gradients (FP32 rounding apart: the sum over bins is a shuffle tree, not two means), bitwise reproducible; single frame
+    and batch, reference and canonical channel maps, edge-case and out-of-bounds RoIs."""
+    rng = np.random.default_rng(46)
+    rois = np.stack([np.concatenate([cases.rois_edge_cases(H, W), cases.rois_random(R, 60 + n), cases.ROIS_OOB.astype(np.float32)])
+                     for n in range(N)]).astype(np.float32)
+    fm = torch.from_numpy(rng.standard_normal((N, nT * k * k, H, W)).astype(np.float32)).to(cuda).requires_grad_(True)
+    tr = dev(rois, cuda)
+    w = torch.from_numpy(rng.standard_normal((N, rois.shape[1], nT)).astype(np.float32)).to(cuda)
+    out = d2t.PSROIPoolVoteFunction.apply(fm, tr, nT, k, canonical)
+    (out * w).sum().backward()
+    fm2 = fm.detach().clone().requires_grad_(True)
+    ref = d2t.PSROIPoolBatchedFunction.apply(fm2, tr, nT, k, canonical).mean(-1).mean(-1)
+    (ref * w).sum().backward()
+    close(out, ref.detach().cpu().numpy(), np.float32)
+    close(fm.grad, fm2.grad.cpu().numpy(), np.float32)
+    fm3 = fm.detach().clone().requires_grad_(True)
+    out3 = d2t.PSROIPoolVoteFunction.apply(fm3, tr, nT, k, canonical)
+    (out3 * w).sum().backward()
+    assert torch.equal(out, out3) and torch.equal(fm.grad, fm3.grad)
+    if N == 1:   # the (C, H, W) / (|R|, 4) form the R-FCN head calls
+        o1 = d2t.PSROIPoolVoteFunction.apply(fm.detach()[0], tr[0], nT, k, canonical)
+        assert torch.equal(o1, out.detach()[0])
+
+
 def test_psroipool_single_frame_and_batched_kernels_agree(cuda):
     """the single-frame entry point runs the per-output kernel, the batched one the channel-owner kernels: bit-identical"""
     nT, H, W, k = 4, 38, 63, 7
