@@ -114,6 +114,10 @@ int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, 
 bool psb_vote_supported(int N, int R, int nT, int H, int W, int k);
 int psb_vote_fwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int psb_vote_bwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+// device-side RoI pipeline (roi_pipeline.cu)
+size_t roi_pipeline_ws_bytes(int A, int pre_nms);
+int roi_decode_launch(const float*, const float*, const float*, float*, float*, int, float, cudaStream_t);
+int roi_nms_launch(const float*, const long long*, const float*, float*, int*, int, int, int, float, void*, size_t, cudaStream_t);
 // fused track head (track_head.cu)
 size_t trackhead_fwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
 size_t trackhead_bwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
@@ -385,6 +389,20 @@ int d2t_trackhead_bwd_f32(const float* grad_out, const float* fm, const float* r
                           size_t ws_bytes, void* stream) {
     return trackhead_bwd_launch(grad_out, fm, rois, weight, grad_fm, grad_weight, grad_bias, R, C, H, W, r_hw, n_out, ws, ws_bytes,
                                 (cudaStream_t)stream);
+}
+
+// ---- device-side RoI pipeline: decode + confidence filter, then NMS over the score-sorted candidates -------------
+size_t d2t_roi_nms_workspace_bytes(int n_anchors, int pre_nms) { return roi_pipeline_ws_bytes(n_anchors, pre_nms); }
+int d2t_roi_decode_filter_f32(const float* anchors, const float* offsets, const float* conf, float* boxes, float* scores,
+                              int n_anchors, float conf_thresh, void* stream) {
+    D2T_REQUIRE(n_anchors == 0 || (anchors && offsets && conf && boxes && scores), "d2t_roi_decode_filter_f32: null pointer");
+    return roi_decode_launch(anchors, offsets, conf, boxes, scores, n_anchors, conf_thresh, (cudaStream_t)stream);
+}
+int d2t_roi_nms_f32(const float* boxes, const long long* order, const float* sorted_scores, float* rois, int* count,
+                    int n_anchors, int pre_nms, int max_rois, float iou_thresh, void* ws, size_t ws_bytes, void* stream) {
+    D2T_REQUIRE(rois && count && (n_anchors == 0 || (boxes && order && sorted_scores)), "d2t_roi_nms_f32: null pointer");
+    return roi_nms_launch(boxes, order, sorted_scores, rois, count, n_anchors, pre_nms, max_rois, iou_thresh, ws, ws_bytes,
+                          (cudaStream_t)stream);
 }
 
 // ---- bin edges -----------------------------------------------------------------------

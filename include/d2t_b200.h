@@ -215,6 +215,23 @@ D2T_API int d2t_trackhead_bwd_f32(const float* grad_out, const float* fm, const 
                           float* grad_fm, float* grad_weight, float* grad_bias, int R, int C, int H, int W, int r_hw,
                           int n_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Device-side RoI pipeline (float32) -----------------------------------------
+ * Extension replacing the host round trip between the RPN and the R-FCN heads (trainer.py:178-190, inference.py:78-84:
+ * RPN outputs -> numpy -> ml_utils frcnn_box_decode + region_filter -> device).  ml_utils' source is unavailable, so the
+ * semantics are the standard Faster R-CNN ones (parity UNPINNED, see csrc/roi_pipeline.cu): decode
+ *   i = a_i + d_i*a_h, j = a_j + d_j*a_w, h = a_h*exp(d_h), w = a_w*exp(d_w), keep conf > conf_thresh, then greedy NMS
+ * over the candidates in descending score order (IoU > iou_thresh suppresses), at most max_rois survivors.
+ *   d2t_roi_decode_filter_f32 : anchors, offsets (A, 4) ijhw; conf (A) -> boxes (A, 4), scores (A) (-inf when filtered)
+ *   [caller sorts scores descending, stable, on the device -> sorted_scores (A), order (A) int64]
+ *   d2t_roi_nms_f32           : the first min(A, pre_nms) candidates (<= 16384) -> rois (max_rois, 4) in score order,
+ *                               zero-filled past *count (device int32).  No device->host synchronisation anywhere.
+ */
+D2T_API size_t d2t_roi_nms_workspace_bytes(int n_anchors, int pre_nms);
+D2T_API int d2t_roi_decode_filter_f32(const float* anchors, const float* offsets, const float* conf, float* boxes,
+                              float* scores, int n_anchors, float conf_thresh, void* stream);
+D2T_API int d2t_roi_nms_f32(const float* boxes, const long long* order, const float* sorted_scores, float* rois, int* count,
+                    int n_anchors, int pre_nms, int max_rois, float iou_thresh, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- integer bin edges (parity instrumentation) ----------------------------
  * edges : (R, r_hw, 4) int32 = (I0, I1, J0, J1) of row-bin / column-bin b,
  * computed on the device by the same code the pooling kernels use.
