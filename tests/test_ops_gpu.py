@@ -672,8 +672,10 @@ def test_psroipool_full_size_cls_head(cuda):
 @pytest.mark.parametrize("canonical", [False, True])
 @pytest.mark.parametrize("N,nT,H,W,k,R", [(3, 4, 38, 63, 7, 50), (2, 31, 38, 63, 7, 300), (4, 2, 11, 10, 6, 9), (1, 5, 20, 21, 3, 700)])
 def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
-    """the batched entry points (one set of launches for N frames) give bit-identical results to N single-frame
-    calls, and both match the oracle (R = 700 on a 20x21 map: long row lists, many RoIs per pixel)."""
+    """the batched entry points (one set of launches for N frames) against N single-frame calls: the forward is
+    bit-identical (both keep the reference's summation order); the backward agrees within the FP32 tolerance (a batch runs
+    the row-list kernels, a single frame the one-launch kernel: different, each fixed, summation orders); both match the
+    oracle (R = 700 on a 20x21 map: long row lists, many RoIs per pixel)."""
     rng = np.random.default_rng(36)
     rois = np.stack([np.concatenate([cases.rois_edge_cases(H, W), cases.rois_random(R, 40 + n), cases.ROIS_OOB.astype(np.float32)])
                      for n in range(N)]).astype(np.float32)
@@ -686,7 +688,10 @@ def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
     for n in range(N):
         o1 = ps_mod.ps_roipool_forward(dev(fm[n], cuda), dev(rois[n], cuda), nT, k, canonical)
         g1 = ps_mod.ps_roipool_backward(dev(go[n], cuda), dev(rois[n], cuda), H, W, canonical)
-        assert torch.equal(out[n], o1) and torch.equal(gin[n], g1)
+        assert torch.equal(out[n], o1)
+        close(g1, gin[n].cpu().numpy(), np.float32)
+        assert torch.equal(g1, ps_mod.ps_roipool_backward(dev(go[n], cuda), dev(rois[n], cuda), H, W, canonical))
+        close(g1, oracle.psroipool_bwd(go[n], rois[n], H, W, canonical), np.float32)
         np.testing.assert_array_equal(out[n].cpu().numpy(), oracle.psroipool_fwd(fm[n], rois[n], nT, k, canonical))
         close(gin[n], oracle.psroipool_bwd(go[n], rois[n], H, W, canonical), np.float32)
 
@@ -702,7 +707,8 @@ def test_psroipool_batched_module_autograd(cuda):
     fm2 = fm.detach().clone().requires_grad_(True)
     outs = torch.stack([d2t.PSROIPool(nT, k)(fm2[n], rois[n]) for n in range(N)])
     (outs * w).sum().backward()
-    assert torch.equal(out, outs) and torch.equal(fm.grad, fm2.grad)
+    assert torch.equal(out, outs)
+    close(fm.grad, fm2.grad.cpu().numpy(), np.float32)
     with pytest.raises(ValueError):
         d2t.PSROIPoolBatched(nT, k)(fm[:, :-1].contiguous(), rois)
 
