@@ -418,13 +418,25 @@ def bind_to_gpu_numa_node(torch, local_rank):
         dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
         dev = torch.cuda.get_device_properties(local_rank).pci_device_id
         path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
-        node = int(path.read_text().strip())
-        if node < 0:
-            return "numa_node unknown (-1): not bound"
-        cpus = set()
-        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
+        def parse(cpulist):
+            out = set()
+            for part in cpulist.strip().split(","):
+                lo, _, hi = part.partition("-")
+                out.update(range(int(lo), int(hi or lo) + 1))
+            return out
+
+        node = int(path.read_text().strip()) if path.exists() else -1
+        if node >= 0:
+            cpus = parse(Path(f"/sys/devices/system/node/node{node}/cpulist").read_text())
+        else:
+            # sysfs does not say (containers often report -1): ask the driver's topology table for the CPU affinity column
+            topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines()
+            head = next(ln for ln in topo if "CPU Affinity" in ln)
+            cols = [c.strip() for c in head.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t")]
+            row = next(ln for ln in topo if ln.replace("\x1b[4m", "").startswith(f"GPU{local_rank}\t") or ln.startswith(f"GPU{local_rank} "))
+            cells = [c.strip() for c in row.split("\t")]
+            cpus = parse(cells[cols.index("CPU Affinity")])
+            node = cells[cols.index("NUMA Affinity")] if "NUMA Affinity" in cols else "?"
         allowed = cpus & set(os.sched_getaffinity(0))
         if not allowed:
             return f"node {node}: none of its CPUs is in this process's affinity mask: not bound"
@@ -491,6 +503,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity0 = os.sched_getaffinity(0)   # restored before the CPU-baseline legs, which use every host core
     numa = bind_to_gpu_numa_node(torch, local) if not args.no_numa else "disabled (--no-numa)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -631,6 +644,7 @@ def run_ours(args):
             train = {"error": repr(exc)}
 
     ms, ms_fused, e2e_ms = global_max([ms, ms_fused, e2e_ms], dev)
+    os.sched_setaffinity(0, affinity0)
 
     if rank == 0:
         peaks = {}
