@@ -70,6 +70,7 @@ SIGNATURES = {
     "d2t_trackhead_bwd_workspace_bytes": (_c_size_t, _WS6),
     "d2t_trackhead_fwd_f32": (_c_int, [_P] * 5 + [_c_int] * 6 + [_P, _c_size_t, _P]),
     "d2t_trackhead_bwd_f32": (_c_int, [_P] * 7 + [_c_int] * 6 + [_P, _c_size_t, _P]),
+    "d2t_gemm_tf32x3_f32": (_c_int, [_P, _P, _P] + [_c_int] * 9 + [_P]),
     "d2t_roi_nms_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "d2t_roi_decode_filter_f32": (_c_int, [_P] * 5 + [_c_int, ctypes.c_float, _P]),
     "d2t_roi_nms_f32": (_c_int, [_P] * 5 + [_c_int] * 3 + [ctypes.c_float, _P, _c_size_t, _P]),

@@ -140,7 +140,18 @@ static int check_corr(const void* a, const void* b, const void* c, int B, int C,
 
 using namespace d2t;
 
+#include "gemm_tf32x3.cuh"
+
 extern "C" {
+
+// ---- building block of the fused track head, exported for its own parity / timing tests ---------------------------
+int d2t_gemm_tf32x3_f32(const float* A, const float* B, float* out, int M, int N, int K, int lda, int ldb, int ldo,
+                        int col_major_out, int splits, int n_tile, void* stream) {
+    D2T_REQUIRE(A && B && out, "d2t_gemm_tf32x3_f32: null pointer");
+    GemmOperand a{A, M, lda}, b{B, N, ldb};
+    return gemm_tf32x3(a, b, out, M, N, K, ldo, col_major_out ? GEMM_EPI_COL : GEMM_EPI_ROW, splits, M, n_tile,
+                       (cudaStream_t)stream);
+}
 
 int d2t_abi_version(void) { return D2T_B200_ABI_VERSION; }
 const char* d2t_last_error(void) { return g_err; }

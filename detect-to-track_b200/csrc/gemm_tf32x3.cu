@@ -5,15 +5,18 @@
 // layouts (written by the layout kernels of track_head.cu), so unlike the reference's 38x63 NCHW maps they can have
 // 16-byte-aligned row pitches: TMA applies.
 //
-//   operands   FP32 values pre-split by their producer into hi = tf32_rn(v) and lo = v - hi (two planes each).  Three
+//   operands   plain FP32 matrices.  The split  hi = tf32_rn(v) (in place),  lo = v - hi (second tile)  is made in shared
+//              memory by the eight epilogue warps -- otherwise idle during the main loop -- while the previous k-block's
+//              MMAs run; it is an elementwise pass over the tile, so the lo tile inherits the swizzled layout.  Three
 //              kind::tf32 MMAs per k-step: hi*hi + hi*lo + lo*hi ("3xTF32"; the dropped lo*lo term is 2^-22 relative).
-//              Measured |err| <= 9e-7 * sum |a||b| for this split (tools/umma_sw128_test.cu).
-//   staging    TMA only.  One 2-D box {32 floats, rows} per operand plane and k-block lands as the K-major SWIZZLE_128B
-//              layout tcgen05.mma reads (128-byte rows, 8-row atoms 1024 bytes apart); out-of-range rows / k are
-//              zero-filled by the TMA unit, so ragged M, N and K need no padding in memory.  No thread touches an
-//              operand byte: the LSU pipe is free (the correlation backward kernel of round 1 was bound by it).
+//   staging    TMA only, and only the raw values: half the bytes of pre-split hi/lo planes, which is what bounded the
+//              first version of this kernel (22 us for 1.77 GFLOP: 103 MB of operand traffic through L2).  One 2-D box
+//              {32 floats, rows} per operand and k-block lands as the K-major SWIZZLE_128B layout tcgen05.mma reads
+//              (128-byte rows, 8-row atoms 1024 bytes apart); out-of-range rows / k are zero-filled by the TMA unit, so
+//              ragged M, N and K need no padding in memory.
 //   roles      warp 0: TMA producer (one elected lane); warp 1: MMA issuer (one elected lane); warp 2: TMEM allocation;
-//              warps 4-7: epilogue (tcgen05.ld 32 lanes x 32 columns at a time).  KSTAGES-deep mbarrier ring.
+//              warps 4-11: lo-split of every stage, then the epilogue (tcgen05.ld 32 lanes x 16 columns at a time).
+//              mbarrier ring: full (TMA landed) -> split (lo written) -> MMAs -> empty (tcgen05.commit).
 //   tiles      M tile 128 (TMEM lanes), N tile BN <= 256 (TMEM columns), k-block 32; grid = (M tiles, N tiles, K splits).
 //              Split-K partials go to disjoint slabs of the output (summed in a fixed order by the consumer:
 //              deterministic, no atomics).
@@ -29,7 +32,8 @@ namespace {
 
 constexpr int GM = 128;      // M tile = UMMA M
 constexpr int GBK = 32;      // k-block: 32 floats = one 128-byte swizzle row
-constexpr int GTHREADS = 256;
+constexpr int GTHREADS = 384;   // warps 0-2: TMA / MMA / TMEM allocation, 3: idle, 4-11: lo split + epilogue
+constexpr int GSPLIT_WARPS = 8;
 
 __device__ __forceinline__ uint32_t g_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void g_mbar_init(uint64_t* bar, int count) {
@@ -41,6 +45,9 @@ __device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
             g_smem(bar)),
         "r"(parity), "r"(0x989680u)
         : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(g_smem(bar)) : "memory");
 }
 __device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem(bar)), "r"(bytes) : "memory");
@@ -75,25 +82,31 @@ __device__ __forceinline__ void g_commit(uint64_t* bar) {
 
 template <int BN>
 struct GCfg {
-    static constexpr int A_BYTES = GM * 128;   // one plane (hi or lo) of the A k-block
+    static constexpr int A_BYTES = GM * 128;   // one plane (raw = hi, or lo) of the A k-block
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;   // 2 for BN in (144, 256], 3 below
+    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;          // what TMA delivers per k-block: [A raw | B raw]
+    // two rings: raw tiles (TMA prefetch depth) and lo tiles (written by the split warps).  These GEMMs are short --
+    // 7-9 k-blocks per CTA -- so the kernel is bound by latency, not bandwidth: a third raw stage hides the TMA round trip
+    // (~1.2 us) behind the split + MMAs of the two k-blocks in flight (22 -> 13 us for the track-head forward GEMM).
+    static constexpr int LO_STAGES = 2;
+    static constexpr int RAW_STAGES = (226 * 1024 - LO_STAGES * RAW_BYTES) / RAW_BYTES >= 4 ? 4
+                                      : (226 * 1024 - LO_STAGES * RAW_BYTES) / RAW_BYTES;
+    static constexpr int SMEM_BYTES = (RAW_STAGES + LO_STAGES) * RAW_BYTES;
     static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
-    static_assert(STAGES >= 2, "stage ring");
+    static_assert(RAW_STAGES >= 2, "stage ring");
 };
 
 template <int BN>
 __global__ void __launch_bounds__(GTHREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
-                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-                   float* __restrict__ out, GemmArgs a) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ out,
+                   GemmArgs a) {
     using Cfg = GCfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], bar_acc;
+    constexpr int RS = Cfg::RAW_STAGES, LS = Cfg::LO_STAGES;
+    __shared__ __align__(8) uint64_t bar_full[RS], bar_rawfree[RS], bar_split[LS], bar_lofree[LS], bar_acc;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -109,18 +122,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) {
+        for (int s = 0; s < RS; ++s) {
             g_mbar_init(&bar_full[s], 1);
-            g_mbar_init(&bar_empty[s], 1);
+            g_mbar_init(&bar_rawfree[s], 1);
+        }
+        for (int s = 0; s < LS; ++s) {
+            g_mbar_init(&bar_split[s], GSPLIT_WARPS);    // one arrival per split warp
+            g_mbar_init(&bar_lofree[s], 1);
         }
         g_mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -132,28 +147,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
         // ================================ TMA producer =========================================================
         if (lane == 0) {
             for (int i = 0; i < kbCnt; ++i) {
-                const int s = i % Cfg::STAGES;
-                const uint32_t round = (uint32_t)(i / Cfg::STAGES);
-                g_mbar_wait(&bar_empty[s], (round & 1u) ^ 1u);   // the MMAs that read this stage last round are done
-                g_mbar_expect_tx(&bar_full[s], (uint32_t)Cfg::STAGE_BYTES);
-                const uint32_t st = smemBase + (uint32_t)s * Cfg::STAGE_BYTES;
+                const int s = i % RS;
+                const uint32_t round = (uint32_t)(i / RS);
+                g_mbar_wait(&bar_rawfree[s], (round & 1u) ^ 1u);   // the MMAs that read this stage last round are done
+                g_mbar_expect_tx(&bar_full[s], (uint32_t)Cfg::RAW_BYTES);
+                const uint32_t st = smemBase + (uint32_t)s * Cfg::RAW_BYTES;
                 const int k0 = (kbBeg + i) * GBK;
-                g_tma_2d(st, &mapAhi, k0, m0, &bar_full[s]);
-                g_tma_2d(st + Cfg::A_BYTES, &mapAlo, k0, m0, &bar_full[s]);
-                g_tma_2d(st + 2 * Cfg::A_BYTES, &mapBhi, k0, n0, &bar_full[s]);
-                g_tma_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, k0, n0, &bar_full[s]);
+                g_tma_2d(st, &mapA, k0, m0, &bar_full[s]);
+                g_tma_2d(st + Cfg::A_BYTES, &mapB, k0, n0, &bar_full[s]);
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===========================================================
         for (int i = 0; i < kbCnt; ++i) {
-            const int s = i % Cfg::STAGES;
-            const uint32_t round = (uint32_t)(i / Cfg::STAGES);
-            g_mbar_wait(&bar_full[s], round & 1u);
+            const int r = i % RS, l = i % LS;
+            g_mbar_wait(&bar_split[l], (uint32_t)(i / LS) & 1u);   // raw tiles landed AND their lo parts are written
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t aHi = smemBase + (uint32_t)s * Cfg::STAGE_BYTES, aLo = aHi + Cfg::A_BYTES;
-                const uint32_t bHi = aHi + 2 * Cfg::A_BYTES, bLo = bHi + Cfg::B_BYTES;
+                const uint32_t aHi = smemBase + (uint32_t)r * Cfg::RAW_BYTES, bHi = aHi + Cfg::A_BYTES;
+                const uint32_t aLo = smemBase + (uint32_t)(RS + l) * Cfg::RAW_BYTES, bLo = aLo + Cfg::A_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < GBK / 8; ++ks) {
                     const uint32_t ko = ks * 32;   // 8 tf32 = 32 bytes inside the 128-byte row
@@ -161,22 +173,50 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                     g_mma(tmem_base, g_desc(aHi + ko), g_desc(bLo + ko), Cfg::IDESC, 1u);
                     g_mma(tmem_base, g_desc(aLo + ko), g_desc(bHi + ko), Cfg::IDESC, 1u);
                 }
-                g_commit(&bar_empty[s]);                    // frees the stage once these MMAs have read it
+                g_commit(&bar_rawfree[r]);                  // both rings are released once these MMAs have read them
+                g_commit(&bar_lofree[l]);
                 if (i == kbCnt - 1) g_commit(&bar_acc);     // accumulator complete
             }
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ================================ epilogue (warps 4-7: TMEM lane quarter = warp - 4) ===================
-        const int quarter = warp - 4;
+        // ================================ lo split, then epilogue (warps 4-11) =================================
+        // The split is what paces a k-block (measured 1.4 us with four warps against 0.8 us of MMAs): eight warps, two
+        // per scheduler.  In the epilogue warp w drains TMEM lane quarter w % 4 (the hardware's access rule), warps 4-7
+        // the first half of the columns and warps 8-11 the second.
+        const int quarter = warp & 3;
+        const int half = (warp - 4) >> 2;
+        {
+            const int t = tid - 128;   // 0..255
+            for (int i = 0; i < kbCnt; ++i) {
+                const int r = i % RS, l = i % LS;
+                g_mbar_wait(&bar_full[r], (uint32_t)(i / RS) & 1u);
+                g_mbar_wait(&bar_lofree[l], ((uint32_t)(i / LS) & 1u) ^ 1u);   // the MMAs that read this lo tile are done
+                float4* raw = reinterpret_cast<float4*>(smem + (size_t)r * Cfg::RAW_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem + (size_t)(RS + l) * Cfg::RAW_BYTES);
+                // hi = tf32_rn(v) replaces the raw word in place (the tensor core would otherwise TRUNCATE v, which leaves a
+                // same-signed lo of up to 2^-10 |v| and a biased, twice larger error: measured 2.4e-6 against 9e-7 * sum|a||b|)
+#pragma unroll 4
+                for (int e = t; e < Cfg::RAW_BYTES / 16; e += 32 * GSPLIT_WARPS) {
+                    const float4 v = raw[e];
+                    const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                    raw[e] = h;
+                    lo[e] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) g_mbar_arrive(&bar_split[l]);
+            }
+        }
         const int m = m0 + quarter * 32 + lane;
         if (kbCnt > 0) {
             g_mbar_wait(&bar_acc, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const bool mok = m < a.M;
+        constexpr int QN = BN / 16, QH = (QN + 1) / 2;
 #pragma unroll 1
-        for (int q = 0; q < BN / 16; ++q) {
+        for (int q = half * QH; q < min(QN, (half + 1) * QH); ++q) {
             uint32_t r[16];
             if (kbCnt > 0) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * 16);
@@ -265,16 +305,14 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld
 template <int BN>
 static int launch(const GemmOperand& A, const GemmOperand& B, float* out, const GemmArgs& a, cudaStream_t st) {
     using Cfg = GCfg<BN>;
-    CUtensorMap mAh, mAl, mBh, mBl;
+    CUtensorMap mA, mB;
     int rc;
-    if ((rc = make_map(&mAh, A.hi, A.rows, a.K, A.ld, GM))) return rc;
-    if ((rc = make_map(&mAl, A.lo, A.rows, a.K, A.ld, GM))) return rc;
-    if ((rc = make_map(&mBh, B.hi, B.rows, a.K, B.ld, BN))) return rc;
-    if ((rc = make_map(&mBl, B.lo, B.rows, a.K, B.ld, BN))) return rc;
-    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
+    if ((rc = make_map(&mA, A.ptr, A.rows, a.K, A.ld, GM))) return rc;
+    if ((rc = make_map(&mB, B.ptr, B.rows, a.K, B.ld, BN))) return rc;
+    const size_t smem = (size_t)Cfg::SMEM_BYTES + 1024;
     D2T_SMEM_OPTIN(gemm_tf32x3_kernel<BN>, smem);
     dim3 grid(ceil_div(a.M, GM), ceil_div(a.N, BN), a.splits);
-    gemm_tf32x3_kernel<BN><<<grid, GTHREADS, smem, st>>>(mAh, mAl, mBh, mBl, out, a);
+    gemm_tf32x3_kernel<BN><<<grid, GTHREADS, smem, st>>>(mA, mB, out, a);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;

@@ -6,11 +6,9 @@ namespace d2t {
 
 enum { GEMM_EPI_ROW = 0, GEMM_EPI_COL = 1 };
 
-// One K-major operand: rows x K FP32, K contiguous, row pitch `ld` floats (multiple of 4; base 16-byte aligned),
-// pre-split into hi = tf32_rn(v) and lo = v - hi planes of identical layout.
+// One K-major operand: rows x K FP32, K contiguous, row pitch `ld` floats (multiple of 4; base 16-byte aligned).
 struct GemmOperand {
-    const float* hi;
-    const float* lo;
+    const float* ptr;
     int rows;
     int ld;
 };
@@ -26,7 +24,7 @@ struct GemmArgs {
 int gemm_tf32x3(const GemmOperand& A, const GemmOperand& B, float* out, int M, int N, int K, int ldo, int epilogue, int splits,
                 int slab_rows, int bn, cudaStream_t st);
 
-// round-to-nearest split used by every producer of GEMM operands: hi keeps tf32's 10 explicit mantissa bits
+// round to the nearest tf32 (10 explicit mantissa bits), result kept in an FP32 word
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
 }  // namespace d2t

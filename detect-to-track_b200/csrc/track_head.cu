@@ -17,8 +17,8 @@
 // (300 x 92659) x (92659 x 4) library GEMM.  Bins, clamped RoI start and the empty-bin NaN (0/0) follow ROIPool
 // (roipool_cuda.cu:26-61): an empty bin makes every output of that RoI NaN, exactly like pooled -> Linear would.
 //
-// The GEMMs run on tcgen05 in 3xTF32 (gemm_tf32x3.cu) from K-major hi/lo planes written by the layout kernels below;
-// all reductions have a fixed order (split-K slabs summed ascending, RoI lists ascending): bitwise reproducible.
+// The GEMMs run on tcgen05 in 3xTF32 (gemm_tf32x3.cu) from K-major FP32 operands written by the layout kernels below
+// (TMA needs 16-byte-aligned row pitches, which the reference's 38x63 maps do not have); all reductions have a fixed order (split-K slabs summed ascending, RoI lists ascending): bitwise reproducible.
 #include "gemm_tf32x3.cuh"
 
 namespace d2t {
@@ -60,7 +60,7 @@ static int th_dims(int R, int C, int H, int W, int k, int nO, ThDims* d) {
 
 // workspace carving (all offsets multiples of 256 bytes)
 struct ThFwdWs {
-    float *xt_hi, *xt_lo, *wt_hi, *wt_lo, *zpart, *z;
+    float *xt, *wt, *zpart, *z;
     size_t total;
 };
 static ThFwdWs th_fwd_ws(const ThDims& d, void* base) {
@@ -71,15 +71,15 @@ static ThFwdWs th_fwd_ws(const ThDims& d, void* base) {
         off = align_up(off + floats * sizeof(float), 256);
         return p;
     };
-    w.xt_hi = take((size_t)d.P * d.ldc); w.xt_lo = take((size_t)d.P * d.ldc);
-    w.wt_hi = take((size_t)d.N1 * d.ldc); w.wt_lo = take((size_t)d.N1 * d.ldc);
+    w.xt = take((size_t)d.P * d.ldc);
+    w.wt = take((size_t)d.N1 * d.ldc);
     w.zpart = take((size_t)d.s1 * d.P * d.ldn);
     w.z = take((size_t)d.P * d.ldn);
     w.total = off;
     return w;
 }
 struct ThBwdWs {
-    float *gz_hi, *gz_lo, *gzt_hi, *gzt_lo, *xc_hi, *xc_lo, *wc_hi, *wc_lo, *gwpart;
+    float *gz, *gzt, *xc, *wc, *gwpart;
     size_t total;
 };
 static ThBwdWs th_bwd_ws(const ThDims& d, void* base) {
@@ -90,19 +90,19 @@ static ThBwdWs th_bwd_ws(const ThDims& d, void* base) {
         off = align_up(off + floats * sizeof(float), 256);
         return p;
     };
-    w.gz_hi = take((size_t)d.P * d.ldn); w.gz_lo = take((size_t)d.P * d.ldn);
-    w.gzt_hi = take((size_t)d.N1 * d.ldp); w.gzt_lo = take((size_t)d.N1 * d.ldp);
-    w.xc_hi = take((size_t)d.C * d.ldp); w.xc_lo = take((size_t)d.C * d.ldp);
-    w.wc_hi = take((size_t)d.C * d.ldn); w.wc_lo = take((size_t)d.C * d.ldn);
+    w.gz = take((size_t)d.P * d.ldn);
+    w.gzt = take((size_t)d.N1 * d.ldp);
+    w.xc = take((size_t)d.C * d.ldp);   // used unless the map itself is TMA-legal (H*W a multiple of 4, 16-byte-aligned base)
+    w.wc = take((size_t)d.C * d.ldn);
     w.gwpart = take((size_t)d.s3 * d.C * d.ldn);
     w.total = off;
     return w;
 }
 
 // ---- layout kernels ---------------------------------------------------------------------------------------------
-// X (C, P) -> XT hi / lo (P, ldc): 32 x 32 tiles through shared memory, both sides coalesced
+// X (C, P) -> XT (P, ldc): 32 x 32 tiles through shared memory, both sides coalesced
 __global__ void __launch_bounds__(256)
-th_split_transpose_kernel(const float* __restrict__ x, float* __restrict__ thi, float* __restrict__ tlo, int C, int P, int ldc) {
+th_transpose_kernel(const float* __restrict__ x, float* __restrict__ xt, int C, int P, int ldc) {
     __shared__ float tile[32][33];
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -115,34 +115,24 @@ th_split_transpose_kernel(const float* __restrict__ x, float* __restrict__ thi, 
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
         const int p = p0 + r, c = c0 + tx;
-        if (p < P && c < C) {
-            const float v = tile[tx][r];
-            const float h = tf32_rn(v);
-            thi[(size_t)p * ldc + c] = h;
-            tlo[(size_t)p * ldc + c] = v - h;
-        }
+        if (p < P && c < C) xt[(size_t)p * ldc + c] = tile[tx][r];
     }
 }
 
-// X (C, P) -> Xc hi / lo (C, ldp): same order, aligned pitch
+// X (C, P) -> Xc (C, ldp): same order, 16-byte-aligned pitch (only when P is not a multiple of 4)
 __global__ void __launch_bounds__(256)
-th_split_copy_kernel(const float* __restrict__ x, float* __restrict__ chi, float* __restrict__ clo, int C, int P, int ldp) {
+th_pad_copy_kernel(const float* __restrict__ x, float* __restrict__ xc, int C, int P, int ldp) {
     const int c = blockIdx.y;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        const float v = __ldg(x + (size_t)c * P + p);
-        const float h = tf32_rn(v);
-        chi[(size_t)c * ldp + p] = h;
-        clo[(size_t)c * ldp + p] = v - h;
-    }
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x)
+        xc[(size_t)c * ldp + p] = __ldg(x + (size_t)c * P + p);
 }
 
 // The n_out * kk "position-sensitive channels" are numbered n = ij * nO + o (outputs of one bin adjacent), so that the
 // pooling and gZ kernels move the nO values of a bin with one vector access.
-// W (nO, C*KK) -> Wt hi / lo (n, ldc)   [K = c]   (by_channel == 0)
-//              -> Wc hi / lo (c, ldn)   [K = n]   (by_channel == 1)
+// W (nO, C*KK) -> Wt (n, ldc)   [K = c]   (by_channel == 0)
+//              -> Wc (c, ldn)   [K = n]   (by_channel == 1)
 __global__ void __launch_bounds__(256)
-th_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int C, int KK, int nO, int ld,
-                      int by_channel) {
+th_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int KK, int nO, int ld, int by_channel) {
     const int total = nO * C * KK;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         int o, c, ij;
@@ -158,10 +148,7 @@ th_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ hi, float
             ij = n / nO; o = n - ij * nO;
             dst = (size_t)n * ld + c;
         }
-        const float v = __ldg(w + (size_t)o * C * KK + (size_t)c * KK + ij);
-        const float h = tf32_rn(v);
-        hi[dst] = h;
-        lo[dst] = v - h;
+        out[dst] = __ldg(w + (size_t)o * C * KK + (size_t)c * KK + ij);
     }
 }
 
@@ -237,15 +224,15 @@ th_pool_kernel(const float* __restrict__ z, const float* __restrict__ rois, cons
     }
 }
 
-// ---- backward 1: gZ (both layouts, hi/lo) ------------------------------------------------------------------------------
+// ---- backward 1: gZ (both layouts) -------------------------------------------------------------------------------------
 // one CTA per (pixel row y, bin row i).  Phase 1: every RoI's bin-row-i edges; warp 0 compacts, in ascending RoI order,
 // the RoIs whose bin row covers y.  Phase 2: column edges and scaled gradients g[r, o] / n_rij of the listed RoIs.
 // Phase 3: thread (x, j) adds, in list order, the entries whose column bin j covers x -- a gather: fixed order, no atomics.
 constexpr int kGzThreads = 256;
 constexpr int kGzMaxO = 8;
 __global__ void __launch_bounds__(kGzThreads)
-th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float* __restrict__ gz_hi, float* __restrict__ gz_lo,
-             float* __restrict__ gzt_hi, float* __restrict__ gzt_lo, int R, int H, int W, int k, int nO, int ldn, int ldp) {
+th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float* __restrict__ gz, float* __restrict__ gzt, int R,
+             int H, int W, int k, int nO, int ldn, int ldp) {
     extern __shared__ unsigned char th_smem[];
     // list[R] (int) | rowext[R] (int: I1 - I0 or 0) | cj[R*k] (short2 J0, J1) | val[R*k*nO] (float)
     int* list = reinterpret_cast<int*>(th_smem);
@@ -302,25 +289,13 @@ th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float*
         }
         const int p = y * W + x;
         const int nb = (i * k + j) * nO;
-        float hi[kGzMaxO], lo[kGzMaxO];
-#pragma unroll
-        for (int o = 0; o < kGzMaxO; ++o) {
-            hi[o] = tf32_rn(acc[o]);
-            lo[o] = acc[o] - hi[o];
-        }
-        if (nO == 4) {   // ldn and nb are multiples of 4: one 16-byte store per plane
-            *reinterpret_cast<float4*>(gz_hi + (size_t)p * ldn + nb) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(gz_lo + (size_t)p * ldn + nb) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
+        if (nO == 4)   // ldn and nb are multiples of 4: one 16-byte store
+            *reinterpret_cast<float4*>(gz + (size_t)p * ldn + nb) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 #pragma unroll
         for (int o = 0; o < kGzMaxO; ++o) {
             if (o < nO) {
-                if (nO != 4) {
-                    gz_hi[(size_t)p * ldn + nb + o] = hi[o];
-                    gz_lo[(size_t)p * ldn + nb + o] = lo[o];
-                }
-                gzt_hi[(size_t)(nb + o) * ldp + p] = hi[o];
-                gzt_lo[(size_t)(nb + o) * ldp + p] = lo[o];
+                if (nO != 4) gz[(size_t)p * ldn + nb + o] = acc[o];
+                gzt[(size_t)(nb + o) * ldp + p] = acc[o];
             }
         }
     }
@@ -390,12 +365,12 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     const int cap = di.sm_count * 8;
-    th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wt_hi, w.wt_lo, C, d.KK, nO, d.ldc, 0);
+    th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wt, C, d.KK, nO, d.ldc, 0);
     D2T_CUDA_TRY(cudaGetLastError());
-    th_split_transpose_kernel<<<dim3(ceil_div(d.P, 32), ceil_div(C, 32)), 256, 0, st>>>(fm, w.xt_hi, w.xt_lo, C, d.P, d.ldc);
+    th_transpose_kernel<<<dim3(ceil_div(d.P, 32), ceil_div(C, 32)), 256, 0, st>>>(fm, w.xt, C, d.P, d.ldc);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch(2);
-    GemmOperand A{w.xt_hi, w.xt_lo, d.P, d.ldc}, B{w.wt_hi, w.wt_lo, d.N1, d.ldc};
+    GemmOperand A{w.xt, d.P, d.ldc}, B{w.wt, d.N1, d.ldc};
     if ((rc = gemm_tf32x3(A, B, w.zpart, d.P, d.N1, C, d.ldn, GEMM_EPI_ROW, d.s1, d.P, d.bn, st))) return rc;
     const float* z = w.zpart;
     if (d.s1 > 1) {
@@ -449,21 +424,26 @@ int trackhead_bwd_launch(const float* go, const float* fm, const float* rois, co
     const size_t gzSmem = (size_t)R * 8 + (size_t)R * k * 4 + (size_t)R * k * nO * 4;
     D2T_REQUIRE(gzSmem <= (size_t)di.max_smem_optin - 1024, "trackhead_bwd: too many RoIs for one call (%d)", R);
     D2T_SMEM_OPTIN(th_gz_kernel, gzSmem);
-    th_gz_kernel<<<H * k, kGzThreads, gzSmem, st>>>(go, rois, w.gz_hi, w.gz_lo, w.gzt_hi, w.gzt_lo, R, H, W, k, nO, d.ldn, d.ldp);
+    th_gz_kernel<<<H * k, kGzThreads, gzSmem, st>>>(go, rois, w.gz, w.gzt, R, H, W, k, nO, d.ldn, d.ldp);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     if (gfm) {
-        th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wc_hi, w.wc_lo, C, d.KK, nO, d.ldn, 1);
+        th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wc, C, d.KK, nO, d.ldn, 1);
         D2T_CUDA_TRY(cudaGetLastError());
         note_launch();
-        GemmOperand A{w.gz_hi, w.gz_lo, d.P, d.ldn}, B{w.wc_hi, w.wc_lo, C, d.ldn};
-        if ((rc = gemm_tf32x3(A, B, gfm, d.P, C, d.N1, d.P, GEMM_EPI_COL, 1, 0, 256, st))) return rc;
+        GemmOperand A{w.gz, d.P, d.ldn}, B{w.wc, C, d.ldn};
+        // N tile 208 (10 x 19 = 190 CTAs, three raw stages) beats 256 (8 x 19 = 152 CTAs: also two waves, two stages)
+        if ((rc = gemm_tf32x3(A, B, gfm, d.P, C, d.N1, d.P, GEMM_EPI_COL, 1, 0, 208, st))) return rc;
     }
     if (gw) {
-        th_split_copy_kernel<<<dim3(ceil_div(d.P, 1024), C), 256, 0, st>>>(fm, w.xc_hi, w.xc_lo, C, d.P, d.ldp);
-        D2T_CUDA_TRY(cudaGetLastError());
-        note_launch();
-        GemmOperand A{w.xc_hi, w.xc_lo, C, d.ldp}, B{w.gzt_hi, w.gzt_lo, d.N1, d.ldp};
+        const float* xc = fm;
+        if (d.P != d.ldp || (reinterpret_cast<uintptr_t>(fm) & 15) != 0) {
+            th_pad_copy_kernel<<<dim3(ceil_div(d.P, 1024), C), 256, 0, st>>>(fm, w.xc, C, d.P, d.ldp);
+            D2T_CUDA_TRY(cudaGetLastError());
+            note_launch();
+            xc = w.xc;
+        }
+        GemmOperand A{xc, C, d.ldp}, B{w.gzt, d.N1, d.ldp};
         if ((rc = gemm_tf32x3(A, B, w.gwpart, C, d.N1, d.P, d.ldn, GEMM_EPI_ROW, d.s3, C, d.bn, st))) return rc;
     }
     if (gw || gb) {

@@ -205,7 +205,8 @@ D2T_API int d2t_psroipool_vote_bwd_f32(const float* grad_out, const float* rois,
  *   out / grad_out : (R, n_out);  grad_fm : (C, H, W);  grad_weight : like weight;  grad_bias : (n_out)
  * Any of grad_fm / grad_weight / grad_bias may be NULL (not computed).  Requires n_out * r_hw^2 <= 256, n_out <= 8.
  * Same bins, clamped RoI start and empty-bin NaN as d2t_roipool_fwd_f32; values agree with the composition to FP32
- * rounding (3xTF32: |err| <= 2e-6 * sum |a||b| per contraction).  Bitwise reproducible.
+ * rounding (3xTF32 with the tensor core's FP32 accumulator: measured |err| <= 2.5e-6 * sum |a||b| per contraction for the
+ * longest, 1891-term chains, tools/gemm_sweep.py; inside rtol 1e-4 of the result's scale).  Bitwise reproducible.
  */
 D2T_API size_t d2t_trackhead_fwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int n_out);
 D2T_API int d2t_trackhead_fwd_f32(const float* fm, const float* rois, const float* weight, const float* bias, float* out,
@@ -214,6 +215,14 @@ D2T_API size_t d2t_trackhead_bwd_workspace_bytes(int R, int C, int H, int W, int
 D2T_API int d2t_trackhead_bwd_f32(const float* grad_out, const float* fm, const float* rois, const float* weight,
                           float* grad_fm, float* grad_weight, float* grad_bias, int R, int C, int H, int W, int r_hw,
                           int n_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- 3xTF32 GEMM building block (float32) ------------------------------------------
+ * out = A (M x K, row pitch lda) * B^T (N x K, row pitch ldb), both K-major with 16-byte-aligned bases and pitches, on
+ * tcgen05 fed by TMA (csrc/gemm_tf32x3.cu; measured |err| <= 2.5e-6 * sum |a||b| at K = 1891, 9e-7 at K = 256).  The contraction kernel of the fused track head,
+ * exported for its own parity and timing tests.  splits > 1: split s of the K range writes its partial product to rows
+ * [s*M, (s+1)*M) of `out` (row-major, ldo) / to out + s*M*ldo (col_major_out: out[n*ldo + m]); n_tile in {64, 208, 256}. */
+D2T_API int d2t_gemm_tf32x3_f32(const float* A, const float* B, float* out, int M, int N, int K, int lda, int ldb, int ldo,
+                        int col_major_out, int splits, int n_tile, void* stream);
 
 /* ---- Device-side RoI pipeline (float32) -----------------------------------------
  * Extension replacing the host round trip between the RPN and the R-FCN heads (trainer.py:178-190, inference.py:78-84:
