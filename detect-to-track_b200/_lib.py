@@ -39,6 +39,9 @@ SIGNATURES = {
     "d2t_corr_bwd_workspace_bytes": (_c_size_t, _WS7),
     "d2t_corr_fwd_f32": (_c_int, _CORR_FWD),
     "d2t_corr_fwd_f64": (_c_int, _CORR_FWD),
+    "d2t_corr_fwd_simt_workspace_bytes": (_c_size_t, _WS6),
+    "d2t_corr_fwd_f32_simt": (_c_int, _CORR_FWD),
+    "d2t_corr_fwd_f32_tc": (_c_int, _CORR_FWD),
     "d2t_corr_fwd_strided_f32": (_c_int, [_P, _P, _P] + [_c_int] * 6 + [ctypes.c_longlong] * 3 + [_P, _c_size_t, _P]),
     "d2t_corr_fwd_strided_f64": (_c_int, [_P, _P, _P] + [_c_int] * 6 + [ctypes.c_longlong] * 3 + [_P, _c_size_t, _P]),
     "d2t_corr_bwd_f32": (_c_int, _CORR_BWD),

@@ -98,6 +98,10 @@ bool corr_umma_bwd_supported(int B, int C, int H, int W, int d, int stride);
 size_t corr_umma_bwd_ws_bytes(int B, int C, int H, int W);
 int corr_umma_bwd_launch(const float*, const float*, const float*, float*, float*, int, int, int, int, void*, size_t,
                          cudaStream_t);
+// tensor-core forward (corr_umma_fwd.cu)
+bool corr_umma_fwd_supported(int B, int C, int H, int W, int d, int stride);
+int corr_umma_fwd_launch(const float*, const float*, float*, int, int, int, int, const CorrOutStrides*, cudaStream_t);
+constexpr int kCorrTensorMinC = 128;   // tensor-core correlation kernels from this many channels (forward and backward)
 // tuned float32 correlation (corr_tile.cu)
 bool corr_tile_supported(int B, int C, int H, int W, int d, int stride);
 bool corr_tile_bwd_supported(int B, int C, int H, int W, int d, int stride);
@@ -158,9 +162,17 @@ const char* d2t_last_error(void) { return g_err; }
 unsigned long long d2t_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- correlation -------------------------------------------------------------------
+// Which forward runs behind d2t_corr_fwd_f32 / d2t_corr_fwd_strided_f32: a function of (C, d_max, stride) only
+static bool use_umma_fwd(int B, int C, int H, int W, int d_max, int stride) {
+    return C >= kCorrTensorMinC && corr_umma_fwd_supported(B, C, H, W, d_max, stride);
+}
 size_t d2t_corr_fwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size) {
+    if (elem_size == 4 && use_umma_fwd(B, C, H, W, d_max, stride)) return 0;   // accumulators live in TMEM: no partial slots
     if (elem_size == 4 && corr_tile_supported(B, C, H, W, d_max, stride)) return corr_tile_fwd_ws_bytes(B, C, H, W, d_max);
     return 0;
+}
+size_t d2t_corr_fwd_simt_workspace_bytes(int B, int C, int H, int W, int d_max, int stride) {
+    return corr_tile_supported(B, C, H, W, d_max, stride) ? corr_tile_fwd_ws_bytes(B, C, H, W, d_max) : 0;
 }
 size_t d2t_corr_bwd_workspace_bytes(int B, int C, int H, int W, int d_max, int stride, int elem_size) {
     if (elem_size == 4 && corr_tile_bwd_supported(B, C, H, W, d_max, stride)) return corr_tile_bwd_ws_bytes(B, C, H, W, d_max);
@@ -171,10 +183,15 @@ static CorrOutStrides dense_strides(int H, int W, int d) {
     const long long kk = (long long)(2 * d + 1) * (2 * d + 1);
     return CorrOutStrides{(long long)H * W * kk, kk, 1};
 }
+// family: 0 = default dispatch, 1 = FP32 pipe (SIMT), 2 = tensor cores
 static int corr_fwd_f32_any(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
-                            CorrOutStrides os, void* ws, size_t ws_bytes, void* stream, const char* who) {
+                            CorrOutStrides os, void* ws, size_t ws_bytes, void* stream, const char* who, int family = 0) {
     int rc = check_corr(fm0, fm1, out, B, C, H, W, d_max, stride, who);
     if (rc) return rc;
+    if ((long long)B * H * W == 0) return D2T_OK;
+    if (family == 2) D2T_REQUIRE(corr_umma_fwd_supported(B, C, H, W, d_max, stride), "%s: needs d_max = 8, stride = 1", who);
+    if (family == 2 || (family == 0 && use_umma_fwd(B, C, H, W, d_max, stride)))
+        return corr_umma_fwd_launch(fm0, fm1, out, B, C, H, W, &os, (cudaStream_t)stream);
     if (corr_tile_supported(B, C, H, W, d_max, stride))
         return corr_tile_fwd_launch(fm0, fm1, out, B, C, H, W, d_max, &os, ws, ws_bytes, (cudaStream_t)stream);
     return corr_fwd_generic_launch<float>(fm0, fm1, out, B, C, H, W, d_max, stride, os, (cudaStream_t)stream);
@@ -192,6 +209,17 @@ int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, i
     if (rc) return rc;
     return corr_fwd_generic_launch<double>(fm0, fm1, out, B, C, H, W, d_max, stride, dense_strides(H, W, d_max),
                                            (cudaStream_t)stream);
+}
+// explicit kernel families (same contract as d2t_corr_fwd_f32; _simt needs d2t_corr_fwd_simt_workspace_bytes, _tc none)
+int d2t_corr_fwd_f32_simt(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
+                          void* ws, size_t ws_bytes, void* stream) {
+    return corr_fwd_f32_any(fm0, fm1, out, B, C, H, W, d_max, stride, dense_strides(H, W, d_max), ws, ws_bytes, stream,
+                            "d2t_corr_fwd_f32_simt", 1);
+}
+int d2t_corr_fwd_f32_tc(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,
+                        void* ws, size_t ws_bytes, void* stream) {
+    return corr_fwd_f32_any(fm0, fm1, out, B, C, H, W, d_max, stride, dense_strides(H, W, d_max), ws, ws_bytes, stream,
+                            "d2t_corr_fwd_f32_tc", 2);
 }
 // strided output: element (b, pos, t) goes to out[b*batch_stride + pos*pos_stride + t*disp_stride] (elements)
 int d2t_corr_fwd_strided_f32(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max, int stride,

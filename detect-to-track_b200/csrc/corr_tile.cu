@@ -52,7 +52,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-constexpr int kCorrBwdUmmaMinC = 128;  // tensor-core backward from this many channels (see use_umma_bwd)
+constexpr int kCorrBwdUmmaMinC = 128;  // = kCorrTensorMinC of api.cu  // tensor-core backward from this many channels (see use_umma_bwd)
 // packed FP32x2 FMA (Blackwell FFMA2): two independent fused multiply-adds per issue slot, same rounding as fmaf.
 typedef unsigned long long f32x2_t;
 __device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {

@@ -84,6 +84,23 @@ D2T_API int d2t_corr_fwd_f32(const float* fm0, const float* fm1, float* out, int
 D2T_API int d2t_corr_fwd_f64(const double* fm0, const double* fm1, double* out, int B, int C, int H, int W, int d_max,
                      int stride, void* ws, size_t ws_bytes, void* stream);
 
+/* Kernel family of d2t_corr_fwd_f32 / d2t_corr_fwd_strided_f32 -- like the backward, a function of (C, d_max, stride) only:
+ *   d_max == 8, stride == 1, C >= 128 : tensor cores (tcgen05 + TMEM, 3xTF32; csrc/corr_umma_fwd.cu: both operands
+ *       MN-major, i.e. NCHW rows as they lie in memory).  |err| <= (2e-6 + 1.5e-8 * C) * sum_c |fm0 * fm1|: the split
+ *       itself is good to 7e-7, the C term is the tensor core's FP32 accumulator, which TRUNCATES -- sums of same-signed
+ *       terms (post-ReLU maps) come out low by about 0.7e-8 * C relative (-1.4e-5 at C = 2048, measured).  Inside rtol
+ *       1e-4, looser than FP32 FMAs (3e-7); d2t_corr_fwd_f32_simt keeps those.  No workspace.
+ *       Dead entries are exact zeros.  Non-finite inputs: a NaN/Inf key or query poisons the 128 x 256 accumulator tiles
+ *       it is staged into (the positions of its 8 x 16 tile / 8-row patch chunk), not only the windows containing it.
+ *   otherwise : FP32 FMAs (SIMT band kernel for d_max in {4, 8} with stride 1, generic gather kernel for the rest).
+ * d2t_corr_fwd_f32_simt / d2t_corr_fwd_f32_tc select a family explicitly (_simt takes the workspace reported by
+ * d2t_corr_fwd_simt_workspace_bytes; _tc requires d_max == 8, stride == 1). */
+D2T_API size_t d2t_corr_fwd_simt_workspace_bytes(int B, int C, int H, int W, int d_max, int stride);
+D2T_API int d2t_corr_fwd_f32_simt(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max,
+                          int stride, void* ws, size_t ws_bytes, void* stream);
+D2T_API int d2t_corr_fwd_f32_tc(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, int d_max,
+                        int stride, void* ws, size_t ws_bytes, void* stream);
+
 /* Strided output (tracker glue fusion, correlation_tracker.py:64-80): element (b, pos = i*W + j, t = ci*(2d+1) + cj)
  * is written to out[b*batch_stride + pos*pos_stride + t*disp_stride] (strides in elements).  {H*W*kk, kk, 1} is the
  * reference layout; {anything, 1, H*W} writes the ((2d+1)^2, H, W) channel-major map the tracker feeds to ROIPool

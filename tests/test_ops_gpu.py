@@ -115,16 +115,60 @@ def test_corr_bench_shapes_vs_reference_kernels(cuda, name, C):
     close(g1, r1.cpu().numpy(), np.float32)
 
 
+@pytest.mark.parametrize("B,C,H,W", [(1, 137, 38, 63), (3, 160, 20, 21), (1, 200, 70, 66), (2, 300, 9, 17), (2, 2048, 38, 63), (1, 128, 5, 70)])
+def test_corr_fwd_tensor_core_kernel(cuda, B, C, H, W):
+    """tcgen05 / 3xTF32 forward (default for d_max = 8, stride 1, C >= 128; MN-major operands).  Stated tolerance
+    |err| <= (2e-6 + 1.5e-8 * C) * sum_c |fm0 * fm1| against the float64 generic kernel (magnitude sum from the same kernel
+    on absolute values) -- the C term is the tensor core's truncating FP32 accumulator, reached by all-positive inputs,
+    which are tested too; dead entries exactly zero; agrees with the FP32-pipe kernel at the op tolerance; ragged channel
+    counts, maps smaller than a tile, partial tiles, chunks outside the image."""
+    from detect_to_track_b200 import _lib
+    lib = _lib.lib()
+    d = 8
+    g = torch.Generator(device="cpu").manual_seed(79)
+    fm0 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    fm1 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    out = torch.full((B, H, W, 17, 17), float("nan"), device=cuda)
+    rc = lib.d2t_corr_fwd_f32_tc(fm0.data_ptr(), fm1.data_ptr(), out.data_ptr(), B, C, H, W, d, 1, None, 0,
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    ref = pc_mod.pointwise_correlation_forward(fm0.double(), fm1.double(), d, 1)
+    mag = pc_mod.pointwise_correlation_forward(fm0.double().abs(), fm1.double().abs(), d, 1)
+    err = (out.double() - ref).abs()
+    bound = 2e-6 + 1.5e-8 * C
+    assert bool((err <= bound * mag + 1e-30).all()), float((err / (mag + 1e-30)).max())
+    pos = torch.empty_like(out)     # same-signed terms: the accumulator bias adds up instead of cancelling
+    rc = lib.d2t_corr_fwd_f32_tc(fm0.abs().data_ptr(), fm1.abs().data_ptr(), pos.data_ptr(), B, C, H, W, d, 1, None, 0,
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    assert bool(((pos.double() - mag).abs() <= bound * mag + 1e-30).all()), float(((pos.double() - mag).abs() / (mag + 1e-30)).max())
+    live = torch.from_numpy(corr_live_mask(H, W, d, 1)).to(cuda)
+    assert bool((out[~live.expand_as(out)] == 0).all())
+    assert torch.equal(out, pc_mod.pointwise_correlation_forward(fm0, fm1, d, 1))     # the default dispatch runs this kernel
+    n = lib.d2t_corr_fwd_simt_workspace_bytes(B, C, H, W, d, 1)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=cuda)
+    simt = torch.empty_like(out)
+    rc = lib.d2t_corr_fwd_f32_simt(fm0.data_ptr(), fm1.data_ptr(), simt.data_ptr(), B, C, H, W, d, 1, ws.data_ptr(), n,
+                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    close(out, simt.cpu().numpy(), np.float32)
+
+
 def test_corr_backward_is_batch_invariant(cuda):
     """the kernel family behind d2t_corr_bwd_f32 depends on (C, d_max, stride) only (include/d2t_b200.h), so the
     gradients of an image are bit-identical whether it is processed alone or inside a batch of 8."""
     for C in (64, 512):   # FP32-pipe family / tensor-core family
         fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(8, C, 38, 63, 8, seed=19, dtype=np.float32))
         g0, g1 = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
+        out = pc_mod.pointwise_correlation_forward(fm0, fm1, 8, 1)
         for b in (0, 5):
             h0, h1 = pc_mod.pointwise_correlation_backward(go[b:b + 1].contiguous(), fm0[b:b + 1].contiguous(),
                                                            fm1[b:b + 1].contiguous(), 8, 1)
             assert torch.equal(g0[b:b + 1], h0) and torch.equal(g1[b:b + 1], h1)
+            if C >= 128:   # tensor-core forward: fixed channel order per item.  (The FP32-pipe forward cuts its stream-K
+                # ranges by the total amount of work, so its summation order -- not its result within rtol -- follows B.)
+                assert torch.equal(out[b:b + 1], pc_mod.pointwise_correlation_forward(fm0[b:b + 1].contiguous(),
+                                                                                      fm1[b:b + 1].contiguous(), 8, 1))
 
 
 def test_corr_nonfinite_inputs(cuda):
@@ -135,8 +179,20 @@ def test_corr_nonfinite_inputs(cuda):
     fm0, fm1, go = (dev(a, cuda) for a in cases.corr_inputs(B, C, H, W, d, seed=23, dtype=np.float32))
     bad = fm1.clone()
     bad[0, 3, 20, 40] = float("inf")
-    out = pc_mod.pointwise_correlation_forward(fm0, bad, d, 1)
-    clean = pc_mod.pointwise_correlation_forward(fm0, fm1, d, 1)
+    from detect_to_track_b200 import _lib
+    lib = _lib.lib()
+
+    def fwd_simt(a, b_):
+        o = torch.empty((B, H, W, 17, 17), device=cuda)
+        n = lib.d2t_corr_fwd_simt_workspace_bytes(B, C, H, W, d, 1)
+        ws = torch.empty(max(n, 1), dtype=torch.uint8, device=cuda)
+        rc = lib.d2t_corr_fwd_f32_simt(a.data_ptr(), b_.data_ptr(), o.data_ptr(), B, C, H, W, d, 1, ws.data_ptr(), n,
+                                       torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        return o
+
+    out = fwd_simt(fm0, bad)
+    clean = fwd_simt(fm0, fm1)
     nonfinite = ~torch.isfinite(out)
     # exactly the (i, j, ci, cj) with i-d+ci == 20 and j-d+cj == 40
     want = torch.zeros_like(nonfinite)
@@ -145,8 +201,14 @@ def test_corr_nonfinite_inputs(cuda):
             want[0, i, j, 20 - i + d, 40 - j + d] = True
     assert torch.equal(nonfinite, want)
     assert torch.equal(out[~want], clean[~want])
-    from detect_to_track_b200 import _lib
-    lib = _lib.lib()
+    # tensor-core forward (default at C >= 128): the windows containing the value are non-finite, and nothing outside the
+    # 8 x 16 tiles whose halo patch holds pixel (20, 40) is touched (rows 8..31, columns 32..62)
+    tc = pc_mod.pointwise_correlation_forward(fm0, bad, d, 1)
+    tcc = pc_mod.pointwise_correlation_forward(fm0, fm1, d, 1)
+    nf = ~torch.isfinite(tc)
+    assert bool(nf[want].all())
+    assert not bool(nf[0, :8].any()) and not bool(nf[0, 32:].any()) and not bool(nf[0, :, :32].any())
+    assert torch.equal(tc[~nf], tcc[~nf])
     g0, g1 = torch.empty_like(fm0), torch.empty_like(fm1)
     rc = lib.d2t_corr_bwd_f32_simt(go.data_ptr(), fm0.data_ptr(), bad.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, C, H, W, d, 1,
                                    None, 0, torch.cuda.current_stream().cuda_stream)
@@ -445,8 +507,12 @@ def test_corr_full_size_adjoint_identity(cuda):
     out = pc_mod.pointwise_correlation_forward(fm0, fm1, 8, 1)
     g0, g1 = pc_mod.pointwise_correlation_backward(go, fm0, fm1, 8, 1)
     lhs = (out.double() * go.double()).sum().item()
-    assert abs(lhs - (fm0.double() * g0.double()).sum().item()) <= 1e-5 * abs(lhs)
-    assert abs(lhs - (fm1.double() * g1.double()).sum().item()) <= 1e-5 * abs(lhs)
+    # lhs is a sum of 5e5 terms of random sign (|lhs| ~ 300, sum |terms| ~ 5e5).  The tensor-core forward's FP32 accumulator
+    # truncates, which biases every one of these all-positive 2048-channel sums by about -1.4e-5 relative
+    # (tools/adjoint_probe.py), so the identity is asked to hold to 3e-5 |lhs| + 1e-8 sum|terms|
+    tol = 3e-5 * abs(lhs) + 1e-8 * (out.double().abs() * go.double().abs()).sum().item()
+    assert abs(lhs - (fm0.double() * g0.double()).sum().item()) <= tol
+    assert abs(lhs - (fm1.double() * g1.double()).sum().item()) <= tol
     # dead rows / columns (F4)
     assert float(out[..., 16, :].abs().max()) == 0 and float(out[..., :, 16].abs().max()) == 0
     # spot-check 64 random outputs against a float64 dot product

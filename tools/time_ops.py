@@ -86,6 +86,15 @@ def main():
         fb = 2 * B * C * H * W * 4 + B * H * W * k2 * 4
         bb = B * H * W * k2 * 4 + 4 * B * C * H * W * 4
         report("corr fwd " + name, timeit(lambda: pc.pointwise_correlation_forward(fm0, fm1, d, 1), args.iters, flush), 2.0 * C * P, fb)
+        if d == 8 and C >= 128:   # the FP32-pipe kernel the default replaced
+            from detect_to_track_b200 import _lib
+            lib = _lib.lib()
+            n = lib.d2t_corr_fwd_simt_workspace_bytes(B, C, H, W, d, 1)
+            wsb = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            o2 = torch.empty((B, H, W, 2 * d + 1, 2 * d + 1), device=dev)
+            st = torch.cuda.current_stream().cuda_stream
+            report("  corr fwd (FP32-pipe kernel) " + name, timeit(lambda: lib.d2t_corr_fwd_f32_simt(
+                fm0.data_ptr(), fm1.data_ptr(), o2.data_ptr(), B, C, H, W, d, 1, wsb.data_ptr(), n, st), args.iters, flush), 2.0 * C * P, fb)
         if not args.skip_bwd:
           report("corr bwd " + name, timeit(lambda: pc.pointwise_correlation_backward(go, fm0, fm1, d, 1), args.iters, flush), 4.0 * C * P, bb)
         if ref is not None and B * C <= 2048:
