@@ -138,7 +138,8 @@ def test_corr_fwd_tensor_core_kernel(cuda, B, C, H, W):
     bound = 2e-6 + 1.5e-8 * C
     assert bool((err <= bound * mag + 1e-30).all()), float((err / (mag + 1e-30)).max())
     pos = torch.empty_like(out)     # same-signed terms: the accumulator bias adds up instead of cancelling
-    rc = lib.d2t_corr_fwd_f32_tc(fm0.abs().data_ptr(), fm1.abs().data_ptr(), pos.data_ptr(), B, C, H, W, d, 1, None, 0,
+    a0, a1 = fm0.abs(), fm1.abs()
+    rc = lib.d2t_corr_fwd_f32_tc(a0.data_ptr(), a1.data_ptr(), pos.data_ptr(), B, C, H, W, d, 1, None, 0,
                                  torch.cuda.current_stream().cuda_stream)
     assert rc == 0, _lib.last_error()
     assert bool(((pos.double() - mag).abs() <= bound * mag + 1e-30).all()), float(((pos.double() - mag).abs() / (mag + 1e-30)).max())
