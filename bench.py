@@ -7,7 +7,7 @@
 
 One STEP = the whole hot path, forward + backward, for 8 frame pairs on one GPU
 (BASELINE.json configs 2+3+4 together, SURVEY.md section 8d shapes):
-    PointwiseCorrelation d=8 on c3/c4/c5 (C=512/1024/2048, 38x63), batch of 8 pairs      3 fwd + 3 bwd calls
+    PointwiseCorrelation d=8 on c3/c4/c5 (C=512/1024/2048, 38x63), batch of 8 pairs      3 fwd + 3 bwd calls (tcgen05)
     PSROIPool 7x7, cls (31 targets) + reg (4 targets), 300 RoIs, 2 frames per pair        32 fwd + 32 bwd calls
     ROIPool 7x7 track head, 1891 channels, 300 RoIs per pair                              8 fwd +  8 bwd calls
 Pairs shard over GPUs with no data-path collective: weak scaling, value =
@@ -239,10 +239,11 @@ def run_per_config(torch, dev, hbm, fp32_peak, tf32_peak, cpu=True):
         kk = (2 * d + 1) ** 2
         tf = _time_call(torch, lambda: pc.pointwise_correlation_forward(fm0, fm1, d, 1), flush)
         tb = _time_call(torch, lambda: pc.pointwise_correlation_backward(go, fm0, fm1, d, 1), flush)
-        tensor_bwd = d == 8 and C >= 128
+        tensor_bwd = d == 8 and C >= 128      # the same rule selects the tensor-core forward
         row = {"config": name, "us_fwd": tf * 1e6, "us_bwd": tb * 1e6,
-               "fwd": {"bound": "fp32", "achieved": 2.0 * C * Pn / tf * 1e-12, "peak": fp32_peak, "unit": "TFLOP/s",
-                       "frac": 2.0 * C * Pn / tf * 1e-12 / fp32_peak,
+               "fwd": {"bound": "tensor" if tensor_bwd else "fp32", "achieved": 2.0 * C * Pn / tf * 1e-12,
+                       "peak": tf32_peak if tensor_bwd else fp32_peak, "unit": "TFLOP/s",
+                       "frac": 2.0 * C * Pn / tf * 1e-12 / (tf32_peak if tensor_bwd else fp32_peak),
                        "hbm_gbs": (2 * B * C * Hh * Ww + B * Hh * Ww * kk) * 4 / tf * 1e-9},
                "bwd": {"bound": "tensor" if tensor_bwd else "fp32", "achieved": 4.0 * C * Pn / tb * 1e-12,
                        "peak": tf32_peak if tensor_bwd else fp32_peak, "unit": "TFLOP/s",
@@ -710,10 +711,13 @@ def run_ours(args):
                  "frac": 2 * flops / t_cb * 1e-12 / tf32_peak, "us_per_call": t_cb * 1e6,
                  "hbm_gbs": 2 * corr_bytes / t_cb * 1e-9,
                  "note": "algorithmic flops; the dense tile x 3xTF32 executes ~8.4x of them on the tensor pipe"},
-                {"bound": "fp32", "kernel": "corr_fwd_tile_kernel<8,8> (c5: C=2048, B=8)", "achieved": flops / t_cf * 1e-12,
-                 "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t_cf * 1e-12 / fp32_peak,
+                {"bound": "tensor", "kernel": "corr_fwd_umma_kernel<8> (c5: C=2048, B=8; 3xTF32, MN-major operands)",
+                 "achieved": flops / t_cf * 1e-12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": flops / t_cf * 1e-12 / tf32_peak,
                  "us_per_launch": t_cf * 1e6, "hbm_gbs": corr_bytes / t_cf * 1e-9,
-                 "peak_source": "measured FFMA micro-benchmark (profiles/r1_microbench.txt)"},
+                 "fp32_pipe_equivalent_frac": flops / t_cf * 1e-12 / fp32_peak,
+                 "note": "algorithmic flops; the dense 128x256 tile x 3xTF32 executes ~9x of them on the tensor pipe (tensor pipe "
+                         "54 % busy, L1 data pipe 97 %: profiles/r2_ncu_corr_fwd_umma_summary.txt); the FP32-pipe kernel it "
+                         "replaced ran at 562 + 42 us"},
                 hbm_row("psb_fwd_kernel (+edges), cls head, 16 frames per call", NF * ps_bytes["cls"][0], med("ps_cls_fwd")),
                 hbm_row("psb_bwd_kernel (+edges, scale, rowlists), cls head, 16 frames per call", NF * ps_bytes["cls"][1], med("ps_cls_bwd")),
                 hbm_row("psb_fwd_kernel (+edges), box head, 16 frames per call", NF * ps_bytes["reg"][0], med("ps_reg_fwd")),

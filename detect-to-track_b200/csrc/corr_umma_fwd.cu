@@ -35,19 +35,31 @@ namespace d2t {
 namespace {
 
 constexpr int FD = 8, FTD = 16, FK1 = 17, FKK = 289;
-constexpr int FM = 128, FN = 256;
+constexpr int FM = 128;
 constexpr int FQROWS = 8, FQCOLS = 16;
 constexpr int FKC = 32;                       // channels per stage
 constexpr int FPROD_WARPS = 8;
 constexpr int FEPI_WARP0 = FPROD_WARPS + 4;
 constexpr int FTHREADS = (FPROD_WARPS + 8) * 32;
 constexpr int FA_BYTES = FKC * FM * 4;        // one plane (hi or lo) of A per stage: 16 KB
-constexpr int FB_BYTES = FKC * FN * 4;        // 32 KB
-constexpr int FSTAGE_BYTES = 2 * FA_BYTES + 2 * FB_BYTES;
 constexpr int FSTAGES = 2;
 constexpr int FLBO = (FKC / 4) * 512;         // bytes between MN atoms (32 positions) of a plane
 constexpr int FSBO = 512;                     // bytes between K atoms (4 channels)
-constexpr int FNB = FKC, FNA = FKC / 2;       // B / A elements a producer thread stages per stage
+constexpr int FNA = FKC / 2;                  // A elements a producer thread stages per stage
+
+// CR = patch rows per chunk: 8 (N = 256) is the efficient shape; 4 (N = 128) doubles the number of items for problems that
+// would otherwise leave most SMs idle (one image: 52 items of 8 rows on 148 SMs).  The channel order of every output is
+// the same in both, so the choice does not change a single bit of the result.
+template <int CR>
+struct FCfg {
+    static constexpr int N = CR * 32;                       // accumulator columns per item
+    static constexpr int NCH = 24 / CR;                     // chunks per tile (patch rows 0 .. 23)
+    static constexpr int B_BYTES = FKC * N * 4;             // one plane of B per stage
+    static constexpr int STAGE_BYTES = 2 * FA_BYTES + 2 * B_BYTES;
+    static constexpr int NB = FKC * CR / 8;                 // B elements a producer thread stages per stage
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                                      ((uint32_t)(FM >> 4) << 24);   // F32 acc, TF32 a/b, MN-major a/b, N, M
+};
 
 struct FPlan {
     int B, C, H, W;
@@ -79,14 +91,11 @@ __device__ __forceinline__ uint64_t f_desc(uint32_t saddr) {
     d |= (uint64_t)1 << 61;
     return d;
 }
-// c_format F32, a/b format TF32, a/b MN-major, N, M
-constexpr uint32_t kFIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(FN >> 3) << 17) |
-                             ((uint32_t)(FM >> 4) << 24);
-__device__ __forceinline__ void f_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void f_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
         " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(kFIdesc), "r"(accumulate), "r"(0u)
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void f_commit(uint64_t* bar) {
@@ -105,14 +114,17 @@ __device__ __forceinline__ float f_tf32_rn(float v) { return __uint_as_float((__
 template <int V>
 struct FInt { static constexpr int value = V; };
 
-// chunk g of the tile whose first query row is i0 holds patch rows i0 - 8 + 8g .. + 7: an item iff some row is in the image
+// chunk g of the tile whose first query row is i0 holds patch rows i0 - 8 + CR*g .. + CR-1: an item iff some row is in the image
+template <int CR>
 __host__ __device__ __forceinline__ bool f_chunk_valid(int i0, int g, int H) {
-    const int r0 = i0 - FD + 8 * g;
-    return r0 + 7 >= 0 && r0 < H;
+    const int r0 = i0 - FD + CR * g;
+    return r0 + CR - 1 >= 0 && r0 < H;
 }
 
 // walks the (item, channel chunk) sequence of one CTA
+template <int CR>
 struct FCursor {
+    static constexpr int NCH = FCfg<CR>::NCH;
     int item, ch;            // ch: channel chunk inside the item
     int b, i0, j0, g, gFirst;
     unsigned gmask;          // bit g set = chunk g of this tile is an item
@@ -125,7 +137,8 @@ struct FCursor {
         int ty = 0;
         for (; ty < p.tilesY; ++ty) {
             const int ii = ty * FQROWS;
-            const int ng = (int)f_chunk_valid(ii, 0, p.H) + (int)f_chunk_valid(ii, 1, p.H) + (int)f_chunk_valid(ii, 2, p.H);
+            int ng = 0;
+            for (int gg = 0; gg < NCH; ++gg) ng += (int)f_chunk_valid<CR>(ii, gg, p.H);
             if (rem < ng * p.tilesX) {
                 const int tx = rem / ng;
                 int k = rem - tx * ng;
@@ -134,8 +147,8 @@ struct FCursor {
                 gmask = 0;
                 gFirst = -1;
                 g = 0;
-                for (int gg = 0; gg < 3; ++gg) {
-                    if (!f_chunk_valid(ii, gg, p.H)) continue;
+                for (int gg = 0; gg < NCH; ++gg) {
+                    if (!f_chunk_valid<CR>(ii, gg, p.H)) continue;
                     gmask |= 1u << gg;
                     if (gFirst < 0) gFirst = gg;
                     if (k == 0) g = gg;
@@ -154,8 +167,10 @@ struct FCursor {
     }
 };
 
+template <int CR>
 __global__ void __launch_bounds__(FTHREADS, 1)
 corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm1, float* __restrict__ out, FPlan p) {
+    using Cfg = FCfg<CR>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bar_full[FSTAGES], bar_empty[FSTAGES], bar_acc_full[2], bar_acc_empty[2];
@@ -167,7 +182,7 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
     const uint64_t planeBytes = (uint64_t)plane * sizeof(float);
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(f_smem(&tmem_base_s)), "r"((uint32_t)(2 * FN)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(f_smem(&tmem_base_s)), "r"((uint32_t)(2 * Cfg::N)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
@@ -193,7 +208,7 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         const int quarter = warp - FEPI_WARP0;
         const int m = quarter * 32 + lane;
         const int qrow = m >> 4, qcol = m & 15;
-        FCursor c;
+        FCursor<CR> c;
         c.start(p);
         uint32_t t = 0;
         while (c.valid(p)) {
@@ -206,20 +221,20 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                 // the entries whose key row belongs to a chunk that is not an item (wholly outside the image)
                 for (int e = 0; e < FKK; ++e) {
                     const int ci = e / FK1, cj = e - ci * FK1;
-                    const bool produced = ci < FTD && cj < FTD && ((c.gmask >> ((qrow + ci) >> 3)) & 1u);
+                    const bool produced = ci < FTD && cj < FTD && ((c.gmask >> ((qrow + ci) / CR)) & 1u);
                     if (!produced) o[(long long)e * p.os.st] = 0.f;
                 }
             }
             f_mbar_wait(&bar_acc_full[ab], (t >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int prl = 0; prl < 8; ++prl) {
-                const int ci = 8 * c.g + prl - qrow;     // row displacement of this patch row for this query
+            for (int prl = 0; prl < CR; ++prl) {
+                const int ci = CR * c.g + prl - qrow;     // row displacement of this patch row for this query
                 // the loads are warp-collective: every lane executes them, the stores are predicated
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t r[16];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * FN + (uint32_t)(prl * 32 + hf * 16);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * Cfg::N + (uint32_t)(prl * 32 + hf * 16);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
                         "%15}, [%16];"
@@ -248,7 +263,7 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         // ================================ MMA issuer (warp 8; warps 9-11 only donate registers) ================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::);
         if (warp == FPROD_WARPS) {
-            FCursor c;
+            FCursor<CR> c;
             c.start(p);
             uint32_t k = 0, t = 0;
             while (c.valid(p)) {
@@ -259,15 +274,15 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                 f_mbar_wait(&bar_full[s], (k >> 1) & 1u);                            // all producer warps have staged the chunk
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t aHi = smemBase + s * FSTAGE_BYTES, aLo = aHi + FA_BYTES;
-                    const uint32_t bHi = aHi + 2 * FA_BYTES, bLo = bHi + FB_BYTES;
-                    const uint32_t dcol = tmem_base + ab * FN;
+                    const uint32_t aHi = smemBase + s * Cfg::STAGE_BYTES, aLo = aHi + FA_BYTES;
+                    const uint32_t bHi = aHi + 2 * FA_BYTES, bLo = bHi + Cfg::B_BYTES;
+                    const uint32_t dcol = tmem_base + ab * Cfg::N;
 #pragma unroll
                     for (int ks = 0; ks < FKC / 8; ++ks) {
                         const uint32_t ko = ks * 2 * FSBO;   // 8 channels = two K atoms
-                        f_mma(dcol, f_desc(aHi + ko), f_desc(bHi + ko), (first && ks == 0) ? 0u : 1u);
-                        f_mma(dcol, f_desc(aHi + ko), f_desc(bLo + ko), 1u);
-                        f_mma(dcol, f_desc(aLo + ko), f_desc(bHi + ko), 1u);
+                        f_mma(dcol, f_desc(aHi + ko), f_desc(bHi + ko), Cfg::IDESC, (first && ks == 0) ? 0u : 1u);
+                        f_mma(dcol, f_desc(aHi + ko), f_desc(bLo + ko), Cfg::IDESC, 1u);
+                        f_mma(dcol, f_desc(aLo + ko), f_desc(bHi + ko), Cfg::IDESC, 1u);
                     }
                     f_commit(&bar_empty[s]);
                     if (last) f_commit(&bar_acc_full[ab]);
@@ -283,37 +298,39 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         asm volatile("setmaxnreg.inc.sync.aligned.u32 200;\n" ::);
         // element (channel k of the stage, position mn) of a plane lives at
         //   ((mn >> 5) * 8 + (k >> 2)) * 512 + (k & 3) * 128 + ((((mn & 31) >> 3) ^ (k & 3)) * 32) + (mn & 7) * 4
-        // B: this warp's patch row is MN atom `warp`, lane = column; A: atom warp >> 1, channels (warp & 1) * 16 ...
+        // B: this warp stages patch row brow (= MN atom brow) for channels bch0 .. bch0 + NB - 1, lane = column;
+        // A: atom warp >> 1, channels (warp & 1) * 16 ...
+        const int brow = warp % CR, bch0 = (warp / CR) * Cfg::NB;
         uint32_t stsA[4], stsB[4];
 #pragma unroll
         for (int kr = 0; kr < 4; ++kr) {
             const uint32_t x = (uint32_t)(kr * 128 + (((lane >> 3) ^ kr) * 32) + (lane & 7) * 4);
-            stsB[kr] = smemBase + 2 * FA_BYTES + warp * FLBO + x;
+            stsB[kr] = smemBase + 2 * FA_BYTES + brow * FLBO + (bch0 / 4) * FSBO + x;
             stsA[kr] = smemBase + (warp >> 1) * FLBO + (warp & 1) * (FNA / 4) * FSBO + x;
         }
         const int aqrow = 2 * (warp >> 1) + (lane >> 4), aqcol = lane & 15;   // query staged by this lane for A
 
-        FCursor ld, st;
+        FCursor<CR> ld, st;
         ld.start(p);
         st.start(p);
         uint32_t k = 0;   // chunks stored
 
-        auto load = [&](float (&v)[FNB + FNA], const FCursor& c) {
+        auto load = [&](float (&v)[Cfg::NB + FNA], const FCursor<CR>& c) {
             const int c0 = c.ch * FKC;
-            {   // B: patch row (8g + warp), column lane (column 31 is padding)
-                const int gi = c.i0 - FD + 8 * c.g + warp, gj = c.j0 - FD + lane;
+            {   // B: patch row (CR*g + brow), column lane (column 31 is padding), channels c0 + bch0 + j
+                const int gi = c.i0 - FD + CR * c.g + brow, gj = c.j0 - FD + lane;
                 const bool ok = lane < FQCOLS + FTD - 1 && gi >= 0 && gi < H && gj >= 0 && gj < W;
-                const int nch = C - c0;
-                uint64_t ba = (uint64_t)(fm1 + ((size_t)c.b * C + c0) * plane + (size_t)(ok ? gi * W + gj : 0));
-                if (ok && nch >= FNB) {
+                const int nch = C - (c0 + bch0);
+                uint64_t ba = (uint64_t)(fm1 + ((size_t)c.b * C + (nch > 0 ? c0 + bch0 : 0)) * plane + (size_t)(ok ? gi * W + gj : 0));
+                if (ok && nch >= Cfg::NB) {
 #pragma unroll
-                    for (int j = 0; j < FNB; ++j) {
+                    for (int j = 0; j < Cfg::NB; ++j) {
                         v[j] = f_ldg_stream(ba);
                         ba += planeBytes;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < FNB; ++j) {
+                    for (int j = 0; j < Cfg::NB; ++j) {
                         v[j] = (ok && j < nch) ? f_ldg_stream(ba) : 0.f;
                         ba += planeBytes;
                     }
@@ -327,29 +344,29 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
                 uint64_t ba = (uint64_t)(fm0 + ((size_t)c.b * C + (nch > 0 ? ca : 0)) * plane + (size_t)(ok ? gi * W + gj : 0));
 #pragma unroll
                 for (int j = 0; j < FNA; ++j) {
-                    v[FNB + j] = (ok && j < nch) ? __ldg(reinterpret_cast<const float*>(ba)) : 0.f;
+                    v[Cfg::NB + j] = (ok && j < nch) ? __ldg(reinterpret_cast<const float*>(ba)) : 0.f;
                     ba += planeBytes;
                 }
             }
         };
-        auto store = [&](const float (&v)[FNB + FNA], auto S) {
-            constexpr uint32_t so = decltype(S)::value * FSTAGE_BYTES;
+        auto store = [&](const float (&v)[Cfg::NB + FNA], auto S) {
+            constexpr uint32_t so = decltype(S)::value * Cfg::STAGE_BYTES;
 #pragma unroll
             for (int j = 0; j < FNA; ++j) {
-                const float hi = f_tf32_rn(v[FNB + j]);
+                const float hi = f_tf32_rn(v[Cfg::NB + j]);
                 const uint32_t ad = stsA[j & 3] + so + (j >> 2) * FSBO;
                 f_sts(ad, hi);
-                f_sts(ad + FA_BYTES, v[FNB + j] - hi);
+                f_sts(ad + FA_BYTES, v[Cfg::NB + j] - hi);
             }
 #pragma unroll
-            for (int j = 0; j < FNB; ++j) {
+            for (int j = 0; j < Cfg::NB; ++j) {
                 const float hi = f_tf32_rn(v[j]);
                 const uint32_t ad = stsB[j & 3] + so + (j >> 2) * FSBO;
                 f_sts(ad, hi);
-                f_sts(ad + FB_BYTES, v[j] - hi);
+                f_sts(ad + Cfg::B_BYTES, v[j] - hi);
             }
         };
-        auto step = [&](float (&v)[FNB + FNA], auto S) {
+        auto step = [&](float (&v)[Cfg::NB + FNA], auto S) {
             constexpr int s = decltype(S)::value;
             f_mbar_wait(&bar_empty[s], ((k >> 1) & 1u) ^ 1u);   // the MMAs that read this stage two chunks ago are done
             store(v, S);
@@ -364,7 +381,7 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
             st.advance(p);
         };
 
-        float va[FNB + FNA], vb[FNB + FNA];
+        float va[Cfg::NB + FNA], vb[Cfg::NB + FNA];
         if (ld.valid(p)) { load(va, ld); ld.advance(p); }
         if (ld.valid(p)) { load(vb, ld); ld.advance(p); }
         while (st.valid(p)) {
@@ -378,7 +395,7 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * FN)));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * Cfg::N)));
     }
 }
 
@@ -392,6 +409,30 @@ bool corr_umma_fwd_supported(int B, int C, int H, int W, int d, int stride) {
     return true;
 }
 
+template <int CR>
+static int f_count_items(int H, int tilesX, int tilesY) {
+    int perImage = 0;
+    for (int ty = 0; ty < tilesY; ++ty) {
+        int ng = 0;
+        for (int g = 0; g < FCfg<CR>::NCH; ++g) ng += f_chunk_valid<CR>(ty * FQROWS, g, H) ? 1 : 0;
+        perImage += ng * tilesX;
+    }
+    return perImage;
+}
+
+template <int CR>
+static int f_launch(const float* fm0, const float* fm1, float* out, FPlan p, int sms, cudaStream_t st) {
+    p.itemsPerImage = f_count_items<CR>(p.H, p.tilesX, p.tilesY);
+    p.nItems = p.B * p.itemsPerImage;
+    const size_t smem = (size_t)FSTAGES * FCfg<CR>::STAGE_BYTES + 1024;
+    D2T_SMEM_OPTIN(corr_fwd_umma_kernel<CR>, smem);
+    const int grid = p.nItems < sms ? p.nItems : sms;
+    corr_fwd_umma_kernel<CR><<<grid, FTHREADS, smem, st>>>(fm0, fm1, out, p);
+    D2T_CUDA_TRY(cudaGetLastError());
+    note_launch();
+    return D2T_OK;
+}
+
 int corr_umma_fwd_launch(const float* fm0, const float* fm1, float* out, int B, int C, int H, int W, const CorrOutStrides* os,
                          cudaStream_t st) {
     DeviceInfo di;
@@ -401,27 +442,15 @@ int corr_umma_fwd_launch(const float* fm0, const float* fm1, float* out, int B, 
     p.B = B; p.C = C; p.H = H; p.W = W;
     p.tilesX = ceil_div(W, FQCOLS);
     p.tilesY = ceil_div(H, FQROWS);
-    int perImage = 0;
-    for (int ty = 0; ty < p.tilesY; ++ty) {
-        int ng = 0;
-        for (int g = 0; g < 3; ++g) ng += f_chunk_valid(ty * FQROWS, g, H) ? 1 : 0;
-        perImage += ng * p.tilesX;
-    }
-    p.itemsPerImage = perImage;
-    p.nItems = B * perImage;
     p.nChunks = ceil_div(C, FKC);
     if (os) {
         p.os = *os;
     } else {
         p.os.sb = (long long)H * W * FKK; p.os.sp = FKK; p.os.st = 1;
     }
-    const size_t smem = (size_t)FSTAGES * FSTAGE_BYTES + 1024;
-    D2T_SMEM_OPTIN(corr_fwd_umma_kernel, smem);
-    const int grid = p.nItems < di.sm_count ? p.nItems : di.sm_count;
-    corr_fwd_umma_kernel<<<grid, FTHREADS, smem, st>>>(fm0, fm1, out, p);
-    D2T_CUDA_TRY(cudaGetLastError());
-    note_launch();
-    return D2T_OK;
+    // 8-row chunks unless they would leave more than half of the SMs without an item (scheduling only: same bits)
+    if (2 * B * f_count_items<8>(H, p.tilesX, p.tilesY) <= di.sm_count) return f_launch<4>(fm0, fm1, out, p, di.sm_count, st);
+    return f_launch<8>(fm0, fm1, out, p, di.sm_count, st);
 }
 
 }  // namespace d2t
