@@ -38,6 +38,16 @@
 
 #include "corr_common.cuh"
 
+// Timing ablation only (tools/experiments/staging_ablation.sh; NEVER defined by csrc/Makefile -- results are garbage):
+//   1  the producers skip the global loads of the X operand (what the LDGs cost)
+//   2  ... and replace its scalar hi/lo stores by what the split warps of a TMA-fed kernel would execute if the raw X tile
+//      had landed in shared memory by itself: LDS.128 raw -> lo = v - trunc_tf32(v) -> STS.128 lo  (raw doubles as hi)
+//   3  as 2, with the rounded hi written back in place as well (the gemm_tf32x3 recipe)
+// The S operand (built from gradOut) is staged as in the product in every mode.
+#ifndef D2T_ABLATE_STAGING
+#define D2T_ABLATE_STAGING 0
+#endif
+
 namespace d2t {
 
 namespace {
@@ -303,6 +313,11 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
         // byte addresses, advanced one plane per channel (kept as integers so that the compiler does not fall back to
         // element-index arithmetic: 2 instructions per load instead of 4)
         uint64_t ba = (uint64_t)(xsrc + ((size_t)c.b * C + c0) * plane + (size_t)gi * W + gj);
+#if D2T_ABLATE_STAGING
+#pragma unroll
+        for (int j = 0; j < XNB; ++j) v[j] = 0.f;
+        (void)ba; (void)bok; (void)nch;
+#else
         if (bok && nch >= XNB) {
 #pragma unroll
             for (int j = 0; j < XNB; ++j) {
@@ -316,6 +331,7 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
                 ba += planeBytes;
             }
         }
+#endif
         const int si = c.r - warp;  // row displacement of query row `warp` for this patch row (warp-uniform)
         uint32_t m = 0;
         if (si >= 0 && si < XTD && c.i0 + warp < H) {
@@ -343,6 +359,22 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
             x_sts(ad, hi);
             x_sts(ad + XA_BYTES, v[XNB + j] - hi);
         }
+#if D2T_ABLATE_STAGING >= 2
+        {
+            const uint32_t hiBase = smemBase + so + 2 * XA_BYTES, loBase = hiBase + XB_BYTES;
+            for (int e = tid * 16; e < XB_BYTES; e += XPROD_WARPS * 32 * 16) {
+                float4 q;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(hiBase + e));
+                const float4 h = make_float4(x_tf32_rn(q.x), x_tf32_rn(q.y), x_tf32_rn(q.z), x_tf32_rn(q.w));
+                if (D2T_ABLATE_STAGING >= 3)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hiBase + e), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(loBase + e), "f"(q.x - h.x), "f"(q.y - h.y), "f"(q.z - h.z),
+                             "f"(q.w - h.w)
+                             : "memory");
+            }
+            return;
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < XNB; ++j) {
             const float hi = x_tf32_rn(v[j]);

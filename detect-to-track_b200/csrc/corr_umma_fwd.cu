@@ -30,6 +30,15 @@
 //   determinism  fixed channel order, no partial sums, no atomics: bitwise reproducible.
 #include "corr_common.cuh"
 
+// Timing ablation only (tools/experiments/staging_ablation.sh; NEVER defined by csrc/Makefile -- results are garbage):
+//   1  the producers skip the global loads of both operands (what the LDGs cost)
+//   2  ... and replace their scalar hi/lo stores by what the split warps of a TMA-fed kernel would execute if the raw tile
+//      had landed in shared memory by itself: LDS.128 raw -> lo = v - trunc_tf32(v) -> STS.128 lo  (raw doubles as hi)
+//   3  as 2, with the rounded hi written back in place as well (the gemm_tf32x3 recipe)
+#ifndef D2T_ABLATE_STAGING
+#define D2T_ABLATE_STAGING 0
+#endif
+
 namespace d2t {
 
 namespace {
@@ -316,6 +325,11 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         uint32_t k = 0;   // chunks stored
 
         auto load = [&](float (&v)[Cfg::NB + FNA], const FCursor<CR>& c) {
+#if D2T_ABLATE_STAGING
+#pragma unroll
+            for (int j = 0; j < Cfg::NB + FNA; ++j) v[j] = 0.f;
+            return;
+#endif
             const int c0 = c.ch * FKC;
             {   // B: patch row (CR*g + brow), column lane (column 31 is padding), channels c0 + bch0 + j
                 const int gi = c.i0 - FD + CR * c.g + brow, gj = c.j0 - FD + lane;
@@ -351,6 +365,27 @@ corr_fwd_umma_kernel(const float* __restrict__ fm0, const float* __restrict__ fm
         };
         auto store = [&](const float (&v)[Cfg::NB + FNA], auto S) {
             constexpr uint32_t so = decltype(S)::value * Cfg::STAGE_BYTES;
+#if D2T_ABLATE_STAGING >= 2
+            {   // [A hi | A lo | B hi | B lo]: vector split of the A and B tiles by the 256 producer threads
+                const uint32_t st0 = smemBase + so;
+                auto split = [&](uint32_t hiBase, uint32_t loBase, int bytes) {
+                    for (int e = tid * 16; e < bytes; e += FPROD_WARPS * 32 * 16) {
+                        float4 q;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(hiBase + e));
+                        const float4 h = make_float4(f_tf32_rn(q.x), f_tf32_rn(q.y), f_tf32_rn(q.z), f_tf32_rn(q.w));
+                        if (D2T_ABLATE_STAGING >= 3)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hiBase + e), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(loBase + e), "f"(q.x - h.x), "f"(q.y - h.y),
+                                     "f"(q.z - h.z), "f"(q.w - h.w)
+                                     : "memory");
+                    }
+                };
+                split(st0, st0 + FA_BYTES, FA_BYTES);
+                split(st0 + 2 * FA_BYTES, st0 + 2 * FA_BYTES + Cfg::B_BYTES, Cfg::B_BYTES);
+                (void)v;
+                return;
+            }
+#endif
 #pragma unroll
             for (int j = 0; j < FNA; ++j) {
                 const float hi = f_tf32_rn(v[Cfg::NB + j]);

@@ -147,6 +147,17 @@ def main():
             if ref is not None:
                 report("  REF psroipool fwd", timeit(lambda: ref.psroipool_fwd(fm, rois, nT, k), 4, flush), None, fb)
                 report("  REF psroipool bwd", timeit(lambda: ref.psroipool_bwd(go, rois, H, W), 4, flush), None, bb)
+    if not args.only or "psbatch" in args.only:
+        H, W, k, R, NF = 38, 63, 7, 300, 16
+        rois = torch.stack([torch.from_numpy(cases.rois_random(R, 1237 + f)) for f in range(NF)]).to(dev)
+        for nm, nT, live in (("cls nT=31", 31, 608), ("reg nT=4", 4, 117)):
+            fm = torch.randn(NF, nT * k * k, H, W, generator=g).to(dev)
+            go = torch.randn(NF, R, nT, k, k, generator=g).to(dev)
+            fb = NF * (live * H * W * 4 + R * nT * k * k * 4 + R * 16)
+            bb = NF * (nT * k * k * H * W * 4 + R * nT * k * k * 4 + R * 16)
+            report(f"psroipool batched fwd {nm} {NF} frames (summed-area)", timeit(lambda: ps.ps_roipool_forward_batched(fm, rois, nT, k), args.iters, flush), None, fb)
+            report(f"psroipool batched fwd {nm} {NF} frames (exact order)", timeit(lambda: ps.ps_roipool_forward_batched(fm, rois, nT, k, False, True), args.iters, flush), None, fb)
+            report(f"psroipool batched bwd {nm} {NF} frames", timeit(lambda: ps.ps_roipool_backward_batched(go, rois, H, W), args.iters, flush), None, bb)
     if args.json:
         Path(args.json).write_text(json.dumps(rows, indent=1))
 
