@@ -136,100 +136,6 @@ psb_fwd_kernel(const float* __restrict__ fm, const uint32_t* __restrict__ edges,
 }
 
 // ----------------------------------------------------------------------------------------------------
-// forward, second generation: summed-area tables.  grid (ceil(nCh / kPsfPlanes), N): CTA = (frame, 4 consecutive channels)
-// ----------------------------------------------------------------------------------------------------
-// psb_fwd_kernel above is instruction-bound (ncu: issue 83 %, 70 % of the instructions in the cell loop): a lane sums its
-// cell pixel by pixel, and the 32 RoIs of a warp have unrelated cell sizes, so every warp walks the largest cell.  Here the
-// CTA turns its plane into a summed-area table  S[y][x] = sum_{y' < y, x' < x} fm[y'][x']  held in DOUBLE precision --
-// sums of at most H*W floats are exact to ~1e-16 relative, so the cancellation of the four-corner lookup costs nothing --
-// and a cell is  S[i1][j1] - S[i0][j1] - S[i1][j0] + S[i0][j0], rounded to float once, then divided by its size like the
-// reference (ps_roipool_cuda.cu:60-69): four loads per output whatever the cell size, no divergence.  The result is the
-// correctly rounded cell sum; the reference's left-to-right float sum differs from it by its own rounding (a few 1e-7
-// relative; tested at rtol 1e-4 + atol 1e-5 max|ref|).  D2T_PS_EXACT_ORDER keeps the bit-identical kernel.
-//   table    thread x runs down column x of the plane straight from global memory (coalesced across the threads, the
-//            loads of a column are independent and issued 8 deep): V[y][x] = column prefix; then thread y runs along row
-//            y of V.  Two short serial passes of H resp. W steps instead of a log-step scan: fewer instructions, and a
-//            handful of CTAs per SM overlap each other's chains.
-//   outputs  thread <- (user of the channel, RoI): packed bin edges from a shared copy of the frame's table (the edge
-//            kernel's output), 4 x LDS.64, 3 x DADD, one float division, one store.
-// Deviation: a non-finite value in the plane reaches every cell below / right of it (Inf - Inf), not only the cells that
-// contain it; the exact kernel keeps the reference's behaviour.
-constexpr int kPsfThreads = 128;
-constexpr int kPsfPlanes = 4;
-__host__ __device__ constexpr int psf_pitch(int W) { return (W + 1) | 1; }   // doubles per table row; odd => row-walkers 2-way at worst
-__global__ void __launch_bounds__(kPsfThreads)
-psf_fwd_kernel(const float* __restrict__ fm, const uint32_t* __restrict__ edges, float* __restrict__ out, int R, int nT, int H,
-               int W, int k, int canonical) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int kk = k * k, nCh = nT * kk, HW = H * W;
-    const int pitch = psf_pitch(W);
-    double* S = reinterpret_cast<double*>(smem_raw);                           // [H + 1][pitch]
-    uint32_t* ed = reinterpret_cast<uint32_t*>(S + (size_t)(H + 1) * pitch);   // [R * k] packed edges of the frame
-    uint32_t* us = ed + (size_t)R * k;                                         // [kk]
-    int* cnt = reinterpret_cast<int*>(us + kk);                                // [8]
-    const int tid = threadIdx.x, n = blockIdx.y;
-    const int ch0 = blockIdx.x * kPsfPlanes, ch1 = min(ch0 + kPsfPlanes, nCh);
-    {
-        const uint32_t* eg = edges + (size_t)n * R * k;
-        for (int idx = tid; idx < R * k; idx += kPsfThreads) ed[idx] = __ldg(eg + idx);
-        for (int x = tid; x <= W; x += kPsfThreads) S[x] = 0.0;            // row 0
-        for (int y = tid; y <= H; y += kPsfThreads) S[(size_t)y * pitch] = 0.0;   // column 0
-    }
-    float* o = out + (size_t)n * R * nCh;
-    for (int ch = ch0; ch < ch1; ++ch) {
-        __syncthreads();   // the previous plane's lookups (S, us) are finished; first time: ed / zero borders are written
-        const int nU = psb_users(ch, nT, kk, canonical != 0, us, cnt);
-        if (nU == 0) continue;   // uniform: nobody reads this channel
-        const float* src = fm + ((size_t)n * nCh + ch) * HW;
-        for (int x = tid; x < W; x += kPsfThreads) {   // column prefixes
-            double acc = 0.0;
-            const float* p = src + x;
-            double* d = S + pitch + x + 1;
-#pragma unroll 8
-            for (int y = 0; y < H; ++y) {
-                acc += (double)__ldg(p + (size_t)y * W);
-                d[(size_t)y * pitch] = acc;
-            }
-        }
-        __syncthreads();
-        for (int y = tid + 1; y <= H; y += kPsfThreads) {   // row prefixes of the column prefixes
-            double* row = S + (size_t)y * pitch;
-            double acc = 0.0;
-#pragma unroll 8
-            for (int x = 1; x <= W; ++x) {
-                acc += row[x];
-                row[x] = acc;
-            }
-        }
-        __syncthreads();
-        for (int idx = tid; idx < nU * R; idx += kPsfThreads) {
-            const int u = idx / R, r = idx - u * R;
-            const uint32_t pk = us[u];
-            const int t = pk >> 16, b = pk & 0xffff;
-            const int i = b / k, j = b - i * k;
-            const uint32_t ei = ed[r * k + i], ej = ed[r * k + j];
-            const int i0 = ei & 255, i1 = (ei >> 8) & 255, j0 = (ej >> 16) & 255, j1 = ej >> 24;
-            float acc = 0.f;
-            if (i1 > i0 && j1 > j0) {   // an empty cell sums nothing (the reference's loops do not run)
-                const double* r0 = S + (size_t)i0 * pitch;
-                const double* r1 = S + (size_t)i1 * pitch;
-                acc = (float)((r1[j1] - r0[j1]) - (r1[j0] - r0[j0]));
-            }
-            const int numel = (i1 - i0) * (j1 - j0);
-            if (numel > 0) acc /= numel;
-            if (t == 0xFFFF) {  // channel 0 of the reference map: bin 0 of every target reads it
-                for (int tt = 0; tt < nT; ++tt) o[((size_t)r * nT + tt) * kk] = acc;
-            } else {
-                o[((size_t)r * nT + t) * kk + b] = acc;
-            }
-        }
-    }
-}
-static size_t psf_smem(int R, int H, int W, int k) {
-    return (size_t)(H + 1) * psf_pitch(W) * sizeof(double) + (size_t)R * k * 4 + (size_t)k * k * 4 + 64;
-}
-
-// ----------------------------------------------------------------------------------------------------
 // backward 2: Vt[((n*kk + b)*nT + t)*R + r] = grad_out[((n*R + r)*nT + t)*kk + b] / cell size
 // ----------------------------------------------------------------------------------------------------
 // grid (ceil(R/32), nT, N), 128 threads: a 32-RoI x kk tile goes through shared memory
@@ -602,17 +508,10 @@ int psb_fwd_launch(const float* fm, const float* rois, float* out, int N, int R,
     uint32_t* edges = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + L.edgesOff);
     int rc = psb_edges_launch(rois, edges, nullptr, N, R, k, H, W, st);
     if (rc) return rc;
-    const int canonical = (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0;
-    const size_t smemS = psf_smem(R, H, W, k);
-    if (!(flags & D2T_PS_EXACT_ORDER) && smemS <= 48 * 1024) {
-        // default: summed-area tables (a few CTAs per SM need the table + the frame's edges to stay below ~48 KB)
-        D2T_SMEM_OPTIN(psf_fwd_kernel, smemS);
-        psf_fwd_kernel<<<dim3(ceil_div(nT * k * k, kPsfPlanes), N), kPsfThreads, smemS, st>>>(fm, edges, out, R, nT, H, W, k, canonical);
-    } else {
-        const size_t smem = (size_t)H * W * 4 + (size_t)k * k * 4 + 64;
-        D2T_SMEM_OPTIN(psb_fwd_kernel, smem);
-        psb_fwd_kernel<<<dim3(nT * k * k, N), kPsbFwdThreads, smem, st>>>(fm, edges, out, R, nT, H, W, k, canonical);
-    }
+    const size_t smem = (size_t)H * W * 4 + (size_t)k * k * 4 + 64;
+    D2T_SMEM_OPTIN(psb_fwd_kernel, smem);
+    psb_fwd_kernel<<<dim3(nT * k * k, N), kPsbFwdThreads, smem, st>>>(fm, edges, out, R, nT, H, W, k,
+                                                                     (flags & D2T_PS_CANONICAL_MAP) ? 1 : 0);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;

@@ -16,7 +16,6 @@ from . import _lib
 from .roipool import _check_rois
 
 _CANONICAL = 1  # D2T_PS_CANONICAL_MAP
-_EXACT_ORDER = 2  # D2T_PS_EXACT_ORDER (batched forward: the reference's pixel-order sum instead of the summed-area lookup)
 
 
 def ps_roipool_forward(FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
@@ -73,13 +72,10 @@ def _check_batched(x: Tensor, rois: Tensor, what: str) -> None:
         raise RuntimeError(f"rois must be (N, |R|, 4) with N = {x.size(0)}; got {tuple(rois.shape)}")
 
 
-def ps_roipool_forward_batched(FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False,
-                               exact_order: bool = False) -> Tensor:
+def ps_roipool_forward_batched(FM: Tensor, rois: Tensor, n_targets: int, r_hw: int, canonical_map: bool = False) -> Tensor:
     """N frames in one set of launches: FM (N, n_targets*r_hw^2, H, W), rois (N, |R|, 4) ->
-    (N, |R|, n_targets, r_hw, r_hw).  Default: every cell is a four-corner lookup in a double-precision summed-area table
-    (the correctly rounded cell sum; equal to N calls of `ps_roipool_forward` up to the rounding of the reference's own
-    pixel-order float sum).  `exact_order=True` sums pixel by pixel in the reference's order: bit-identical to
-    `ps_roipool_forward`, about 3x slower.  Extension: the reference pools one frame per call (rfcn.py:36-41)."""
+    (N, |R|, n_targets, r_hw, r_hw).  Bit-identical to N calls of `ps_roipool_forward`.  Extension: the reference
+    pools one frame per call (rfcn.py:36-41)."""
     if FM.dim() != 4:
         raise RuntimeError(f"FM must be (N, n_targets*r_hw^2, H, W); got {tuple(FM.shape)}")
     _check_batched(FM, rois, "FM")
@@ -94,7 +90,7 @@ def ps_roipool_forward_batched(FM: Tensor, rois: Tensor, n_targets: int, r_hw: i
         ws, ws_ptr, ws_n = _lib.workspace(nbytes, FM.device)
         rc = lib.d2t_psroipool_fwd_batched_f32(
             FM.data_ptr(), rois.data_ptr(), out.data_ptr(), N, R, n_targets, H, W, r_hw,
-            (_CANONICAL if canonical_map else 0) | (_EXACT_ORDER if exact_order else 0), ws_ptr, ws_n, _lib.stream_ptr(FM.device))
+            _CANONICAL if canonical_map else 0, ws_ptr, ws_n, _lib.stream_ptr(FM.device))
         _lib.check(rc, "ps_roipool_forward_batched")
     return out
 

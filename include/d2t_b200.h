@@ -173,11 +173,6 @@ D2T_API int d2t_roipool_bwd_f64(const double* grad_out, const double* rois, doub
  *        t*k*k + i*k + j; 0 (default) = the reference's (t+1)*(i*k+j) (F6).
  */
 #define D2T_PS_CANONICAL_MAP 1
-/*        bit 1 (D2T_PS_EXACT_ORDER), batched forward only: sum every cell pixel by pixel in the reference's order
- *        (bit-identical to ps_roipool_cuda.cu:60-69) instead of the default summed-area lookup, whose result is the
- *        correctly rounded cell sum and differs from the reference's float sum by rounding only (rtol 1e-4 contract).
- *        The single-frame entry points always keep the reference's order. */
-#define D2T_PS_EXACT_ORDER 2
 D2T_API size_t d2t_psroipool_fwd_workspace_bytes(int R, int n_targets, int H, int W, int r_hw, int elem_size);
 D2T_API int d2t_psroipool_fwd_f32(const float* fm, const float* rois, float* out, int R, int n_targets, int H, int W,
                           int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
@@ -194,9 +189,8 @@ D2T_API int d2t_psroipool_bwd_f64(const double* grad_out, const double* rois, do
 /* ---- PSROIPool over a batch of frames (float32) ---------------------------
  * Extension: the reference pools one frame per call (rfcn.py:36-41, called per frame from trainer.py:208-209).
  * fm : (N, n_targets*r_hw^2, H, W);  rois : (N, R, 4);  out / grad_out : (N, R, n_targets, r_hw, r_hw);
- * grad_fm : (N, n_targets*r_hw^2, H, W).  Frame n uses rois[n].  One set of launches covers all frames (a CTA owns
- * (frame, channel) planes).  Forward: summed-area tables in double precision -- equal to N single-frame calls up to the
- * rounding of the reference's own pixel-order sum; with D2T_PS_EXACT_ORDER bit-identical to them.
+ * grad_fm : (N, n_targets*r_hw^2, H, W).  Frame n uses rois[n].  Results are bit-identical to N single-frame calls;
+ * one set of launches covers all frames (a CTA owns one (frame, channel) plane).
  */
 D2T_API size_t d2t_psroipool_fwd_batched_workspace_bytes(int N, int R, int n_targets, int H, int W, int r_hw, int elem_size);
 D2T_API int d2t_psroipool_fwd_batched_f32(const float* fm, const float* rois, float* out, int N, int R, int n_targets,

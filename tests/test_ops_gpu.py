@@ -739,10 +739,9 @@ def test_psroipool_full_size_cls_head(cuda):
 @pytest.mark.parametrize("canonical", [False, True])
 @pytest.mark.parametrize("N,nT,H,W,k,R", [(3, 4, 38, 63, 7, 50), (2, 31, 38, 63, 7, 300), (4, 2, 11, 10, 6, 9), (1, 5, 20, 21, 3, 700)])
 def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
-    """the batched entry points (one set of launches for N frames) against N single-frame calls: with exact_order the
-    forward is bit-identical (both keep the reference's summation order), the default summed-area forward (correctly rounded
-    cell sums) agrees within the FP32 tolerance and is reproducible; the backward agrees within the FP32 tolerance (a batch
-    runs the row-list kernels, a single frame the one-launch kernel: different, each fixed, summation orders); all match the
+    """the batched entry points (one set of launches for N frames) against N single-frame calls: the forward is
+    bit-identical (both keep the reference's summation order); the backward agrees within the FP32 tolerance (a batch runs
+    the row-list kernels, a single frame the one-launch kernel: different, each fixed, summation orders); both match the
     oracle (R = 700 on a 20x21 map: long row lists, many RoIs per pixel)."""
     rng = np.random.default_rng(36)
     rois = np.stack([np.concatenate([cases.rois_edge_cases(H, W), cases.rois_random(R, 40 + n), cases.ROIS_OOB.astype(np.float32)])
@@ -750,9 +749,7 @@ def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
     Rt = rois.shape[1]
     fm = rng.standard_normal((N, nT * k * k, H, W)).astype(np.float32)
     go = rng.standard_normal((N, Rt, nT, k, k)).astype(np.float32)
-    out = ps_mod.ps_roipool_forward_batched(dev(fm, cuda), dev(rois, cuda), nT, k, canonical, exact_order=True)
-    sat = ps_mod.ps_roipool_forward_batched(dev(fm, cuda), dev(rois, cuda), nT, k, canonical)
-    assert torch.equal(sat, ps_mod.ps_roipool_forward_batched(dev(fm, cuda), dev(rois, cuda), nT, k, canonical))
+    out = ps_mod.ps_roipool_forward_batched(dev(fm, cuda), dev(rois, cuda), nT, k, canonical)
     gin = ps_mod.ps_roipool_backward_batched(dev(go, cuda), dev(rois, cuda), H, W, canonical)
     assert torch.equal(gin, ps_mod.ps_roipool_backward_batched(dev(go, cuda), dev(rois, cuda), H, W, canonical))
     for n in range(N):
@@ -762,14 +759,7 @@ def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
         close(g1, gin[n].cpu().numpy(), np.float32)
         assert torch.equal(g1, ps_mod.ps_roipool_backward(dev(go[n], cuda), dev(rois[n], cuda), H, W, canonical))
         close(g1, oracle.psroipool_bwd(go[n], rois[n], H, W, canonical), np.float32)
-        want = oracle.psroipool_fwd(fm[n], rois[n], nT, k, canonical)
-        np.testing.assert_array_equal(out[n].cpu().numpy(), want)
-        close(sat[n], want, np.float32)
-        # the summed-area result is the correctly rounded cell mean: compare with a float64 evaluation of the same cells
-        w64 = oracle.psroipool_fwd(fm[n].astype(np.float64), rois[n].astype(np.float64), nT, k, canonical)
-        e32 = oracle.psroipool_fwd(fm[n], rois[n], nT, k, canonical).astype(np.float64)
-        same_cells = np.abs(e32 - w64) <= 1e-5 * np.abs(w64).max()   # (float64 RoIs can move an edge; skip those cells)
-        assert np.abs(sat[n].cpu().numpy().astype(np.float64) - w64)[same_cells].max() <= 2e-7 * np.abs(w64).max()
+        np.testing.assert_array_equal(out[n].cpu().numpy(), oracle.psroipool_fwd(fm[n], rois[n], nT, k, canonical))
         close(gin[n], oracle.psroipool_bwd(go[n], rois[n], H, W, canonical), np.float32)
 
 
@@ -784,7 +774,7 @@ def test_psroipool_batched_module_autograd(cuda):
     fm2 = fm.detach().clone().requires_grad_(True)
     outs = torch.stack([d2t.PSROIPool(nT, k)(fm2[n], rois[n]) for n in range(N)])
     (outs * w).sum().backward()
-    close(out, outs.detach().cpu().numpy(), np.float32)   # summed-area forward vs the reference's pixel-order sum
+    assert torch.equal(out, outs)
     close(fm.grad, fm2.grad.cpu().numpy(), np.float32)
     with pytest.raises(ValueError):
         d2t.PSROIPoolBatched(nT, k)(fm[:, :-1].contiguous(), rois)
@@ -819,15 +809,12 @@ def test_psroipool_vote_matches_pool_then_mean(cuda, N, nT, H, W, k, R, canonica
 
 
 def test_psroipool_single_frame_and_batched_kernels_agree(cuda):
-    """the single-frame entry point runs the per-output kernel, the batched one the channel-owner kernels: bit-identical with
-    exact_order, within the FP32 tolerance for the default summed-area tables"""
+    """the single-frame entry point runs the per-output kernel, the batched one the channel-owner kernels: bit-identical"""
     nT, H, W, k = 4, 38, 63, 7
     rois = _roipool_rois(H, W, np.float32, R=60)
     fm, _ = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 37, np.float32)
     tf, tr = dev(fm, cuda), dev(rois, cuda)
-    one = ps_mod.ps_roipool_forward(tf, tr, nT, k)
-    assert torch.equal(one, ps_mod.ps_roipool_forward_batched(tf[None], tr[None], nT, k, exact_order=True)[0])
-    close(ps_mod.ps_roipool_forward_batched(tf[None], tr[None], nT, k)[0], one.cpu().numpy(), np.float32)
+    assert torch.equal(ps_mod.ps_roipool_forward(tf, tr, nT, k), ps_mod.ps_roipool_forward_batched(tf[None], tr[None], nT, k)[0])
 
 
 # ------------------------------------------------------------------ error behaviour + autograd wiring

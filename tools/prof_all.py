@@ -3,7 +3,7 @@ correlation c5 B=8 (SIMT forward + finalize, flip + tcgen05 backward), track-hea
 batched over 16 frames fwd/bwd and single-frame, fused track head fwd/bwd.
 
     python tools/prof_all.py [passes]
-    ncu --set full --clock-control none --import-source on -k regex:'corr_|roipool_|psb_|psf_|psroipool_|gemm_|th_' \
+    ncu --set full --clock-control none --import-source on -k regex:'corr_|roipool_|psb_|psroipool_|gemm_|th_' \
         -s <launches of the warm-up pass> -c <launches of one pass> -o gpurun_out/prof_all python tools/prof_all.py 2
 """
 import sys

@@ -155,8 +155,7 @@ def main():
             go = torch.randn(NF, R, nT, k, k, generator=g).to(dev)
             fb = NF * (live * H * W * 4 + R * nT * k * k * 4 + R * 16)
             bb = NF * (nT * k * k * H * W * 4 + R * nT * k * k * 4 + R * 16)
-            report(f"psroipool batched fwd {nm} {NF} frames (summed-area)", timeit(lambda: ps.ps_roipool_forward_batched(fm, rois, nT, k), args.iters, flush), None, fb)
-            report(f"psroipool batched fwd {nm} {NF} frames (exact order)", timeit(lambda: ps.ps_roipool_forward_batched(fm, rois, nT, k, False, True), args.iters, flush), None, fb)
+            report(f"psroipool batched fwd {nm} {NF} frames", timeit(lambda: ps.ps_roipool_forward_batched(fm, rois, nT, k), args.iters, flush), None, fb)
             report(f"psroipool batched bwd {nm} {NF} frames", timeit(lambda: ps.ps_roipool_backward_batched(go, rois, H, W), args.iters, flush), None, bb)
     if args.json:
         Path(args.json).write_text(json.dumps(rows, indent=1))
