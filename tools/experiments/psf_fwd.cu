@@ -4,7 +4,7 @@
 // 16 frames x 300 RoIs (profiles/r2_psf_experiment.txt):
 //   psb_fwd_kernel (shipped)                                     140 us   105 M warp instructions, issue 83 %
 //   double-precision summed-area table, column scan from global  263 us   latency: 5 serial load batches per plane
-//   same, cooperative prefetched plane loads, 256 threads        132 us   FP64: ~330 warp-level DADD/F2F per plane
+//   same, cooperative prefetched plane loads, 256 threads        132 us   two serial scans + 5 barriers per plane
 //   float row prefix sums (below)                                128 us   64 M warp instructions, barrier-bound
 // The per-OUTPUT work drops 3x (160 vs 460 instructions per 32 outputs), but a plane-owner kernel pays a fixed cost per
 // plane -- load, scan (a 63-step serial chain on 38 threads while the other warps wait at the barrier), users -- for only
@@ -22,8 +22,8 @@
 // in P[j1] - P[j0] costs ~W * 2^-24 of the row's magnitude (tested at rtol 1e-4 + atol 1e-5 max|ref|, and at 3e-6 max|ref|
 // against a float64 evaluation).  D2T_PS_EXACT_ORDER keeps the bit-identical kernel.
 // (A full summed-area table -- four loads per cell, no loop at all -- needs DOUBLE precision to be safe against maps with a
-// DC offset, and FP64 is what it then waits for: measured 263 us / 132 us after tuning against 140 us for the kernel
-// above; B200's FP64 rate does not carry a scan per plane.  profiles/r2_ncu_psf_summary.txt)
+// DC offset; it was measured first: 263 us, 132 us after tuning, against 140 us for the kernel above: two serial scans
+// per plane instead of one.  profiles/r2_psf_experiment.txt)
 //   planes   the CTA's live channels (host-computed bitmask, SURVEY.md F6: 608 of 1519) are walked in turn; the loads of
 //            plane p + 1 are in flight (registers) while plane p is scanned and looked up.
 //   scan     thread y runs along row y (W steps of LDS / FADD / STS; the reads are independent of the running sum).
