@@ -348,9 +348,13 @@ def run_train_step(torch, dev, rank, world, barrier, pairs=PAIRS_PER_GPU, steps=
     from detect_to_track_b200 import train_step as ts
     torch.manual_seed(1239)                               # identical initial weights on every rank
     out = {}
-    for fused in (False, True):
-        model = ts.DetectTrackModule("resnet101", 3, fused_tracker=fused).to(dev)
-        stepm = ts.DetectTrackTrainStep(model)
+    # reference_composition: the reference's module graph as it is (per-pair backbone calls, NCHW, conv -> FrozenBN as two ops);
+    # fused_tracker: + the fused tracker / vote operators; fast: + conv / frozen-BN folding, channels_last convolutions and
+    # ONE backbone / RPN call per minibatch (train_step.py: same function, tested) -- what a user of this package would run
+    for key, fused, fast in (("reference_composition", False, False), ("fused_tracker", True, False),
+                             ("fused_tracker_fast_backbone", True, True)):
+        model = ts.DetectTrackModule("resnet101", 3, fused_tracker=fused, fast_backbone=fast).to(dev)
+        stepm = ts.DetectTrackTrainStep(model, batch_backbone=fast)
         ddp = stepm
         if world > 1:
             ddp = torch.nn.parallel.DistributedDataParallel(stepm, device_ids=[dev.index], bucket_cap_mb=25,
@@ -392,7 +396,7 @@ def run_train_step(torch, dev, rank, world, barrier, pairs=PAIRS_PER_GPU, steps=
         ms, last = timed(True)
         ms_nosync = timed(False)[0] if world > 1 else ms
         ms, ms_nosync = global_max([ms, ms_nosync], dev)
-        out["fused_tracker" if fused else "reference_composition"] = {
+        out[key] = {
             "ms_per_step": ms, "pairs_per_s": world * pairs / (ms * 1e-3), "loss": last,
             "ms_per_step_without_gradient_sync": ms_nosync, "exposed_allreduce_ms": max(0.0, ms - ms_nosync)}
         out["trainable_parameter_mb"] = ts.trainable_parameter_bytes(stepm) / 1e6

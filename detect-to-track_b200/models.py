@@ -37,7 +37,9 @@ class _RFCNHead(nn.Module):
 
     def forward(self, x: Tensor, regions: Tensor) -> Tensor:
         x = x[None, :, :, :]
-        score_map = self.sm_conv(x).squeeze(0)
+        # (.contiguous() is a no-op for the reference's NCHW stack; it converts once when the convolutions above run
+        # channels_last -- the op itself, like the reference's, takes contiguous maps only)
+        score_map = self.sm_conv(x).squeeze(0).contiguous()
         return self.pool_and_vote(score_map, regions)
 
 

@@ -47,8 +47,57 @@ class Normalizer(nn.Module):
         return (x - self.mean) / self.std
 
 
-def resnet_backbone(backbone_arch: str = "resnet101", first_trainable_stage: int = 3) -> nn.Module:
-    """models/resnet.py:12-39 with `weights=None` (random init: there is no network for checkpoints)."""
+def _frozen_bn_affine(bn: nn.Module) -> Tuple[Tensor, Tensor]:
+    """FrozenBatchNorm2d as y = x * scale + shift (torchvision/ops/misc.py: scale = weight * rsqrt(var + eps),
+    shift = bias - mean * scale); cached on the module, refreshed when one of its buffers changes or moves."""
+    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, bn.weight.device)
+    cached = getattr(bn, "_d2t_affine", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
+            shift = bn.bias - bn.running_mean * scale
+        cached = (key, scale, shift)
+        bn._d2t_affine = cached
+    return cached[1], cached[2]
+
+
+def _conv_frozen_bn(conv: nn.Conv2d, bn: nn.Module, x: Tensor) -> Tensor:
+    """conv followed by a FROZEN batch norm, as one convolution: bn(conv(x, W)) = conv(x, W * scale) + shift.  The two
+    elementwise passes over the activation (and their two backward passes) become one pass over the weight; a frozen
+    conv's scaled weight is cached."""
+    scale, shift = _frozen_bn_affine(bn)
+    if conv.weight.requires_grad:
+        w = conv.weight * scale.view(-1, 1, 1, 1)
+    else:
+        key = (conv.weight._version, conv.weight.device, bn._d2t_affine[0])
+        cached = getattr(conv, "_d2t_scaled", None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                cached = (key, (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(
+                    memory_format=torch.channels_last if conv.weight.is_contiguous(memory_format=torch.channels_last)
+                    else torch.contiguous_format))
+            conv._d2t_scaled = cached
+        w = cached[1]
+    return nn.functional.conv2d(x, w, shift, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def _bottleneck_forward_folded(self, x: Tensor) -> Tensor:
+    """torchvision.models.resnet.Bottleneck.forward with every conv + FrozenBatchNorm2d pair folded (same parameters, same
+    state_dict, same result up to rounding)"""
+    out = relu(_conv_frozen_bn(self.conv1, self.bn1, x))
+    out = relu(_conv_frozen_bn(self.conv2, self.bn2, out))
+    out = _conv_frozen_bn(self.conv3, self.bn3, out)
+    identity = x if self.downsample is None else _conv_frozen_bn(self.downsample[0], self.downsample[1], x)
+    return relu(out + identity)
+
+
+def resnet_backbone(backbone_arch: str = "resnet101", first_trainable_stage: int = 3, fast: bool = False) -> nn.Module:
+    """models/resnet.py:12-39 with `weights=None` (random init: there is no network for checkpoints).
+
+    `fast=True` (extension; same parameters and state_dict keys, same function up to rounding): every conv + frozen-BN pair
+    of the bottleneck blocks runs as one convolution with a scaled weight, and the stack runs in channels_last so that cuDNN
+    picks its NHWC tensor-core kernels without layout conversions around every convolution; the three pyramid maps are
+    converted back to contiguous NCHW for the ops."""
     from torchvision.models import resnet
     from torchvision.models._utils import IntermediateLayerGetter
     from torchvision.ops.misc import FrozenBatchNorm2d
@@ -70,7 +119,18 @@ def resnet_backbone(backbone_arch: str = "resnet101", first_trainable_stage: int
         if not (m and int(m.group(1)) >= first_trainable_stage):
             prm.requires_grad_(False)
     getter = IntermediateLayerGetter(net, {"layer2": "c3", "layer3": "c4", "layer4": "c5"})
-    return nn.Sequential(Normalizer(), getter)
+    if not fast:
+        return nn.Sequential(Normalizer(), getter)
+    import types
+    for mod in net.modules():
+        if isinstance(mod, resnet.Bottleneck):
+            mod.forward = types.MethodType(_bottleneck_forward_folded, mod)
+    getter = getter.to(memory_format=torch.channels_last)
+    # index 1 stays the getter's parameter prefix ("backbone.1.layer3..."): the wrapper modules hold no parameters of their own
+    seq = nn.Sequential(Normalizer(), getter)
+    seq.register_forward_pre_hook(lambda _m, args: (args[0].contiguous(memory_format=torch.channels_last),))
+    seq.register_forward_hook(lambda _m, _a, out: {k: v.contiguous() for k, v in out.items()})
+    return seq
 
 
 class RPN(nn.Module):
@@ -99,11 +159,16 @@ class DetectTrackModule(nn.Module):
     state_dict's keys line up).  `fused_tracker=True` selects the fused operators (track head + glue, PSROIPool + vote; extensions)."""
 
     def __init__(self, backbone_arch: str = "resnet101", first_trainable_stage: int = 3, n_anchors: int = N_ANCHORS,
-                 n_classes: int = 30, k: int = 7, d_max: int = 8, r_hw: int = 7, fused_tracker: bool = False) -> None:
+                 n_classes: int = 30, k: int = 7, d_max: int = 8, r_hw: int = 7, fused_tracker: bool = False,
+                 fast_backbone: bool = False) -> None:
         super().__init__()
-        self.backbone = resnet_backbone(backbone_arch, first_trainable_stage)
+        self.backbone = resnet_backbone(backbone_arch, first_trainable_stage, fast=fast_backbone)
         self.rpn = RPN(1024, n_anchors)
         self.rcnn = RFCN(2048, n_classes, k, fused=fused_tracker)
+        if fast_backbone:
+            # the dilated 3x3 conv of the R-FCN head (rfcn.py:57) has no tensor-core backward-data kernel in cuDNN's NCHW path
+            # (1.2 ms per frame in `dgrad_engine`); with a channels_last weight cuDNN runs the whole head NHWC
+            self.rcnn.channel_reduce = self.rcnn.channel_reduce.to(memory_format=torch.channels_last)
         self.c_tracker = CorrelationTracker(d_max, r_hw, self.rpn.conv.out_channels, fused=fused_tracker)
 
 
@@ -167,15 +232,20 @@ class DetectTrackTrainStep(nn.Module):
     (trainer.py:133-256) with the host-side label encoders / region filters replaced by the synthetic targets, summed over
     the minibatch (trainer.py:258-266).  Wrapping THIS module in DistributedDataParallel gives the data-parallel step."""
 
-    def __init__(self, model: DetectTrackModule, coefs=LOSS_COEFS) -> None:
+    def __init__(self, model: DetectTrackModule, coefs=LOSS_COEFS, batch_backbone: bool = False) -> None:
         super().__init__()
         self.model = model
         self.coefs = coefs
+        # batch_backbone (extension): backbone and RPN run ONCE on all 2 * pairs frames of the minibatch instead of once per
+        # pair (trainer.py:141-143).  Same function -- the batch norms are frozen, so no statistic couples the frames --
+        # with an eighth of the launches and larger convolution grids; heads and tracker stay per frame / per pair.
+        self.batch_backbone = batch_backbone
 
-    def pair_losses(self, item: Dict[str, Tensor]) -> Tuple[Tensor, ...]:
+    def pair_losses(self, item: Dict[str, Tensor], fmaps: Dict[str, Tensor] = None, rpn_out=None) -> Tuple[Tensor, ...]:
         m = self.model
-        fmaps = m.backbone(item["x"])                                   # c3 (2,512,H/8,W/8), c4 (2,1024,H/16,..), c5 (2,2048,..)
-        o_hat, b_hat, fm_reg = m.rpn(fmaps["c4"])
+        if fmaps is None:
+            fmaps = m.backbone(item["x"])                               # c3 (2,512,H/8,W/8), c4 (2,1024,H/16,..), c5 (2,2048,..)
+        o_hat, b_hat, fm_reg = m.rpn(fmaps["c4"]) if rpn_out is None else rpn_out
         o_loss = (item["lw_rpn"] * focal_loss(o_hat, item["c_star_rpn"])).mean()
         b_loss_rpn = bbox_loss(b_hat, item["b_star_rpn"], item["c_star_rpn"]).mean()
         c5_0, c5_1 = fmaps["c5"]
@@ -193,8 +263,16 @@ class DetectTrackTrainStep(nn.Module):
 
     def forward(self, minibatch: List[Dict[str, Tensor]]) -> Tuple[Tensor, Tensor]:
         terms = None
-        for item in minibatch:
-            cur = torch.stack(self.pair_losses(item))
+        fm_all = rpn_all = None
+        if self.batch_backbone and len(minibatch) > 1:
+            fm_all = self.model.backbone(torch.cat([item["x"] for item in minibatch]))
+            rpn_all = self.model.rpn(fm_all["c4"])
+        for n, item in enumerate(minibatch):
+            if fm_all is None:
+                cur = torch.stack(self.pair_losses(item))
+            else:
+                sl = slice(2 * n, 2 * n + 2)
+                cur = torch.stack(self.pair_losses(item, {k: v[sl] for k, v in fm_all.items()}, tuple(t[sl] for t in rpn_all)))
             terms = cur if terms is None else terms + cur
         coefs = torch.as_tensor(self.coefs, dtype=terms.dtype, device=terms.device)
         return (terms * coefs).sum(), terms.detach()

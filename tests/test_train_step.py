@@ -56,6 +56,37 @@ def test_module_layout_follows_the_reference():
     assert any("layer2" in n for n in frozen) and not any("layer3" in n or "layer4" in n for n in frozen)
 
 
+def test_fast_backbone_is_the_same_function():
+    """resnet_backbone(fast=True) -- conv + frozen BN folded into one convolution, channels_last stack -- has the same
+    state_dict keys and computes the same pyramid and the same gradients (float64: to rounding of 1e-12)."""
+    torch.manual_seed(0)
+    a = ts.resnet_backbone("resnet50", 3, fast=False).double()
+    b = ts.resnet_backbone("resnet50", 3, fast=True).double()
+    assert list(a.state_dict()) == list(b.state_dict())
+    b.load_state_dict(a.state_dict())
+    x = torch.rand(2, 3, 64, 96, dtype=torch.float64)
+    fa, fb = a(x), b(x)
+    for k in ("c3", "c4", "c5"):
+        assert fb[k].is_contiguous()
+        torch.testing.assert_close(fb[k], fa[k], rtol=1e-12, atol=1e-12)
+    sum((v ** 2).sum() for v in fa.values()).backward()
+    sum((v ** 2).sum() for v in fb.values()).backward()
+    gb = dict(b.named_parameters())
+    n_grads = 0
+    for n, p in a.named_parameters():
+        assert (p.grad is None) == (gb[n].grad is None), n
+        if p.grad is not None:
+            n_grads += 1
+            assert float((p.grad - gb[n].grad).norm()) <= 1e-12 * float(p.grad.norm()) + 1e-300, n
+    assert n_grads > 0
+    # a changed frozen-BN buffer or frozen weight invalidates the cached scaled weights
+    with torch.no_grad():
+        for m in (a, b):
+            m[1].layer1[0].bn1.weight.mul_(0.5)
+            m[1].layer1[0].conv1.weight.mul_(1.5)
+    torch.testing.assert_close(b(x)["c5"], a(x)["c5"], rtol=1e-12, atol=1e-12)
+
+
 def test_synthetic_batch_shapes():
     b = ts.synthetic_batch(2, 64, 96, 11, 30, seed=5)
     assert len(b) == 2 and tuple(b[0]["x"].shape) == (2, 3, 64, 96)
@@ -144,3 +175,26 @@ def test_one_training_step_on_the_gpu_reference_composition_vs_fused(cuda):
     for n, gr in losses[False][2].items():
         ref_scale = float(gr.abs().max()) or 1.0
         torch.testing.assert_close(losses[True][2][n], gr, rtol=1e-3, atol=1e-4 * ref_scale, msg=n)
+
+
+@pytest.mark.gpu
+def test_fast_backbone_and_batched_step_match_the_reference_composition_on_the_gpu(cuda):
+    """fast_backbone (folded frozen BN, channels_last stack and R-FCN conv) + batch_backbone (backbone / RPN once per minibatch)
+    against the per-pair NCHW composition: same losses, same gradients (FP32 convolutions, different cuDNN kernels)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res = {}
+    for fast in (False, True):
+        torch.manual_seed(11)
+        model = ts.DetectTrackModule("resnet50", 3, fused_tracker=False, fast_backbone=fast).to(cuda)
+        stepm = ts.DetectTrackTrainStep(model, batch_backbone=fast)
+        batch = ts.synthetic_batch(3, 160, 192, 24, 30, seed=21, device=cuda)
+        loss, terms = stepm(batch)
+        loss.backward()
+        res[fast] = (terms, {n: p.grad.detach().clone() for n, p in stepm.named_parameters() if p.grad is not None})
+    assert list(res[True][1]) == list(res[False][1])
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=1e-4, atol=1e-6)
+    # every convolution runs a different cuDNN kernel (NHWC, other batch size), so single elements differ by more than an
+    # elementwise FP32 tolerance wherever a ReLU input sits at zero; per parameter the gradients agree in norm
+    worst = max((float((res[True][1][n] - gr).norm() / (gr.norm() + 1e-30)), n) for n, gr in res[False][1].items())
+    assert worst[0] <= 2e-3, worst

@@ -15,17 +15,12 @@ pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 R = 300
 
 
-def build(channels_last=False):
+def build(fast=False, fused=False, batched=False):
     torch.manual_seed(1239)
-    model = ts.DetectTrackModule("resnet101", 3, fused_tracker=False).to(dev)
-    if channels_last:
-        model.backbone = model.backbone.to(memory_format=torch.channels_last)
-    stepm = ts.DetectTrackTrainStep(model)
+    model = ts.DetectTrackModule("resnet101", 3, fused_tracker=fused, fast_backbone=fast).to(dev)
+    stepm = ts.DetectTrackTrainStep(model, batch_backbone=batched)
     opt = ts.make_optimizer(stepm)
     batch = ts.synthetic_batch(pairs, 608, 1008, R, 30, seed=1239, device=dev)
-    if channels_last:
-        for it in batch:
-            it["x"] = it["x"].contiguous(memory_format=torch.channels_last)
     return stepm, opt, batch
 
 
@@ -45,25 +40,22 @@ def timeit(stepm, opt, batch, n=3):
     for _ in range(n):
         loss = step(stepm, opt, batch)
     torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / n * 1e3, float(loss)
+    return (time.perf_counter() - t0) / n * 1e3, float(loss.detach())
 
 
 print("allow_tf32 conv:", torch.backends.cudnn.allow_tf32, " matmul:", torch.backends.cuda.matmul.allow_tf32, " benchmark:", torch.backends.cudnn.benchmark)
-stepm, opt, batch = build()
-ms, loss = timeit(stepm, opt, batch)
-print(f"baseline                      {ms:8.1f} ms / step of {pairs} pairs   loss {loss:.4f}")
-with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, torch.profiler.ProfilerActivity.CPU]) as prof:
-    step(stepm, opt, batch)
-    torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
-torch.backends.cudnn.benchmark = True
-ms, loss = timeit(stepm, opt, batch)
-print(f"cudnn.benchmark               {ms:8.1f} ms   loss {loss:.4f}")
-del stepm, opt, batch
-torch.cuda.empty_cache()
-stepm, opt, batch = build(channels_last=True)
-ms, loss = timeit(stepm, opt, batch)
-print(f"benchmark + channels_last     {ms:8.1f} ms   loss {loss:.4f}")
-torch.backends.cudnn.allow_tf32 = False
-ms, loss = timeit(stepm, opt, batch)
-print(f"  ... with conv TF32 disabled {ms:8.1f} ms   loss {loss:.4f}")
+for fast, fused, batched in ((False, False, False), (True, False, False), (True, False, True), (True, True, True)):
+    stepm, opt, batch = build(fast, fused, batched)
+    ms, loss = timeit(stepm, opt, batch)
+    print(f"fast_backbone={fast!s:5s} fused_tracker={fused!s:5s} batch_backbone={batched!s:5s} {ms:8.1f} ms / step of {pairs} pairs   loss {loss:.4f}")
+    if fast and not fused and batched:
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, torch.profiler.ProfilerActivity.CPU]) as prof:
+            step(stepm, opt, batch)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=24, max_name_column_width=70))
+        torch.backends.cudnn.benchmark = True
+        ms, loss = timeit(stepm, opt, batch)
+        print(f"  ... with cudnn.benchmark      {ms:8.1f} ms   loss {loss:.4f}")
+        torch.backends.cudnn.benchmark = False
+    del stepm, opt, batch
+    torch.cuda.empty_cache()
