@@ -73,6 +73,10 @@ SIGNATURES = {
     "d2t_trackhead_bwd_workspace_bytes": (_c_size_t, _WS6),
     "d2t_trackhead_fwd_f32": (_c_int, [_P] * 5 + [_c_int] * 6 + [_P, _c_size_t, _P]),
     "d2t_trackhead_bwd_f32": (_c_int, [_P] * 7 + [_c_int] * 6 + [_P, _c_size_t, _P]),
+    "d2t_trackhead_fwd_batched_workspace_bytes": (_c_size_t, _WS7),
+    "d2t_trackhead_bwd_batched_workspace_bytes": (_c_size_t, _WS7),
+    "d2t_trackhead_fwd_batched_f32": (_c_int, [_P] * 5 + [_c_int] * 7 + [_P, _c_size_t, _P]),
+    "d2t_trackhead_bwd_batched_f32": (_c_int, [_P] * 7 + [_c_int] * 7 + [_P, _c_size_t, _P]),
     "d2t_gemm_tf32x3_f32": (_c_int, [_P, _P, _P] + [_c_int] * 9 + [_P]),
     "d2t_roi_nms_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "d2t_roi_decode_filter_f32": (_c_int, [_P] * 5 + [_c_int, ctypes.c_float, _P]),

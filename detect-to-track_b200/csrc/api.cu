@@ -123,12 +123,12 @@ size_t roi_pipeline_ws_bytes(int A, int pre_nms);
 int roi_decode_launch(const float*, const float*, const float*, float*, float*, int, float, cudaStream_t);
 int roi_nms_launch(const float*, const long long*, const float*, float*, int*, int, int, int, float, void*, size_t, cudaStream_t);
 // fused track head (track_head.cu)
-size_t trackhead_fwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
-size_t trackhead_bwd_ws_bytes(int R, int C, int H, int W, int k, int nO);
-int trackhead_fwd_launch(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*,
+size_t trackhead_fwd_ws_bytes(int NB, int R, int C, int H, int W, int k, int nO);
+size_t trackhead_bwd_ws_bytes(int NB, int R, int C, int H, int W, int k, int nO);
+int trackhead_fwd_launch(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, void*,
                          size_t, cudaStream_t);
 int trackhead_bwd_launch(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int,
-                         int, void*, size_t, cudaStream_t);
+                         int, int, void*, size_t, cudaStream_t);
 
 static int check_corr(const void* a, const void* b, const void* c, int B, int C, int H, int W, int d, int stride,
                       const char* who) {
@@ -414,19 +414,39 @@ int d2t_psroipool_vote_bwd_f32(const float* grad_out, const float* rois, float* 
 
 // ---- fused track head: ROIPool -> Linear ---------------------------------------------
 size_t d2t_trackhead_fwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int n_out) {
-    return trackhead_fwd_ws_bytes(R, C, H, W, r_hw, n_out);
+    return trackhead_fwd_ws_bytes(1, R, C, H, W, r_hw, n_out);
 }
 size_t d2t_trackhead_bwd_workspace_bytes(int R, int C, int H, int W, int r_hw, int n_out) {
-    return trackhead_bwd_ws_bytes(R, C, H, W, r_hw, n_out);
+    return trackhead_bwd_ws_bytes(1, R, C, H, W, r_hw, n_out);
 }
 int d2t_trackhead_fwd_f32(const float* fm, const float* rois, const float* weight, const float* bias, float* out, int R, int C,
                           int H, int W, int r_hw, int n_out, void* ws, size_t ws_bytes, void* stream) {
-    return trackhead_fwd_launch(fm, rois, weight, bias, out, R, C, H, W, r_hw, n_out, ws, ws_bytes, (cudaStream_t)stream);
+    return trackhead_fwd_launch(fm, rois, weight, bias, out, 1, R, C, H, W, r_hw, n_out, ws, ws_bytes, (cudaStream_t)stream);
 }
 int d2t_trackhead_bwd_f32(const float* grad_out, const float* fm, const float* rois, const float* weight, float* grad_fm,
                           float* grad_weight, float* grad_bias, int R, int C, int H, int W, int r_hw, int n_out, void* ws,
                           size_t ws_bytes, void* stream) {
-    return trackhead_bwd_launch(grad_out, fm, rois, weight, grad_fm, grad_weight, grad_bias, R, C, H, W, r_hw, n_out, ws, ws_bytes,
+    return trackhead_bwd_launch(grad_out, fm, rois, weight, grad_fm, grad_weight, grad_bias, 1, R, C, H, W, r_hw, n_out, ws, ws_bytes,
+                                (cudaStream_t)stream);
+}
+// the same operator over N images that share weight and bias (the track features of N frame pairs)
+size_t d2t_trackhead_fwd_batched_workspace_bytes(int N, int R, int C, int H, int W, int r_hw, int n_out) {
+    return trackhead_fwd_ws_bytes(N, R, C, H, W, r_hw, n_out);
+}
+size_t d2t_trackhead_bwd_batched_workspace_bytes(int N, int R, int C, int H, int W, int r_hw, int n_out) {
+    return trackhead_bwd_ws_bytes(N, R, C, H, W, r_hw, n_out);
+}
+int d2t_trackhead_fwd_batched_f32(const float* fm, const float* rois, const float* weight, const float* bias, float* out, int N,
+                                  int R, int C, int H, int W, int r_hw, int n_out, void* ws, size_t ws_bytes, void* stream) {
+    D2T_REQUIRE(N >= 0, "d2t_trackhead_fwd_batched_f32: bad batch size %d", N);
+    if (N == 0) return D2T_OK;
+    return trackhead_fwd_launch(fm, rois, weight, bias, out, N, R, C, H, W, r_hw, n_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d2t_trackhead_bwd_batched_f32(const float* grad_out, const float* fm, const float* rois, const float* weight, float* grad_fm,
+                                  float* grad_weight, float* grad_bias, int N, int R, int C, int H, int W, int r_hw, int n_out,
+                                  void* ws, size_t ws_bytes, void* stream) {
+    D2T_REQUIRE(N > 0, "d2t_trackhead_bwd_batched_f32: bad batch size %d", N);
+    return trackhead_bwd_launch(grad_out, fm, rois, weight, grad_fm, grad_weight, grad_bias, N, R, C, H, W, r_hw, n_out, ws, ws_bytes,
                                 (cudaStream_t)stream);
 }
 

@@ -247,6 +247,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 }
             } else {
                 float* dst = out + (size_t)split * a.slab_rows * a.ldo + (size_t)nb * a.ldo + m;
+                if (a.col_rows > 0) {   // batch of images stacked along M: image b = m / col_rows owns its own output block
+                    const int b = m / a.col_rows;
+                    dst = out + (size_t)b * a.col_stride + (size_t)nb * a.ldo + (m - b * a.col_rows);
+                }
 #pragma unroll
                 for (int x = 0; x < 16; ++x)
                     if (nb + x < a.N) dst[(size_t)x * a.ldo] = __uint_as_float(r[x]);
@@ -321,7 +325,7 @@ static int launch(const GemmOperand& A, const GemmOperand& B, float* out, const 
 }  // namespace
 
 int gemm_tf32x3(const GemmOperand& A, const GemmOperand& B, float* out, int M, int N, int K, int ldo, int epilogue, int splits,
-                int slab_rows, int bn, cudaStream_t st) {
+                int slab_rows, int bn, cudaStream_t st, int col_rows, long long col_stride) {
     D2T_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "gemm_tf32x3: bad shape M=%d N=%d K=%d splits=%d", M, N, K, splits);
     D2T_REQUIRE(A.rows >= M && B.rows >= N, "gemm_tf32x3: operand has fewer rows than the problem");
     D2T_REQUIRE(epilogue == GEMM_EPI_COL || (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0),
@@ -329,6 +333,8 @@ int gemm_tf32x3(const GemmOperand& A, const GemmOperand& B, float* out, int M, i
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.ldo = ldo; a.epilogue = epilogue; a.splits = splits; a.slab_rows = slab_rows;
     a.kblocks = ceil_div(K, GBK);
+    a.col_rows = col_rows; a.col_stride = col_stride;
+    D2T_REQUIRE(col_rows == 0 || (epilogue == GEMM_EPI_COL && splits == 1), "gemm_tf32x3: batched output needs the COL epilogue, no split-K");
     switch (bn) {
         case 208: return launch<208>(A, B, out, a, st);
         case 256: return launch<256>(A, B, out, a, st);

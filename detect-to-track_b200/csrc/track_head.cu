@@ -28,22 +28,24 @@ namespace {
 constexpr int kThMaxN = 256;   // n_out * r_hw^2 must fit one UMMA N tile
 
 struct ThDims {
+    int NB;                 // images per call (the track features of NB frame pairs share one weight)
     int R, C, H, W, k, nO;
-    int P, KK, N1;          // pixels, bins, n_out * bins
+    int P, KK, N1;          // pixels per image, bins, n_out * bins
     int ldc, ldp, ldn;      // pitches (floats, multiples of 4) of K = C, K = P and K = N1 operands / N1-wide outputs
     int bn;                 // N tile for the N = N1 GEMMs
     int s1, s3;             // split-K factors of forward GEMM / weight-gradient GEMM
 };
 
-static int th_dims(int R, int C, int H, int W, int k, int nO, ThDims* d) {
-    D2T_REQUIRE(R >= 0 && C > 0 && H > 0 && W > 0 && k > 0 && nO > 0, "trackhead: bad shape R=%d C=%d H=%d W=%d r_hw=%d n_out=%d", R,
-                C, H, W, k, nO);
+static int th_dims(int NB, int R, int C, int H, int W, int k, int nO, ThDims* d) {
+    D2T_REQUIRE(NB > 0 && R >= 0 && C > 0 && H > 0 && W > 0 && k > 0 && nO > 0,
+                "trackhead: bad shape N=%d R=%d C=%d H=%d W=%d r_hw=%d n_out=%d", NB, R, C, H, W, k, nO);
     D2T_REQUIRE(nO * k * k <= kThMaxN, "trackhead: n_out * r_hw^2 must be <= %d", kThMaxN);
-    D2T_REQUIRE(H < 32768 && W < 32768 && (long long)C * H * W < (1ll << 31), "trackhead: map too large");
+    D2T_REQUIRE(H < 32768 && W < 32768 && (long long)NB * C * H * W < (1ll << 31) && (long long)NB * R < (1ll << 24),
+                "trackhead: map too large");
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
-    d->R = R; d->C = C; d->H = H; d->W = W; d->k = k; d->nO = nO;
+    d->NB = NB; d->R = R; d->C = C; d->H = H; d->W = W; d->k = k; d->nO = nO;
     d->P = H * W; d->KK = k * k; d->N1 = nO * k * k;
     d->ldc = (int)align_up(C, 4); d->ldp = (int)align_up(d->P, 4); d->ldn = (int)align_up(d->N1, 4);
     d->bn = d->N1 <= 64 ? 64 : d->N1 <= 208 ? 208 : 256;
@@ -53,8 +55,8 @@ static int th_dims(int R, int C, int H, int W, int k, int nO, ThDims* d) {
         if (s > kb) s = kb;
         return s < 1 ? 1 : s;
     };
-    d->s1 = splits(ceil_div(d->P, 128), C);
-    d->s3 = splits(ceil_div(C, 128), d->P);
+    d->s1 = splits(ceil_div(NB * d->P, 128), C);
+    d->s3 = splits(ceil_div(C, 128), NB * d->ldp);
     return D2T_OK;
 }
 
@@ -71,10 +73,10 @@ static ThFwdWs th_fwd_ws(const ThDims& d, void* base) {
         off = align_up(off + floats * sizeof(float), 256);
         return p;
     };
-    w.xt = take((size_t)d.P * d.ldc);
+    w.xt = take((size_t)d.NB * d.P * d.ldc);
     w.wt = take((size_t)d.N1 * d.ldc);
-    w.zpart = take((size_t)d.s1 * d.P * d.ldn);
-    w.z = take((size_t)d.P * d.ldn);
+    w.zpart = take((size_t)d.s1 * d.NB * d.P * d.ldn);
+    w.z = take((size_t)d.NB * d.P * d.ldn);
     w.total = off;
     return w;
 }
@@ -90,9 +92,9 @@ static ThBwdWs th_bwd_ws(const ThDims& d, void* base) {
         off = align_up(off + floats * sizeof(float), 256);
         return p;
     };
-    w.gz = take((size_t)d.P * d.ldn);
-    w.gzt = take((size_t)d.N1 * d.ldp);
-    w.xc = take((size_t)d.C * d.ldp);   // used unless the map itself is TMA-legal (H*W a multiple of 4, 16-byte-aligned base)
+    w.gz = take((size_t)d.NB * d.P * d.ldn);
+    w.gzt = take((size_t)d.N1 * d.NB * d.ldp);   // [n][image b][ldp]: K of the weight-gradient GEMM runs over all images
+    w.xc = take((size_t)d.C * d.NB * d.ldp);     // used unless NB == 1 and the map itself is TMA-legal (H*W % 4 == 0, aligned base)
     w.wc = take((size_t)d.C * d.ldn);
     w.gwpart = take((size_t)d.s3 * d.C * d.ldn);
     w.total = off;
@@ -104,6 +106,8 @@ static ThBwdWs th_bwd_ws(const ThDims& d, void* base) {
 __global__ void __launch_bounds__(256)
 th_transpose_kernel(const float* __restrict__ x, float* __restrict__ xt, int C, int P, int ldc) {
     __shared__ float tile[32][33];
+    x += (size_t)blockIdx.z * C * P;          // image blockIdx.z: rows b*P .. b*P + P-1 of the tall XT
+    xt += (size_t)blockIdx.z * P * ldc;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
@@ -119,12 +123,14 @@ th_transpose_kernel(const float* __restrict__ x, float* __restrict__ xt, int C, 
     }
 }
 
-// X (C, P) -> Xc (C, ldp): same order, 16-byte-aligned pitch (only when P is not a multiple of 4)
+// X (NB, C, P) -> Xc (C, NB * ldp): channel-major over all images, every image block ldp floats wide (16-byte-aligned pitch),
+// pad columns zero (they are inside the K range of the weight-gradient GEMM when NB > 1)
 __global__ void __launch_bounds__(256)
-th_pad_copy_kernel(const float* __restrict__ x, float* __restrict__ xc, int C, int P, int ldp) {
-    const int c = blockIdx.y;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x)
-        xc[(size_t)c * ldp + p] = __ldg(x + (size_t)c * P + p);
+th_pad_copy_kernel(const float* __restrict__ x, float* __restrict__ xc, int C, int P, int ldp, int NB) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float* src = x + ((size_t)b * C + c) * P;
+    float* dst = xc + (size_t)c * NB * ldp + (size_t)b * ldp;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < ldp; p += gridDim.x * blockDim.x) dst[p] = p < P ? __ldg(src + p) : 0.f;
 }
 
 // The n_out * kk "position-sensitive channels" are numbered n = ij * nO + o (outputs of one bin adjacent), so that the
@@ -178,6 +184,9 @@ th_pool_kernel(const float* __restrict__ z, const float* __restrict__ rois, cons
     extern __shared__ float th_part[];   // [KK][NO]
     const int KK = k * k;
     const int r = blockIdx.x;
+    z += (size_t)blockIdx.y * H * W * ldn;        // image blockIdx.y
+    rois += (size_t)blockIdx.y * R * 4;
+    out += (size_t)blockIdx.y * R * NO;
     const float* roi = rois + (size_t)r * 4;
     const float r0 = __ldg(roi), r1 = __ldg(roi + 1), r2 = __ldg(roi + 2), r3 = __ldg(roi + 3);
     for (int base = 0; base < KK * 4; base += kPoolThreads2) {   // uniform trip count: every lane reaches the shuffles
@@ -232,7 +241,7 @@ constexpr int kGzThreads = 256;
 constexpr int kGzMaxO = 8;
 __global__ void __launch_bounds__(kGzThreads)
 th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float* __restrict__ gz, float* __restrict__ gzt, int R,
-             int H, int W, int k, int nO, int ldn, int ldp) {
+             int H, int W, int k, int nO, int ldn, int ldp, int ldpT) {
     extern __shared__ unsigned char th_smem[];
     // list[R] (int) | rowext[R] (int: I1 - I0 or 0) | cj[R*k] (short2 J0, J1) | val[R*k*nO] (float)
     int* list = reinterpret_cast<int*>(th_smem);
@@ -242,6 +251,15 @@ th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float*
     __shared__ int nlist;
     const int y = blockIdx.x / k, i = blockIdx.x - y * k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    g += (size_t)blockIdx.y * R * nO;              // image blockIdx.y
+    rois += (size_t)blockIdx.y * R * 4;
+    gz += (size_t)blockIdx.y * H * W * ldn;
+    gzt += (size_t)blockIdx.y * ldp;               // this image's column block of the (N1, ldpT) transposed layout
+    if (y == H - 1)                                // pad columns of the block: inside the K range of the weight-gradient GEMM
+        for (int e = tid; e < k * nO * (ldp - H * W); e += kGzThreads) {
+            const int n = i * k * nO + e / (ldp - H * W), p = H * W + e % (ldp - H * W);
+            gzt[(size_t)n * ldpT + p] = 0.f;
+        }
     for (int r = tid; r < R; r += kGzThreads) {
         const float* roi = rois + (size_t)r * 4;
         int i0, i1;
@@ -295,7 +313,7 @@ th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float*
         for (int o = 0; o < kGzMaxO; ++o) {
             if (o < nO) {
                 if (nO != 4) gz[(size_t)p * ldn + nb + o] = acc[o];
-                gzt[(size_t)(nb + o) * ldp + p] = acc[o];
+                gzt[(size_t)(nb + o) * ldpT + p] = acc[o];
             }
         }
     }
@@ -338,21 +356,23 @@ static int grid_for(size_t n, int block, int cap) {
 
 }  // namespace
 
-size_t trackhead_fwd_ws_bytes(int R, int C, int H, int W, int k, int nO) {
+size_t trackhead_fwd_ws_bytes(int NB, int R, int C, int H, int W, int k, int nO) {
     ThDims d;
-    if (th_dims(R, C, H, W, k, nO, &d)) return 0;
+    if (th_dims(NB, R, C, H, W, k, nO, &d)) return 0;
     return th_fwd_ws(d, nullptr).total;
 }
-size_t trackhead_bwd_ws_bytes(int R, int C, int H, int W, int k, int nO) {
+size_t trackhead_bwd_ws_bytes(int NB, int R, int C, int H, int W, int k, int nO) {
     ThDims d;
-    if (th_dims(R, C, H, W, k, nO, &d)) return 0;
+    if (th_dims(NB, R, C, H, W, k, nO, &d)) return 0;
     return th_bwd_ws(d, nullptr).total;
 }
 
-int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight, const float* bias, float* out, int R, int C,
+// fm (NB, C, H, W), rois (NB, R, 4), out (NB, R, nO): the NB images share weight and bias; one set of launches, the
+// forward GEMM runs over all NB * H * W positions at once
+int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight, const float* bias, float* out, int NB, int R, int C,
                          int H, int W, int k, int nO, void* wsp, size_t ws_bytes, cudaStream_t st) {
     ThDims d;
-    int rc = th_dims(R, C, H, W, k, nO, &d);
+    int rc = th_dims(NB, R, C, H, W, k, nO, &d);
     if (rc) return rc;
     if (R == 0) return D2T_OK;
     D2T_REQUIRE(nO <= 8, "trackhead_fwd: n_out must be <= 8");
@@ -367,14 +387,15 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
     const int cap = di.sm_count * 8;
     th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wt, C, d.KK, nO, d.ldc, 0);
     D2T_CUDA_TRY(cudaGetLastError());
-    th_transpose_kernel<<<dim3(ceil_div(d.P, 32), ceil_div(C, 32)), 256, 0, st>>>(fm, w.xt, C, d.P, d.ldc);
+    th_transpose_kernel<<<dim3(ceil_div(d.P, 32), ceil_div(C, 32), NB), 256, 0, st>>>(fm, w.xt, C, d.P, d.ldc);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch(2);
-    GemmOperand A{w.xt, d.P, d.ldc}, B{w.wt, d.N1, d.ldc};
-    if ((rc = gemm_tf32x3(A, B, w.zpart, d.P, d.N1, C, d.ldn, GEMM_EPI_ROW, d.s1, d.P, d.bn, st))) return rc;
+    const int PT = NB * d.P;
+    GemmOperand A{w.xt, PT, d.ldc}, B{w.wt, d.N1, d.ldc};
+    if ((rc = gemm_tf32x3(A, B, w.zpart, PT, d.N1, C, d.ldn, GEMM_EPI_ROW, d.s1, PT, d.bn, st))) return rc;
     const float* z = w.zpart;
     if (d.s1 > 1) {
-        const int n4 = d.P * d.ldn / 4;
+        const int n4 = PT * d.ldn / 4;
         th_reduce_slabs_kernel<<<grid_for(n4, 256, cap), 256, 0, st>>>(reinterpret_cast<const float4*>(w.zpart),
                                                                        reinterpret_cast<float4*>(w.z), n4, d.s1);
         D2T_CUDA_TRY(cudaGetLastError());
@@ -384,14 +405,14 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
     {
         const size_t psm = (size_t)d.KK * nO * sizeof(float);
         switch (nO) {
-            case 1: th_pool_kernel<1><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
-            case 2: th_pool_kernel<2><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
-            case 3: th_pool_kernel<3><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
-            case 4: th_pool_kernel<4><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
-            case 5: th_pool_kernel<5><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
-            case 6: th_pool_kernel<6><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
-            case 7: th_pool_kernel<7><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
-            case 8: th_pool_kernel<8><<<R, kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 1: th_pool_kernel<1><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 2: th_pool_kernel<2><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 3: th_pool_kernel<3><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 4: th_pool_kernel<4><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 5: th_pool_kernel<5><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 6: th_pool_kernel<6><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 7: th_pool_kernel<7><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
+            case 8: th_pool_kernel<8><<<dim3(R, NB), kPoolThreads2, psm, st>>>(z, rois, bias, out, R, H, W, k, d.ldn); break;
             default: set_error("trackhead_fwd: n_out must be <= 8"); return D2T_ERR_BAD_ARG;
         }
     }
@@ -400,17 +421,18 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
     return D2T_OK;
 }
 
+// go (NB, R, nO), gfm (NB, C, H, W); gw / gb are the sums over the NB images (one GEMM with K over all images / one pass)
 int trackhead_bwd_launch(const float* go, const float* fm, const float* rois, const float* weight, float* gfm, float* gw, float* gb,
-                         int R, int C, int H, int W, int k, int nO, void* wsp, size_t ws_bytes, cudaStream_t st) {
+                         int NB, int R, int C, int H, int W, int k, int nO, void* wsp, size_t ws_bytes, cudaStream_t st) {
     ThDims d;
-    int rc = th_dims(R, C, H, W, k, nO, &d);
+    int rc = th_dims(NB, R, C, H, W, k, nO, &d);
     if (rc) return rc;
     D2T_REQUIRE(nO <= kGzMaxO, "trackhead_bwd: n_out must be <= %d", kGzMaxO);
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     const int cap = di.sm_count * 8;
     if (R == 0) {   // no RoIs: every gradient is zero
-        if (gfm) D2T_CUDA_TRY(cudaMemsetAsync(gfm, 0, (size_t)C * d.P * sizeof(float), st));
+        if (gfm) D2T_CUDA_TRY(cudaMemsetAsync(gfm, 0, (size_t)NB * C * d.P * sizeof(float), st));
         if (gw) D2T_CUDA_TRY(cudaMemsetAsync(gw, 0, (size_t)nO * C * d.KK * sizeof(float), st));
         if (gb) D2T_CUDA_TRY(cudaMemsetAsync(gb, 0, (size_t)nO * sizeof(float), st));
         return D2T_OK;
@@ -424,30 +446,34 @@ int trackhead_bwd_launch(const float* go, const float* fm, const float* rois, co
     const size_t gzSmem = (size_t)R * 8 + (size_t)R * k * 4 + (size_t)R * k * nO * 4;
     D2T_REQUIRE(gzSmem <= (size_t)di.max_smem_optin - 1024, "trackhead_bwd: too many RoIs for one call (%d)", R);
     D2T_SMEM_OPTIN(th_gz_kernel, gzSmem);
-    th_gz_kernel<<<H * k, kGzThreads, gzSmem, st>>>(go, rois, w.gz, w.gzt, R, H, W, k, nO, d.ldn, d.ldp);
+    const int ldpT = NB * d.ldp;
+    th_gz_kernel<<<dim3(H * k, NB), kGzThreads, gzSmem, st>>>(go, rois, w.gz, w.gzt, R, H, W, k, nO, d.ldn, d.ldp, ldpT);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     if (gfm) {
         th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wc, C, d.KK, nO, d.ldn, 1);
         D2T_CUDA_TRY(cudaGetLastError());
         note_launch();
-        GemmOperand A{w.gz, d.P, d.ldn}, B{w.wc, C, d.ldn};
+        GemmOperand A{w.gz, NB * d.P, d.ldn}, B{w.wc, C, d.ldn};
         // N tile 208 (10 x 19 = 190 CTAs, three raw stages) beats 256 (8 x 19 = 152 CTAs: also two waves, two stages)
-        if ((rc = gemm_tf32x3(A, B, gfm, d.P, C, d.N1, d.P, GEMM_EPI_COL, 1, 0, 208, st))) return rc;
+        if ((rc = gemm_tf32x3(A, B, gfm, NB * d.P, C, d.N1, d.P, GEMM_EPI_COL, 1, 0, 208, st, NB > 1 ? d.P : 0, (long long)C * d.P)))
+            return rc;
     }
     if (gw) {
         const float* xc = fm;
-        if (d.P != d.ldp || (reinterpret_cast<uintptr_t>(fm) & 15) != 0) {
-            th_pad_copy_kernel<<<dim3(ceil_div(d.P, 1024), C), 256, 0, st>>>(fm, w.xc, C, d.P, d.ldp);
+        if (NB > 1 || d.P != d.ldp || (reinterpret_cast<uintptr_t>(fm) & 15) != 0) {
+            th_pad_copy_kernel<<<dim3(ceil_div(d.ldp, 1024), C, NB), 256, 0, st>>>(fm, w.xc, C, d.P, d.ldp, NB);
             D2T_CUDA_TRY(cudaGetLastError());
             note_launch();
             xc = w.xc;
         }
-        GemmOperand A{xc, C, d.ldp}, B{w.gzt, d.N1, d.ldp};
-        if ((rc = gemm_tf32x3(A, B, w.gwpart, C, d.N1, d.P, d.ldn, GEMM_EPI_ROW, d.s3, C, d.bn, st))) return rc;
+        // K runs over the pixels of all images (pad columns are zero in both operands; for one image K = P and TMA zero-fills)
+        const int Kw = NB > 1 ? ldpT : d.P;
+        GemmOperand A{xc, C, ldpT}, B{w.gzt, d.N1, ldpT};
+        if ((rc = gemm_tf32x3(A, B, w.gwpart, C, d.N1, Kw, d.ldn, GEMM_EPI_ROW, d.s3, C, d.bn, st))) return rc;
     }
     if (gw || gb) {
-        th_reduce_w_kernel<<<grid_for((size_t)C * d.N1, 256, cap), 256, 0, st>>>(w.gwpart, go, gw, gb, R, C, d.KK, nO, d.ldn, d.s3);
+        th_reduce_w_kernel<<<grid_for((size_t)C * d.N1, 256, cap), 256, 0, st>>>(w.gwpart, go, gw, gb, NB * R, C, d.KK, nO, d.ldn, d.s3);
         D2T_CUDA_TRY(cudaGetLastError());
         note_launch();
     }

@@ -233,6 +233,18 @@ D2T_API int d2t_trackhead_bwd_f32(const float* grad_out, const float* fm, const 
                           float* grad_fm, float* grad_weight, float* grad_bias, int R, int C, int H, int W, int r_hw,
                           int n_out, void* ws, size_t ws_bytes, void* stream);
 
+/* The same operator over N images that share weight and bias -- the track features of N frame pairs (extension: the
+ * reference runs its tracker one pair per call, correlation_tracker.py:56-87).  fm : (N, C, H, W);  rois : (N, R, 4);
+ * out / grad_out : (N, R, n_out);  grad_fm : (N, C, H, W);  grad_weight / grad_bias : sums over the N images.  One set of
+ * launches: the forward and grad_fm GEMMs run over all N*H*W positions, the grad_weight GEMM contracts over them. */
+D2T_API size_t d2t_trackhead_fwd_batched_workspace_bytes(int N, int R, int C, int H, int W, int r_hw, int n_out);
+D2T_API int d2t_trackhead_fwd_batched_f32(const float* fm, const float* rois, const float* weight, const float* bias, float* out,
+                          int N, int R, int C, int H, int W, int r_hw, int n_out, void* ws, size_t ws_bytes, void* stream);
+D2T_API size_t d2t_trackhead_bwd_batched_workspace_bytes(int N, int R, int C, int H, int W, int r_hw, int n_out);
+D2T_API int d2t_trackhead_bwd_batched_f32(const float* grad_out, const float* fm, const float* rois, const float* weight,
+                          float* grad_fm, float* grad_weight, float* grad_bias, int N, int R, int C, int H, int W, int r_hw,
+                          int n_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- 3xTF32 GEMM building block (float32) ------------------------------------------
  * out = A (M x K, row pitch lda) * B^T (N x K, row pitch ldb), both K-major with 16-byte-aligned bases and pitches, on
  * tcgen05 fed by TMA (csrc/gemm_tf32x3.cu; measured |err| <= 2.5e-6 * sum |a||b| at K = 1891, 9e-7 at K = 256).  The contraction kernel of the fused track head,

@@ -14,7 +14,7 @@ import detect_to_track_b200 as d2t
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.lib()
     declared = _lib.header_symbols()
-    assert len(declared) == 47
+    assert len(declared) == 51
     assert sorted(_lib.SIGNATURES) == declared
     for name in declared:
         assert hasattr(lib, name), name

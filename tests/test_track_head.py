@@ -58,6 +58,39 @@ def test_track_head_matches_the_composition(cuda, C, H, W, R, k, n_out):
     assert all(torch.equal(a, b) for a, b in zip(got, again))          # bitwise reproducible
 
 
+@pytest.mark.parametrize("N,C,H,W,R,k,n_out", [(3, 37, 20, 21, 40, 7, 4), (2, 130, 38, 63, 77, 7, 4), (4, 8, 9, 10, 5, 3, 2),
+                                               (2, 300, 12, 70, 33, 5, 8), (8, 257, 38, 63, 50, 7, 4)])
+def test_track_head_batched_matches_per_image_composition(cuda, N, C, H, W, R, k, n_out):
+    """the batched form (N images, shared weight / bias, one set of launches; H*W not a multiple of 4 in most cases, so the
+    padded K blocks of the weight-gradient GEMM are exercised): t_hat and grad_fm per image, grad_weight / grad_bias summed
+    over the images -- against the reference composition per image, and bitwise reproducible; N = 1 batched == unbatched."""
+    g = torch.Generator(device="cpu").manual_seed(2000 + C)
+    fm = torch.randn(N, C, H, W, generator=g).to(cuda)
+    rois = torch.stack([torch.from_numpy(inside(cases.rois_random(R, 90 + n))) for n in range(N)]).to(cuda)
+    weight = (torch.randn(n_out, C * k * k, generator=g) / (C * k * k) ** 0.5).to(cuda)
+    bias = torch.randn(n_out, generator=g).to(cuda)
+    go = torch.randn(N, R, n_out, generator=g).to(cuda)
+    out = th.track_head_forward(fm, rois, weight, bias, k)
+    got = th.track_head_backward(go, fm, rois, weight, k)
+    assert tuple(out.shape) == (N, R, n_out) and tuple(got[0].shape) == tuple(fm.shape)
+    gw, gb = 0, 0
+    for n in range(N):
+        want = composition(fm[n], rois[n], weight, bias, k, go[n])
+        close(out[n], want[0], f"t_hat[{n}]")
+        close(got[0][n], want[1], f"grad_fm[{n}]")
+        gw, gb = gw + want[2], gb + want[3]
+    close(got[1], gw, "grad_weight")
+    close(got[2], gb, "grad_bias")
+    assert torch.equal(out, th.track_head_forward(fm, rois, weight, bias, k))
+    assert all(torch.equal(a, b) for a, b in zip(got, th.track_head_backward(go, fm, rois, weight, k)))
+    one = th.track_head_forward(fm[:1], rois[:1], weight, bias, k)
+    assert torch.equal(one[0], th.track_head_forward(fm[0], rois[0], weight, bias, k))
+    # autograd through the batched Function
+    fm_r, w_r, b_r = fm.clone().requires_grad_(True), weight.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    (th.TrackHeadFunction.apply(fm_r, rois, w_r, b_r, k) * go).sum().backward()
+    assert torch.equal(fm_r.grad, got[0]) and torch.equal(w_r.grad, got[1]) and torch.equal(b_r.grad, got[2])
+
+
 def test_track_head_full_size_vs_reference_kernels(cuda):
     """BASELINE config 4 (C = 1891, 38x63, 300 RoIs, k = 7, Linear(92659, 4)): the fused head against the reference's own
     ROIPool kernels (oracle/_ref) + float64 Linear, on the WHOLE tensors, including RoIs with empty bins (NaN rows)."""
