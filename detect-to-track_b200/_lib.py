@@ -18,7 +18,7 @@ _PKG = Path(__file__).resolve().parent
 _ROOT = _PKG.parent
 SO_PATH = _PKG / "libd2t_b200.so"
 HEADER = _ROOT / "include" / "d2t_b200.h"
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c_int, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
 
@@ -68,7 +68,8 @@ SIGNATURES = {
     "d2t_psroipool_bwd_batched_f32": (_c_int, _PSPOOL_B),
     "d2t_psroipool_vote_supported": (_c_int, _WS6),
     "d2t_psroipool_vote_fwd_f32": (_c_int, [_P, _P, _P] + [_c_int] * 7 + [_P]),
-    "d2t_psroipool_vote_bwd_f32": (_c_int, [_P, _P, _P] + [_c_int] * 7 + [_P]),
+    "d2t_psroipool_vote_bwd_workspace_bytes": (_c_size_t, _WS6),
+    "d2t_psroipool_vote_bwd_f32": (_c_int, [_P, _P, _P] + [_c_int] * 7 + [_P, _c_size_t, _P]),
     "d2t_trackhead_fwd_workspace_bytes": (_c_size_t, _WS6),
     "d2t_trackhead_bwd_workspace_bytes": (_c_size_t, _WS6),
     "d2t_trackhead_fwd_f32": (_c_int, [_P] * 5 + [_c_int] * 6 + [_P, _c_size_t, _P]),

@@ -117,7 +117,8 @@ int corr_tile_bwd_simt_launch(const float*, const float*, const float*, float*, 
 // PSROIPool + vote (pool_ps.cu)
 bool psb_vote_supported(int N, int R, int nT, int H, int W, int k);
 int psb_vote_fwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
-int psb_vote_bwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+size_t psb_vote_bwd_ws_bytes(int N, int R, int nT, int H, int W, int k);
+int psb_vote_bwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 // device-side RoI pipeline (roi_pipeline.cu)
 size_t roi_pipeline_ws_bytes(int A, int pre_nms);
 int roi_decode_launch(const float*, const float*, const float*, float*, float*, int, float, cudaStream_t);
@@ -399,8 +400,12 @@ int d2t_psroipool_vote_fwd_f32(const float* fm, const float* rois, float* out, i
     D2T_REQUIRE(psb_vote_supported(N, R, n_targets, H, W, r_hw), "d2t_psroipool_vote_fwd_f32: shape not supported (see d2t_psroipool_vote_supported)");
     return psb_vote_fwd_launch(fm, rois, out, N, R, n_targets, H, W, r_hw, flags, (cudaStream_t)stream);
 }
+size_t d2t_psroipool_vote_bwd_workspace_bytes(int N, int R, int n_targets, int H, int W, int r_hw) {
+    if (N <= 0 || R <= 0) return 0;
+    return psb_vote_bwd_ws_bytes(N, R, n_targets, H, W, r_hw);
+}
 int d2t_psroipool_vote_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int N, int R, int n_targets, int H,
-                               int W, int r_hw, int flags, void* stream) {
+                               int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream) {
     D2T_REQUIRE(N >= 0 && R >= 0 && n_targets > 0 && H > 0 && W > 0 && r_hw > 0, "d2t_psroipool_vote_bwd_f32: bad shape");
     if (N == 0) return D2T_OK;
     if (R == 0) {
@@ -409,7 +414,7 @@ int d2t_psroipool_vote_bwd_f32(const float* grad_out, const float* rois, float* 
     }
     D2T_REQUIRE(grad_out && rois && grad_fm, "d2t_psroipool_vote_bwd_f32: null pointer");
     D2T_REQUIRE(psb_vote_supported(N, R, n_targets, H, W, r_hw), "d2t_psroipool_vote_bwd_f32: shape not supported (see d2t_psroipool_vote_supported)");
-    return psb_vote_bwd_launch(grad_out, rois, grad_fm, N, R, n_targets, H, W, r_hw, flags, (cudaStream_t)stream);
+    return psb_vote_bwd_launch(grad_out, rois, grad_fm, N, R, n_targets, H, W, r_hw, flags, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // ---- fused track head: ROIPool -> Linear ---------------------------------------------

@@ -470,7 +470,19 @@ bool psb_supported(int N, int R, int nT, int H, int W, int k) {
 }
 
 static bool psb2_ok(int R, int H, int W, int k);
-// Which backward runs: the one-launch kernel for a single frame (latency matters: 87 us against 116 us for the four
+// third generation (pool_ps3.cu): targets on the lanes, CTA = (frame, pixel row, column block); the default wherever it applies
+bool psb3_supported(int N, int R, int nT, int H, int W, int k);
+size_t psb3_ws_bytes(int N, int R, int nT, int H, int W, int k);
+int psb3_bwd_launch(const float*, const float*, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+// Where the third generation runs (measured on B200, 300 RoIs on 38x63; profiles/r2_time_psroipool_v3.txt): a single frame
+// always (class head 39 us against 91 us for psb2 and 58 us for the reference's atomic kernel; box head 22.5 / 40 / 26 us);
+// a batch of frames when the targets fill at least half a warp (class head, 16 frames: 213 us against 257 us), while for
+// few targets its per-CTA fixed work outweighs the row-list kernels (box head, 16 frames: 97 us against 71 us).
+static bool psb3_use(int N, int R, int nT, int H, int W, int k) {
+    if (!psb3_supported(N, R, nT, H, W, k)) return false;
+    return N == 1 || nT > 8 || !psb_supported(N, R, nT, H, W, k);
+}
+// Which of the OLDER backward kernels runs otherwise: the one-launch kernel for a single frame (latency matters: 87 us against 116 us for the four
 // round-1 launches at the class-head size) and for maps the round-1 kernels cannot pack (H or W above 255); a BATCH of
 // frames fills the chip and is throughput-bound, where the round-1 row-list kernels execute fewer instructions
 // (254 us against 400 us for 16 frames; profiles/r2_ncu_psb2_summary.txt).
@@ -481,10 +493,11 @@ static bool psb2_use(int N, int R, int nT, int H, int W, int k) {
 bool psb_bwd_supported(int N, int R, int nT, int H, int W, int k) {
     if (N <= 0 || R <= 0 || nT <= 0 || k <= 0 || H <= 0 || W <= 0 || N > 65535 || nT >= 0xFFFF) return false;
     if ((long long)nT * k * k > 0x7fffffffLL / 4 || (long long)R * nT * k * k >= (1ll << 31)) return false;
-    return psb2_ok(R, H, W, k) || psb_supported(N, R, nT, H, W, k);
+    return psb3_supported(N, R, nT, H, W, k) || psb2_ok(R, H, W, k) || psb_supported(N, R, nT, H, W, k);
 }
 
 size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd) {
+    if (bwd && psb3_use(N, R, nT, H, W, k)) return psb3_ws_bytes(N, R, nT, H, W, k);
     if (bwd && psb2_use(N, R, nT, H, W, k)) return 0;   // the one-launch backward needs no workspace
     return psb_layout(N, R, nT, H, W, k, bwd).total;
 }
@@ -577,8 +590,13 @@ int psb_vote_fwd_launch(const float* fm, const float* rois, float* out, int N, i
     return D2T_OK;
 }
 
+size_t psb_vote_bwd_ws_bytes(int N, int R, int nT, int H, int W, int k) {
+    return psb3_supported(N, R, nT, H, W, k) ? psb3_ws_bytes(N, R, nT, H, W, k) : 0;
+}
+
 int psb_vote_bwd_launch(const float* go, const float* rois, float* gin, int N, int R, int nT, int H, int W, int k, int flags,
-                        cudaStream_t st) {
+                        void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (psb3_supported(N, R, nT, H, W, k)) return psb3_bwd_launch(go, rois, gin, N, R, nT, H, W, k, flags, 1, ws, ws_bytes, st);
     const size_t smem2 = psb2_smem(R, H, W, k);
     D2T_SMEM_OPTIN(psb2_bwd_kernel, smem2);
     psb2_bwd_kernel<<<dim3(nT * k * k, N), kPsb2Threads, smem2, st>>>(go, rois, gin, R, nT, H, W, k,
@@ -595,6 +613,7 @@ static bool psb2_ok(int R, int H, int W, int k) {
 
 int psb_bwd_launch(const float* go, const float* rois, float* gin, int N, int R, int nT, int H, int W, int k, int flags,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (psb3_use(N, R, nT, H, W, k)) return psb3_bwd_launch(go, rois, gin, N, R, nT, H, W, k, flags, 0, ws, ws_bytes, st);
     if (psb2_use(N, R, nT, H, W, k)) {
         const size_t smem2 = psb2_smem(R, H, W, k);
         D2T_SMEM_OPTIN(psb2_bwd_kernel, smem2);

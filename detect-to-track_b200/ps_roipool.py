@@ -162,8 +162,11 @@ class PSROIPoolVoteFunction(Function):
             _lib.check_input(g, "gradOut")
             with torch.cuda.device(g.device):
                 grad_FM = torch.empty((N, n_targets * r_hw * r_hw, H, W), dtype=g.dtype, device=g.device)
+                nbytes = _lib.lib().d2t_psroipool_vote_bwd_workspace_bytes(N, R, n_targets, H, W, r_hw)
+                ws, ws_ptr, ws_n = _lib.workspace(nbytes, g.device)
                 rc = _lib.lib().d2t_psroipool_vote_bwd_f32(g.data_ptr(), roisb.data_ptr(), grad_FM.data_ptr(), N, R, n_targets, H, W,
-                                                           r_hw, _CANONICAL if canonical_map else 0, _lib.stream_ptr(g.device))
+                                                           r_hw, _CANONICAL if canonical_map else 0, ws_ptr, ws_n,
+                                                           _lib.stream_ptr(g.device))
                 _lib.check(rc, "ps_roipool_vote_backward")
         return (grad_FM[0] if single else grad_FM), None, None, None, None
 

@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define D2T_B200_ABI_VERSION 1
+#define D2T_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define D2T_API __attribute__((visibility("default")))
@@ -202,15 +202,17 @@ D2T_API int d2t_psroipool_bwd_batched_f32(const float* grad_out, const float* ro
 /* ---- PSROIPool + vote over a batch of frames (float32) ---------------------------
  * Extension: the R-FCN heads follow PSROIPool by the vote `pooled.mean(-1).mean(-1)` (rfcn.py:40-41).  These entry points
  * return the vote directly -- out / grad_out : (N, R, n_targets) -- without forming the (N, R, n_targets, r_hw, r_hw)
- * tensor or launching the two reductions (forward: one warp per (frame, RoI, target); backward: the one-launch channel-
- * owner kernel reading grad_out / r_hw^2 per bin).  fm, rois, grad_fm as in the batched PSROIPool.  Values agree with the
+ * tensor or launching the two reductions (forward: one warp per (frame, RoI, target); backward: the PSROIPool backward
+ * kernels reading grad_out / r_hw^2 per bin).  fm, rois, grad_fm as in the batched PSROIPool.  Values agree with the
  * composition to FP32 rounding; bitwise reproducible.  d2t_psroipool_vote_supported tells whether the shape fits
- * (RoI bitmasks and one plane in shared memory); no workspace. */
+ * (RoI bitmasks and one plane in shared memory); the forward needs no workspace, the backward
+ * d2t_psroipool_vote_bwd_workspace_bytes (ABI version 2). */
 D2T_API int d2t_psroipool_vote_supported(int N, int R, int n_targets, int H, int W, int r_hw);
 D2T_API int d2t_psroipool_vote_fwd_f32(const float* fm, const float* rois, float* out, int N, int R, int n_targets, int H,
                                int W, int r_hw, int flags, void* stream);
+D2T_API size_t d2t_psroipool_vote_bwd_workspace_bytes(int N, int R, int n_targets, int H, int W, int r_hw);
 D2T_API int d2t_psroipool_vote_bwd_f32(const float* grad_out, const float* rois, float* grad_fm, int N, int R, int n_targets,
-                               int H, int W, int r_hw, int flags, void* stream);
+                               int H, int W, int r_hw, int flags, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Fused track head: ROIPool -> view -> Linear (float32) -----------------------
  * Extension beside the API-parity ops: the reference's track-regression head (correlation_tracker.py:82-85)

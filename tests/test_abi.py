@@ -14,7 +14,7 @@ import detect_to_track_b200 as d2t
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.lib()
     declared = _lib.header_symbols()
-    assert len(declared) == 51
+    assert len(declared) == 52
     assert sorted(_lib.SIGNATURES) == declared
     for name in declared:
         assert hasattr(lib, name), name
@@ -46,7 +46,7 @@ def test_empty_problem_is_a_noop():
 
 def test_workspace_queries_need_no_gpu():
     lib = _lib.lib()
-    assert lib.d2t_psroipool_bwd_workspace_bytes(300, 31, 38, 63, 7, 4) == 0      # one-launch backward: no workspace
+    assert lib.d2t_psroipool_bwd_workspace_bytes(300, 31, 38, 63, 7, 4) > 300 * 49 * 32 * 4   # transposed gradients + edges
     assert lib.d2t_psroipool_bwd_workspace_bytes(300, 31, 38, 63, 7, 8) > 0       # float64: per-pixel gather kernels
     assert lib.d2t_roipool_fwd_workspace_bytes(300, 1891, 38, 63, 7, 4) == 0
     assert lib.d2t_corr_fwd_workspace_bytes(1, 8, 10, 10, 3, 2, 8) == 0
