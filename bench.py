@@ -732,8 +732,8 @@ def run_ours(args):
                  "note": "algorithmic flops; the dense 128x256 tile x 3xTF32 executes ~9x of them on the tensor pipe (tensor pipe "
                          "54 % busy, L1 data pipe 97 %: profiles/r2_ncu_corr_fwd_umma_summary.txt); the FP32-pipe kernel it "
                          "replaced ran at 562 + 42 us"},
-                hbm_row("psb_fwd_kernel (+edges), cls head, 16 frames per call", NF * ps_bytes["cls"][0], med("ps_cls_fwd")),
-                hbm_row("psb_bwd_kernel (+edges, scale, rowlists), cls head, 16 frames per call", NF * ps_bytes["cls"][1], med("ps_cls_bwd")),
+                hbm_row("psb_fwd_kernel (+edges, cell-size order), cls head, 16 frames per call", NF * ps_bytes["cls"][0], med("ps_cls_fwd")),
+                hbm_row("psb3_bwd_kernel<32,32> (+prep: edges, transposed gradients, zero fill), cls head, 16 frames per call", NF * ps_bytes["cls"][1], med("ps_cls_bwd")),
                 hbm_row("psb_fwd_kernel (+edges), box head, 16 frames per call", NF * ps_bytes["reg"][0], med("ps_reg_fwd")),
                 hbm_row("psb_bwd_kernel (+edges, scale, rowlists), box head, 16 frames per call", NF * ps_bytes["reg"][1], med("ps_reg_bwd")),
                 {"bound": "tensor", "kernel": "fused track head forward, 8 pairs per call (layout + gemm_tf32x3_kernel<208> + pool; 3xTF32)",
