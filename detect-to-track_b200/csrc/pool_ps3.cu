@@ -156,13 +156,17 @@ psb3_prep_kernel(const float* __restrict__ go, const float* __restrict__ rois, u
             const int hh = hS[i], ww = wS[j];
             const bool live = hh > 0 && ww > 0;
             const float fn = (float)(hh * ww);
-            for (int t = g; t < nT; t += kP3PrepThreads / 64) {
-                float v = 0.f;
-                if (live) {
-                    const float gv = vote ? __ldg(src + t) * gscale : __ldg(src + t * kk + b);
-                    v = gv / fn;   // ps_roipool_cuda.cu:134-137
-                }
-                tile[t * pitch + b] = v;
+            // nT <= 32: eight targets per thread, all loads requested before the first division (one memory latency)
+            float gv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int t = g + q * (kP3PrepThreads / 64);
+                gv[q] = (live && t < nT) ? (vote ? __ldg(src + t) * gscale : __ldg(src + t * kk + b)) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int t = g + q * (kP3PrepThreads / 64);
+                if (t < nT) tile[t * pitch + b] = live ? gv[q] / fn : 0.f;   // ps_roipool_cuda.cu:134-137
             }
         }
     }
