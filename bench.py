@@ -805,6 +805,27 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank, world=1):
     copy_stream = torch.cuda.Stream(device=dev)
     grad_keys = ("c3", "c4", "c5", "reg", "cls_map", "reg_map")
 
+    # The tracker reads the stride-8 level through `interpolate(scale_factor=1/2)` (nearest: pixels (2y, 2x);
+    # correlation_tracker.py:64-66), so the odd rows of c3 are never read on the device.  The graph step uploads the even
+    # rows only -- one cudaMemcpy2DAsync per map, source and destination pitch of two rows, into the full-size device
+    # buffer the module is given -- which takes 19.6 MB per pair off the PCIe-bound leg.  The
+    # columns stay: a pitch cannot skip them.  Same module call, same result (the step's loss is checked against the
+    # eager step, which uploads everything); `h2d_bytes_per_step` counts the bytes that are copied.
+    even_rows = None
+    try:
+        from cuda.bindings import runtime as cudart
+        def even_rows(dst, src):
+            ch, h2, w2 = src.shape
+            rowb = w2 * src.element_size()
+            err = cudart.cudaMemcpy2DAsync(dst.data_ptr(), 2 * rowb, src.data_ptr(), 2 * rowb, rowb, ch * (h2 // 2),
+                                           cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, copy_stream.cuda_stream)[0]
+            if err != cudart.cudaError_t.cudaSuccess:
+                raise RuntimeError(f"cudaMemcpy2DAsync: {err}")
+    except Exception as exc:   # no cuda-python: upload the whole map
+        print(f"[bench] e2e: cuda-python unavailable ({exc!r}); uploading all rows of c3", file=sys.stderr, flush=True)
+        even_rows = None
+    c3_bytes = sum(t.numel() * t.element_size() for it in host for t in it["c3"])
+
     def pair_loss(d):
         """the public modules on one pair's device tensors -> scalar loss (autograd graph attached)"""
         pyr0 = {"c3": d["c3"][0], "c4": d["c4"][0], "c5": d["c5"][0]}
@@ -906,7 +927,10 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank, world=1):
                 copy_stream.wait_event(done[st])  # the replay that last read this set has finished
                 for k, v in host[n].items():
                     for i, t in enumerate(v):
-                        sets[st][k][i].copy_(t, non_blocking=True)
+                        if k == "c3" and even_rows is not None:
+                            even_rows(sets[st][k][i], t)
+                        else:
+                            sets[st][k][i].copy_(t, non_blocking=True)
                 ready[st].record(copy_stream)
 
         state = {"have0": False}  # pair 0 of the coming step is already on its way (prefetched during the last step)
@@ -956,6 +980,9 @@ def run_e2e(torch, dev, d2t, steps, barrier, rank, world=1):
         if not (got == got and abs(got - want) <= 1e-4 * max(1.0, abs(want))):
             raise RuntimeError(f"graph-replayed step loss {got} != eager loss {want}")
         one_step, mode = graph_step, "module calls of a pair captured as a CUDA graph (2 static input sets)"
+        if even_rows is not None:
+            h2d -= c3_bytes // 2
+            mode += "; of the stride-8 maps only the even rows are uploaded (the rows nearest-neighbour down-sampling reads)"
     one_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
