@@ -392,7 +392,37 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
     note_launch(2);
     const int PT = NB * d.P;
     GemmOperand A{w.xt, PT, d.ldc}, B{w.wt, d.N1, d.ldc};
-    if ((rc = gemm_tf32x3(A, B, w.zpart, PT, d.N1, C, d.ldn, GEMM_EPI_ROW, d.s1, PT, d.bn, st))) return rc;
+    // Wave quantisation: 8 pairs of 38x63 positions are 150 tiles of 128 rows on 148 SMs -- as one launch the last two tiles
+    // are a second wave as long as the first (122 us instead of 61).  When a few tiles spill over a whole number of waves,
+    // the first waves * SMs tiles run un-split and the spill runs as a short split-K problem whose slabs (in w.z) are summed
+    // into the tail rows of the result.
+    const int tiles = ceil_div(PT, 128), kb = ceil_div(C, 32);
+    const int spill = tiles % di.sm_count;
+    if (d.s1 == 1 && tiles > di.sm_count && spill > 0 && spill * 8 <= di.sm_count && kb >= 8) {
+        const int M1 = (tiles - spill) * 128, Mt = PT - M1;
+        int stail = di.sm_count / (4 * spill);
+        if (stail > kb / 2) stail = kb / 2;
+        if (stail < 1) stail = 1;
+        if ((long long)stail * Mt <= (long long)PT) {
+            GemmOperand A1{w.xt, M1, d.ldc}, At{w.xt + (size_t)M1 * d.ldc, Mt, d.ldc};
+            if ((rc = gemm_tf32x3(A1, B, w.zpart, M1, d.N1, C, d.ldn, GEMM_EPI_ROW, 1, M1, d.bn, st))) return rc;
+            float* tailOut = w.zpart + (size_t)M1 * d.ldn;
+            if (stail == 1) {
+                if ((rc = gemm_tf32x3(At, B, tailOut, Mt, d.N1, C, d.ldn, GEMM_EPI_ROW, 1, Mt, d.bn, st))) return rc;
+            } else {
+                if ((rc = gemm_tf32x3(At, B, w.z, Mt, d.N1, C, d.ldn, GEMM_EPI_ROW, stail, Mt, d.bn, st))) return rc;
+                const int n4t = Mt * d.ldn / 4;
+                th_reduce_slabs_kernel<<<grid_for(n4t, 256, cap), 256, 0, st>>>(reinterpret_cast<const float4*>(w.z),
+                                                                                reinterpret_cast<float4*>(tailOut), n4t, stail);
+                D2T_CUDA_TRY(cudaGetLastError());
+                note_launch();
+            }
+        } else if ((rc = gemm_tf32x3(A, B, w.zpart, PT, d.N1, C, d.ldn, GEMM_EPI_ROW, d.s1, PT, d.bn, st))) {
+            return rc;
+        }
+    } else if ((rc = gemm_tf32x3(A, B, w.zpart, PT, d.N1, C, d.ldn, GEMM_EPI_ROW, d.s1, PT, d.bn, st))) {
+        return rc;
+    }
     const float* z = w.zpart;
     if (d.s1 > 1) {
         const int n4 = PT * d.ldn / 4;
