@@ -339,7 +339,7 @@ def run_reference_gpu(torch, dev):
 
 
 # --------------------------------------------------------------------------------------------- config 5: train step
-def run_train_step(torch, dev, rank, world, barrier, pairs=PAIRS_PER_GPU, steps=3, warmup=2):
+def run_train_step(torch, dev, rank, world, barrier, pairs=PAIRS_PER_GPU, steps=5, warmup=2):
     """BASELINE config 5: full D&T R-FCN ResNet-101 training step (backbone -> RPN -> R-FCN heads -> correlation tracker ->
     losses -> backward -> SGD) on synthetic 608x1008 frame pairs, `pairs` per GPU per step, DistributedDataParallel over
     the pair shards (bucketed NCCL all-reduce overlapped with the backward).  Images cross PCIe inside the timed region
@@ -383,21 +383,22 @@ def run_train_step(torch, dev, rank, world, barrier, pairs=PAIRS_PER_GPU, steps=
             for _ in range(warmup):
                 last = one_step(sync)
             barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            ev[0].record()
+            for n in range(steps):
                 last = one_step(sync)
-            e1.record()
+                ev[n + 1].record()
             barrier()
             if not (last == last):
                 raise RuntimeError("train step produced a NaN loss")
-            return e0.elapsed_time(e1) / steps, last
+            each = sorted(ev[n].elapsed_time(ev[n + 1]) for n in range(steps))
+            return ev[0].elapsed_time(ev[steps]) / steps, last, each[steps // 2]
 
-        ms, last = timed(True)
+        ms, last, ms_median = timed(True)
         ms_nosync = timed(False)[0] if world > 1 else ms
-        ms, ms_nosync = global_max([ms, ms_nosync], dev)
+        ms, ms_nosync, ms_median = global_max([ms, ms_nosync, ms_median], dev)
         out[key] = {
-            "ms_per_step": ms, "pairs_per_s": world * pairs / (ms * 1e-3), "loss": last,
+            "ms_per_step": ms, "ms_per_step_median": ms_median, "pairs_per_s": world * pairs / (ms * 1e-3), "loss": last,
             "ms_per_step_without_gradient_sync": ms_nosync, "exposed_allreduce_ms": max(0.0, ms - ms_nosync)}
         out["trainable_parameter_mb"] = ts.trainable_parameter_bytes(stepm) / 1e6
         out["h2d_bytes_per_step"] = h2d

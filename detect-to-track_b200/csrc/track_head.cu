@@ -130,6 +130,14 @@ th_pad_copy_kernel(const float* __restrict__ x, float* __restrict__ xc, int C, i
     const int c = blockIdx.y, b = blockIdx.z;
     const float* src = x + ((size_t)b * C + c) * P;
     float* dst = xc + (size_t)c * NB * ldp + (size_t)b * ldp;
+    if ((P & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {
+        // even plane size: every source row starts on an 8-byte boundary (the destination pitch is a multiple of 16 bytes)
+        const float2* s2 = reinterpret_cast<const float2*>(src);
+        float2* d2 = reinterpret_cast<float2*>(dst);
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ldp / 2; q += gridDim.x * blockDim.x)
+            d2[q] = 2 * q < P ? __ldg(s2 + q) : make_float2(0.f, 0.f);
+        return;
+    }
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < ldp; p += gridDim.x * blockDim.x) dst[p] = p < P ? __ldg(src + p) : 0.f;
 }
 
@@ -492,7 +500,7 @@ int trackhead_bwd_launch(const float* go, const float* fm, const float* rois, co
     if (gw) {
         const float* xc = fm;
         if (NB > 1 || d.P != d.ldp || (reinterpret_cast<uintptr_t>(fm) & 15) != 0) {
-            th_pad_copy_kernel<<<dim3(ceil_div(d.ldp, 1024), C, NB), 256, 0, st>>>(fm, w.xc, C, d.P, d.ldp, NB);
+            th_pad_copy_kernel<<<dim3(ceil_div(d.ldp, 2048), C, NB), 256, 0, st>>>(fm, w.xc, C, d.P, d.ldp, NB);
             D2T_CUDA_TRY(cudaGetLastError());
             note_launch();
             xc = w.xc;
