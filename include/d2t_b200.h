@@ -189,8 +189,11 @@ D2T_API int d2t_psroipool_bwd_f64(const double* grad_out, const double* rois, do
 /* ---- PSROIPool over a batch of frames (float32) ---------------------------
  * Extension: the reference pools one frame per call (rfcn.py:36-41, called per frame from trainer.py:208-209).
  * fm : (N, n_targets*r_hw^2, H, W);  rois : (N, R, 4);  out / grad_out : (N, R, n_targets, r_hw, r_hw);
- * grad_fm : (N, n_targets*r_hw^2, H, W).  Frame n uses rois[n].  Results are bit-identical to N single-frame calls;
- * one set of launches covers all frames (a CTA owns one (frame, channel) plane).
+ * grad_fm : (N, n_targets*r_hw^2, H, W).  Frame n uses rois[n].  One set of launches covers all frames.  The forward is
+ * bit-identical to N single-frame calls (and to the reference kernel); the backward is bit-identical to N single-frame
+ * calls for more than 8 targets (both run pool_ps3.cu: targets on the lanes, a CTA per (frame, pixel row, column block), no
+ * floating-point atomics, no difference arrays) and agrees within FP32 rounding otherwise (row-list kernels).  Always
+ * bitwise reproducible run to run.
  */
 D2T_API size_t d2t_psroipool_fwd_batched_workspace_bytes(int N, int R, int n_targets, int H, int W, int r_hw, int elem_size);
 D2T_API int d2t_psroipool_fwd_batched_f32(const float* fm, const float* rois, float* out, int N, int R, int n_targets,
