@@ -67,9 +67,8 @@ static size_t p3_smem(int R, int nT, int k, int XB) {
 // b * XB * (TP + 1) + t of its users (t, b), ascending t
 struct P3Tab {
     int nLive;
-    uint16_t ch[kP3MaxCh];        // live channel l -> channel
-    uint16_t start[kP3MaxCh + 2];  // users of live channel l: user[start[l] .. start[l + 1])
-    uint32_t user[kP3MaxCh];
+    uint32_t rec[kP3MaxCh];    // live channel l: first user (11 bits) | number of users << 11 (6 bits) | channel << 17
+    uint32_t user[kP3MaxCh];   // byte offsets into U, grouped by channel, ascending t inside a channel
 };
 
 static void p3_build_tab(P3Tab& tab, int nT, int k, int canonical, int XB) {
@@ -82,14 +81,9 @@ static void p3_build_tab(P3Tab& tab, int nT, int k, int canonical, int XB) {
     int nU = 0, nLive = 0;
     for (int ch = 0; ch < nCh; ++ch) {
         pos[ch] = (uint16_t)nU;
-        if (cnt[ch]) {
-            tab.ch[nLive] = (uint16_t)ch;
-            tab.start[nLive] = (uint16_t)nU;
-            ++nLive;
-        }
+        if (cnt[ch]) tab.rec[nLive++] = (uint32_t)nU | ((uint32_t)cnt[ch] << 11) | ((uint32_t)ch << 17);
         nU += cnt[ch];
     }
-    tab.start[nLive] = (uint16_t)nU;
     tab.nLive = nLive;
     for (int t = 0; t < nT; ++t)
         for (int b = 0; b < kk; ++b) tab.user[pos[canonical ? t * kk + b : (t + 1) * b]++] = (uint32_t)((b * XB * P + t) * 4);
@@ -320,20 +314,24 @@ psb3_bwd_kernel(const float* __restrict__ gT, const uint32_t* __restrict__ erow,
         constexpr int CPW = 32 / XB;   // channels per step
         const int x = lane & (XB - 1), sub = lane / XB;
         const bool xin = x0 + x < W;
-        const char* Ux = reinterpret_cast<const char*>(U + x * P);
+        const uint32_t ux = (uint32_t)__cvta_generic_to_shared(U + x * P);   // shared-window address of this lane's column
         float* dst = gin + ((size_t)n * nCh * H + y) * W + x0 + x;
         const unsigned HW = (unsigned)(H * W);   // nCh * H * W < 2^31 (psb3_supported)
         const int nLive = tab.nLive;
         for (int l0 = warp * CPW; l0 < nLive; l0 += NW * CPW) {
             const int l = l0 + sub;
             const bool ok = l < nLive;
-            const int ll = ok ? l : l0;
-            int u = tab.start[ll];
-            const int u1 = ok ? (int)tab.start[ll + 1] : u;
+            const uint32_t rec = tab.rec[ok ? l : l0];
+            const uint32_t* up = tab.user + (rec & 2047u);
+            int nu = ok ? (int)((rec >> 11) & 63u) : 0;
             float acc = 0.f;
 #pragma unroll 1
-            for (; u < u1; ++u) acc += *reinterpret_cast<const float*>(Ux + tab.user[u]);
-            if (ok && xin) dst[(unsigned)tab.ch[ll] * HW] = acc;
+            for (; nu > 0; --nu, ++up) {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ux + *up) : "memory");
+                acc += v;
+            }
+            if (ok && xin) dst[(rec >> 17) * HW] = acc;
         }
     }
 }
