@@ -537,6 +537,12 @@ bool psb_supported(int N, int R, int nT, int H, int W, int k) {
 }
 
 static bool psb2_ok(int R, int H, int W, int k);
+// the round-1 row-list BACKWARD finds the users of a channel with one thread per bin and runs kPsbRowThreads threads
+// (the forward runs kPsbFwdThreads): r_hw <= 8.  (r_hw = 9 used to reach it and read past its tables -- found by the
+// r_hw = 9 cases of test_psroipool_batched_equals_per_frame.)
+static bool psb_rowlist_bwd_ok(int N, int R, int nT, int H, int W, int k) {
+    return k * k <= kPsbRowThreads && psb_supported(N, R, nT, H, W, k);
+}
 // third generation (pool_ps3.cu): targets on the lanes, CTA = (frame, pixel row, column block); the default wherever it applies
 bool psb3_supported(int N, int R, int nT, int H, int W, int k);
 size_t psb3_ws_bytes(int N, int R, int nT, int H, int W, int k);
@@ -547,20 +553,20 @@ int psb3_bwd_launch(const float*, const float*, float*, int, int, int, int, int,
 // few targets its per-CTA fixed work outweighs the row-list kernels (box head, 16 frames: 97 us against 71 us).
 static bool psb3_use(int N, int R, int nT, int H, int W, int k) {
     if (!psb3_supported(N, R, nT, H, W, k)) return false;
-    return N == 1 || nT > 8 || !psb_supported(N, R, nT, H, W, k);
+    return N == 1 || nT > 8 || !psb_rowlist_bwd_ok(N, R, nT, H, W, k);
 }
 // Which of the OLDER backward kernels runs otherwise: the one-launch kernel for a single frame (latency matters: 87 us against 116 us for the four
 // round-1 launches at the class-head size) and for maps the round-1 kernels cannot pack (H or W above 255); a BATCH of
 // frames fills the chip and is throughput-bound, where the round-1 row-list kernels execute fewer instructions
 // (254 us against 400 us for 16 frames; profiles/r2_ncu_psb2_summary.txt).
 static bool psb2_use(int N, int R, int nT, int H, int W, int k) {
-    return psb2_ok(R, H, W, k) && (N == 1 || !psb_supported(N, R, nT, H, W, k));
+    return psb2_ok(R, H, W, k) && (N == 1 || !psb_rowlist_bwd_ok(N, R, nT, H, W, k));
 }
 
 bool psb_bwd_supported(int N, int R, int nT, int H, int W, int k) {
     if (N <= 0 || R <= 0 || nT <= 0 || k <= 0 || H <= 0 || W <= 0 || N > 65535 || nT >= 0xFFFF) return false;
     if ((long long)nT * k * k > 0x7fffffffLL / 4 || (long long)R * nT * k * k >= (1ll << 31)) return false;
-    return psb3_supported(N, R, nT, H, W, k) || psb2_ok(R, H, W, k) || psb_supported(N, R, nT, H, W, k);
+    return psb3_supported(N, R, nT, H, W, k) || psb2_ok(R, H, W, k) || psb_rowlist_bwd_ok(N, R, nT, H, W, k);
 }
 
 size_t psb_ws_bytes(int N, int R, int nT, int H, int W, int k, bool bwd) {

@@ -670,7 +670,7 @@ def test_roipool_full_size_track_head_vs_reference_kernels(cuda):
 # ------------------------------------------------------------------ PSROIPool
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("canonical", [False, True])
-@pytest.mark.parametrize("nT,H,W,k", [(1, 10, 10, 6), (2, 11, 10, 7), (4, 38, 63, 7), (31, 38, 63, 7)])
+@pytest.mark.parametrize("nT,H,W,k", [(1, 10, 10, 6), (2, 11, 10, 7), (4, 38, 63, 7), (31, 38, 63, 7), (33, 12, 13, 3), (2, 20, 21, 9)])
 def test_psroipool_vs_oracle(cuda, nT, H, W, k, canonical, dtype):
     rois = _roipool_rois(H, W, dtype, R=60)
     fm, go = cases.pool_inputs(nT * k * k, H, W, (rois.shape[0], nT, k, k), 34, dtype)
@@ -737,7 +737,8 @@ def test_psroipool_full_size_cls_head(cuda):
 
 
 @pytest.mark.parametrize("canonical", [False, True])
-@pytest.mark.parametrize("N,nT,H,W,k,R", [(3, 4, 38, 63, 7, 50), (2, 31, 38, 63, 7, 300), (4, 2, 11, 10, 6, 9), (1, 5, 20, 21, 3, 700)])
+@pytest.mark.parametrize("N,nT,H,W,k,R", [(3, 4, 38, 63, 7, 50), (2, 31, 38, 63, 7, 300), (4, 2, 11, 10, 6, 9), (1, 5, 20, 21, 3, 700),
+                                           (2, 33, 12, 13, 3, 20), (2, 3, 20, 21, 9, 30)])
 def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
     """the batched entry points (one set of launches for N frames) against N single-frame calls: the forward is
     bit-identical (both keep the reference's summation order); so is the backward wherever a batch and a single frame run
@@ -757,7 +758,7 @@ def test_psroipool_batched_equals_per_frame(cuda, N, nT, H, W, k, R, canonical):
         o1 = ps_mod.ps_roipool_forward(dev(fm[n], cuda), dev(rois[n], cuda), nT, k, canonical)
         g1 = ps_mod.ps_roipool_backward(dev(go[n], cuda), dev(rois[n], cuda), H, W, canonical)
         assert torch.equal(out[n], o1)
-        if nT > 8 or N == 1:
+        if (8 < nT <= 32 and k <= 8) or N == 1:   # same kernel (pool_ps3.cu); 33 targets / r_hw = 9: the older kernels
             assert torch.equal(g1, gin[n])
         else:
             close(g1, gin[n].cpu().numpy(), np.float32)
