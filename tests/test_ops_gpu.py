@@ -926,3 +926,66 @@ def test_golden_psroipool(cuda, case):
     else:
         close(out, g["out"], dtype, scale=1.0)
     close(ps_mod.ps_roipool_backward(dev(g["go"], cuda), dev(g["rois"], cuda), H, W), g["gin"], dtype)
+
+
+# ------------------------------------------------------------------ randomized shape sweep (dispatch boundaries)
+
+
+@pytest.mark.parametrize("case", range(48))
+def test_shape_sweep_pooling_vs_oracle(cuda, case):
+    """Seeded random shapes for ROIPool / PSROIPool, single frame and batched, against the oracle: r_hw from 1 to 10, target
+    counts on both sides of every lane split (1 .. 40), channel counts that are not multiples of the slab, maps from 1x1 to
+    wider than 255, RoI counts from 1 to several hundred.  The point is the DISPATCH boundaries between kernel families
+    (a batched r_hw = 9 backward used to reach a kernel built for r_hw <= 8)."""
+    rng = np.random.default_rng(1000 + case)
+    k = int(rng.integers(1, 11))
+    nT = int(rng.choice([1, 2, 3, 4, 5, 8, 9, 16, 17, 31, 32, 33, 40]))
+    H, W = int(rng.integers(1, 48)), int(rng.integers(1, 80))
+    if case % 6 == 5:
+        W = int(rng.integers(256, 320))
+    R = int(rng.choice([1, 2, 7, 33, 150, 400]))
+    C = int(rng.integers(1, 40))
+    N = int(rng.integers(1, 4))
+    rois = np.stack([np.concatenate([cases.rois_random(R, 5000 + 10 * case + n), cases.rois_edge_cases(H, W)[:6]])
+                     for n in range(N)]).astype(np.float32)
+    Rt = rois.shape[1]
+    # ROIPool (single frame)
+    fm = rng.standard_normal((C, H, W)).astype(np.float32)
+    go = rng.standard_normal((Rt, C, k, k)).astype(np.float32)
+    want = oracle.roipool_fwd(fm, rois[0], k)
+    out = rp_mod.roipool_forward(dev(fm, cuda), dev(rois[0], cuda), k)
+    close(out, want, np.float32, scale=float(np.nanmax(np.abs(want))) if np.isfinite(want).any() else 1.0, equal_nan=True)
+    close(rp_mod.roipool_backward(dev(go, cuda), dev(rois[0], cuda), H, W), oracle.roipool_bwd(go, rois[0], H, W), np.float32)
+    # PSROIPool, both channel maps, single frame and batched
+    canonical = bool(case & 1)
+    sfm = rng.standard_normal((N, nT * k * k, H, W)).astype(np.float32)
+    sgo = rng.standard_normal((N, Rt, nT, k, k)).astype(np.float32)
+    outb = ps_mod.ps_roipool_forward_batched(dev(sfm, cuda), dev(rois, cuda), nT, k, canonical)
+    ginb = ps_mod.ps_roipool_backward_batched(dev(sgo, cuda), dev(rois, cuda), H, W, canonical)
+    for n in range(N):
+        np.testing.assert_array_equal(outb[n].cpu().numpy(), oracle.psroipool_fwd(sfm[n], rois[n], nT, k, canonical))
+        wantg = oracle.psroipool_bwd(sgo[n], rois[n], H, W, canonical)
+        close(ginb[n], wantg, np.float32)
+        close(ps_mod.ps_roipool_backward(dev(sgo[n], cuda), dev(rois[n], cuda), H, W, canonical), wantg, np.float32)
+        np.testing.assert_array_equal(ps_mod.ps_roipool_forward(dev(sfm[n], cuda), dev(rois[n], cuda), nT, k, canonical).cpu().numpy(),
+                                      oracle.psroipool_fwd(sfm[n], rois[n], nT, k, canonical))
+
+
+@pytest.mark.parametrize("case", range(32))
+def test_shape_sweep_correlation_vs_oracle(cuda, case):
+    """Seeded random shapes for the correlation: displacements 1 .. 8, strides 1 .. 3, channel counts on both sides of the
+    tensor-core threshold (128) and not multiples of the stage size, maps smaller than a tile and not multiples of it."""
+    rng = np.random.default_rng(2000 + case)
+    d = int(rng.choice([1, 2, 3, 4, 8, 8]))
+    stride = int(rng.choice([1, 1, 1, 2, 3]))
+    C = int(rng.choice([1, 3, 31, 64, 127, 128, 129, 160, 257]))
+    B = int(rng.integers(1, 4))
+    H, W = int(rng.integers(1, 30)), int(rng.integers(1, 40))
+    fm0, fm1, go = cases.corr_inputs(B, C, H, W, d, 3000 + case)
+    want = oracle.corr_fwd(fm0, fm1, d, stride)
+    out = pc_mod.pointwise_correlation_forward(dev(fm0, cuda), dev(fm1, cuda), d, stride)
+    close(out, want, np.float32, scale=float(np.abs(want).max()) if want.size else 1.0)
+    g0, g1 = pc_mod.pointwise_correlation_backward(dev(go, cuda), dev(fm0, cuda), dev(fm1, cuda), d, stride)
+    w0, w1 = oracle.corr_bwd(go, fm0, fm1, d, stride)
+    close(g0, w0, np.float32)
+    close(g1, w1, np.float32)
