@@ -170,3 +170,35 @@ def test_gemm_building_block_matches_float64(cuda, M, N, K, splits, bn, col):
     ref = A[:, :K].double() @ B[:, :K].double().t()
     mag = A[:, :K].double().abs() @ B[:, :K].double().abs().t()
     assert bool(((got.double() - ref).abs() <= 4e-6 * mag + 1e-30).all())
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_track_head_shape_sweep(cuda, case):
+    """Seeded random shapes of the fused head against the per-image composition: image counts whose position tiles do and do
+    not fill whole waves (the spill path of the forward GEMM), r_hw 1 .. 7, 1 .. 5 outputs, channel counts that are not
+    multiples of the GEMM's K block, maps down to 1x1."""
+    rng = np.random.default_rng(7000 + case)
+    k = int(rng.integers(1, 8))
+    n_out = int(rng.integers(1, 6))
+    N = int(rng.choice([1, 2, 3, 8, 9, 17]))
+    C = int(rng.choice([1, 5, 31, 32, 33, 100, 257]))
+    H, W = int(rng.integers(1, 40)), int(rng.integers(1, 64))
+    if case % 8 == 7:
+        N, H, W = 8, 38, 63            # 150 position tiles on 148 SMs
+    R = int(rng.choice([1, 3, 40, 120]))
+    g = torch.Generator(device="cpu").manual_seed(7100 + case)
+    fm = torch.randn(N, C, H, W, generator=g).to(cuda)
+    rois = torch.stack([torch.from_numpy(inside(cases.rois_random(R, 7200 + 20 * case + n))) for n in range(N)]).to(cuda)
+    weight = (torch.randn(n_out, C * k * k, generator=g) / (C * k * k) ** 0.5).to(cuda)
+    bias = torch.randn(n_out, generator=g).to(cuda)
+    go = torch.randn(N, R, n_out, generator=g).to(cuda)
+    out = th.track_head_forward(fm, rois, weight, bias, k)
+    got = th.track_head_backward(go, fm, rois, weight, k)
+    gw, gb = 0, 0
+    for n in range(N):
+        want = composition(fm[n], rois[n], weight, bias, k, go[n])
+        close(out[n], want[0], f"t_hat[{n}]")
+        close(got[0][n], want[1], f"grad_fm[{n}]")
+        gw, gb = gw + want[2], gb + want[3]
+    close(got[1], gw, "grad_weight")
+    close(got[2], gb, "grad_bias")
