@@ -358,6 +358,42 @@ def test_roipool_backward_stays_inside_its_buffers(cuda, C, H, W, R):
     close(gin.view(C, H, W), want, np.float32)
 
 
+@pytest.mark.parametrize("N,nT,H,W,k,R", [(1, 31, 38, 63, 7, 300), (3, 31, 38, 63, 7, 40), (2, 4, 17, 50, 5, 33), (1, 5, 9, 33, 8, 600),
+                                           (2, 3, 20, 21, 9, 30)])
+def test_psroipool_backward_stays_inside_its_buffers(cuda, N, nT, H, W, k, R):
+    """the float32 PSROIPool backward (pool_ps3.cu and the fallback kernels) through the C ABI with its output, its gradient
+    input and its WORKSPACE each embedded in sentinel-filled allocations: guard zones untouched, every output element written
+    (the prep kernel zero-fills the channels nobody reads, the main kernel writes the rest), result equal to the oracle."""
+    from detect_to_track_b200 import _lib
+    lib = _lib.lib()
+    guard, sentinel = 4096, 1234.5
+    rois_np = np.stack([np.concatenate([cases.rois_edge_cases(H, W), cases.rois_random(R, 8100 + n), cases.ROIS_OOB.astype(np.float32)])
+                        for n in range(N)]).astype(np.float32)
+    Rt = rois_np.shape[1]
+    g = torch.Generator(device="cpu").manual_seed(8)
+    nCh = nT * k * k
+    n_go, n_out = N * Rt * nCh, N * nCh * H * W
+    gob = torch.full((guard + n_go,), sentinel, device=cuda)
+    go = gob[guard:]
+    go.copy_(torch.randn(n_go, generator=g))
+    rois = dev(rois_np, cuda)
+    buf = torch.full((n_out + 2 * guard,), sentinel, device=cuda)
+    gin = buf[guard:guard + n_out]
+    nws = lib.d2t_psroipool_bwd_batched_workspace_bytes(N, Rt, nT, H, W, k, 4)
+    wsb = torch.full((max(nws, 1) + 2 * guard,), 0x5A, dtype=torch.uint8, device=cuda)
+    rc = lib.d2t_psroipool_bwd_batched_f32(go.data_ptr(), rois.data_ptr(), gin.data_ptr(), N, Rt, nT, H, W, k, 0,
+                                           wsb.data_ptr() + guard if nws else None, nws, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + n_out:] == sentinel).all())
+    assert bool((gob[:guard] == sentinel).all())
+    assert bool((wsb[:guard] == 0x5A).all()) and bool((wsb[guard + nws:] == 0x5A).all())
+    assert not bool((gin == sentinel).any()) and bool(torch.isfinite(gin).all())
+    gv = gin.view(N, nCh, H, W)
+    for n in range(N):
+        close(gv[n], oracle.psroipool_bwd(go.view(N, Rt, nT, k, k)[n].cpu().numpy(), rois_np[n], H, W), np.float32)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_pooling_with_no_rois(cuda, dtype):
     """R = 0: the forward returns an empty tensor and the backward a zero gradient of the map's shape (the reference

@@ -37,3 +37,31 @@ for (nT, H, W, k, dt) in [(31, 38, 63, 7, np.float32), (2, 11, 10, 6, np.float64
     ps.ps_roipool_backward(torch.from_numpy(go).to(dev), r, H, W)
 torch.cuda.synchronize()
 print("sanitize run ok")
+# round 2: batched PSROIPool (ordered forward, targets-on-lanes backward in both column-block widths, box-head lane split,
+# row-list fallback, r_hw = 9 / 33 targets on the older kernels), pool + vote, fused track head (incl. the spill path)
+from detect_to_track_b200 import track_head as th  # noqa: E402
+import detect_to_track_b200 as d2t  # noqa: E402
+for (N, nT, H, W, k, R) in [(16, 31, 38, 63, 7, 300), (2, 31, 38, 63, 7, 40), (3, 4, 38, 63, 7, 50), (2, 33, 12, 13, 3, 20),
+                            (2, 3, 20, 21, 9, 30), (1, 5, 20, 21, 3, 700), (2, 2, 12, 300, 7, 25)]:
+    rois = torch.stack([torch.from_numpy(np.concatenate([cases.rois_edge_cases(H, W), cases.rois_random(R, 11 + n),
+                                                         cases.ROIS_OOB.astype(np.float32)])) for n in range(N)]).to(dev)
+    Rt = rois.shape[1]
+    g = torch.Generator(device="cpu").manual_seed(3)
+    fm = torch.randn(N, nT * k * k, H, W, generator=g).to(dev)
+    go = torch.randn(N, Rt, nT, k, k, generator=g).to(dev)
+    ps.ps_roipool_forward_batched(fm, rois, nT, k)
+    ps.ps_roipool_backward_batched(go, rois, H, W)
+    ps.ps_roipool_backward(go[0], rois[0], H, W, True)
+    fm.requires_grad_(True)
+    d2t.PSROIPoolVoteFunction.apply(fm, rois, nT, k, False).sum().backward()
+for (N, C, H, W, R, k, nO) in [(2, 37, 20, 21, 40, 7, 4), (8, 40, 38, 63, 30, 7, 4), (1, 130, 38, 63, 77, 7, 4)]:
+    g = torch.Generator(device="cpu").manual_seed(4)
+    fm = torch.randn(N, C, H, W, generator=g).to(dev)
+    rois = torch.stack([torch.from_numpy(cases.rois_random(R, 21 + n)) for n in range(N)]).to(dev)
+    w = (torch.randn(nO, C * k * k, generator=g) / 50).to(dev)
+    b = torch.zeros(nO, device=dev)
+    tgo = torch.randn(N, R, nO, generator=g).to(dev)
+    th.track_head_forward(fm, rois, w, b, k)
+    th.track_head_backward(tgo, fm, rois, w, k)
+torch.cuda.synchronize()
+print("sanitize run (round 2) ok")
