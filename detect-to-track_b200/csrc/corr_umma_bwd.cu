@@ -171,6 +171,11 @@ corr_bwd_umma_kernel(const float* __restrict__ gsrc, const float* __restrict__ x
     const size_t plane = (size_t)H * W;
     const uint64_t planeBytes = (uint64_t)plane * sizeof(float);
 
+    // The grad_FM1 kernel does not read anything this kernel writes (its input is the flipped gradOut of the flip kernel, which
+    // is complete before this kernel starts): let it be launched as this kernel's CTAs exit, so that the SMs whose CTA had one
+    // item less than the others start on grad_FM1 instead of idling through the tail (programmatic dependent launch)
+    if (MODE == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(x_smem(&tmem_base_s)), "r"((uint32_t)(2 * XN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -508,7 +513,20 @@ int corr_umma_bwd_launch(const float* go, const float* fm0, const float* fm1, fl
     corr_bwd_umma_kernel<0><<<grid, XTHREADS, smem, st>>>(go, fm1, g0, p);   // grad_FM0: G = gradOut, X = FM1
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
-    corr_bwd_umma_kernel<1><<<grid, XTHREADS, smem, st>>>(gt, fm0, g1, p);   // grad_FM1: G = flipped gradOut, X = FM0
+    {   // grad_FM1: G = flipped gradOut, X = FM0; may start while grad_FM0's last CTAs are still running (see the kernel)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(XTHREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const float* gtc = gt;
+        D2T_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_bwd_umma_kernel<1>, gtc, fm0, g1, p));
+    }
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;
