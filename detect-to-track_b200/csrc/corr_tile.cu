@@ -368,6 +368,8 @@ corr_bwd_tile_kernel(const float* __restrict__ go, const float* __restrict__ xsr
     extern __shared__ __align__(16) float smem[];
     float* red = smem + kStages * STAGE_FLOATS;  // 2 x [256 threads][RP]: partials of chunk n / n+1
     constexpr int RED_FLOATS = kCorrThreads * RP;
+    // the grad_FM1 launch reads nothing this one writes: it may start as soon as SMs are free (programmatic dependent launch)
+    if (MODE == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -649,7 +651,19 @@ static int bwd_launch(const float* go, const float* fm0, const float* fm1, float
     k0<<<p.G, kCorrThreads, smem, st>>>(go, fm1, g0, p);
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
-    k1<<<p.G, kCorrThreads, smem, st>>>(go, fm0, g1, p);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(p.G);
+        cfg.blockDim = dim3(kCorrThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        D2T_CUDA_TRY(cudaLaunchKernelEx(&cfg, k1, go, fm0, g1, p));
+    }
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     return D2T_OK;

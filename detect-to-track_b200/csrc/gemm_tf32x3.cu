@@ -111,6 +111,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * GM, n0 = blockIdx.y * BN, split = blockIdx.z;
+    // a following launch that carries the programmatic-serialization attribute (i.e. one the caller knows to be independent of
+    // this GEMM, like the pad copy of the track-head backward) may start while this grid runs; ignored otherwise
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // k-blocks of this split: an even share, the first `rem` splits take one more
     const int per = a.kblocks / a.splits, rem = a.kblocks % a.splits;
     const int kbBeg = split * per + min(split, rem);

@@ -147,6 +147,7 @@ th_pad_copy_kernel(const float* __restrict__ x, float* __restrict__ xc, int C, i
 //              -> Wc (c, ldn)   [K = n]   (by_channel == 1)
 __global__ void __launch_bounds__(256)
 th_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int KK, int nO, int ld, int by_channel) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see launch_overlapped
     const int total = nO * C * KK;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         int o, c, ij;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(kGzThreads)
 th_gz_kernel(const float* __restrict__ g, const float* __restrict__ rois, float* __restrict__ gz, float* __restrict__ gzt, int R,
              int H, int W, int k, int nO, int ldn, int ldp, int ldpT) {
     extern __shared__ unsigned char th_smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see launch_overlapped
     // list[R] (int) | rowext[R] (int: I1 - I0 or 0) | cj[R*k] (short2 J0, J1) | val[R*k*nO] (float)
     int* list = reinterpret_cast<int*>(th_smem);
     int* rowext = list + R;
@@ -356,6 +358,23 @@ th_reduce_w_kernel(const float* __restrict__ part, const float* __restrict__ g, 
     }
 }
 
+// launch `kernel` so that it may start before the previous kernel of the stream has finished (programmatic dependent launch):
+// only for a kernel that reads nothing the previous one writes, after a kernel that executes griddepcontrol.launch_dependents
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_overlapped(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int grid_for(size_t n, int block, int cap) {
     size_t g = (n + block - 1) / block;
     if (g > (size_t)cap) g = cap;
@@ -395,7 +414,9 @@ int trackhead_fwd_launch(const float* fm, const float* rois, const float* weight
     const int cap = di.sm_count * 8;
     th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wt, C, d.KK, nO, d.ldc, 0);
     D2T_CUDA_TRY(cudaGetLastError());
-    th_transpose_kernel<<<dim3(ceil_div(d.P, 32), ceil_div(C, 32), NB), 256, 0, st>>>(fm, w.xt, C, d.P, d.ldc);
+    // independent of the weight re-layout before it
+    D2T_CUDA_TRY(launch_overlapped(th_transpose_kernel, dim3(ceil_div(d.P, 32), ceil_div(C, 32), NB), dim3(256), 0, st, fm, w.xt, C, d.P,
+                                   d.ldc));
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch(2);
     const int PT = NB * d.P;
@@ -489,7 +510,9 @@ int trackhead_bwd_launch(const float* go, const float* fm, const float* rois, co
     D2T_CUDA_TRY(cudaGetLastError());
     note_launch();
     if (gfm) {
-        th_weight_prep_kernel<<<grid_for((size_t)d.N1 * C, 256, cap), 256, 0, st>>>(weight, w.wc, C, d.KK, nO, d.ldn, 1);
+        // independent of the gZ gather before it
+        D2T_CUDA_TRY(launch_overlapped(th_weight_prep_kernel, dim3(grid_for((size_t)d.N1 * C, 256, cap)), dim3(256), 0, st, weight, w.wc,
+                                       C, d.KK, nO, d.ldn, 1));
         D2T_CUDA_TRY(cudaGetLastError());
         note_launch();
         GemmOperand A{w.gz, NB * d.P, d.ldn}, B{w.wc, C, d.ldn};
@@ -500,7 +523,13 @@ int trackhead_bwd_launch(const float* go, const float* fm, const float* rois, co
     if (gw) {
         const float* xc = fm;
         if (NB > 1 || d.P != d.ldp || (reinterpret_cast<uintptr_t>(fm) & 15) != 0) {
-            th_pad_copy_kernel<<<dim3(ceil_div(d.ldp, 2048), C, NB), 256, 0, st>>>(fm, w.xc, C, d.P, d.ldp, NB);
+            // independent of the grad_X GEMM before it (reads fm, writes w.xc): an HBM-bound copy under a tensor-bound GEMM
+            if (gfm) {
+                D2T_CUDA_TRY(launch_overlapped(th_pad_copy_kernel, dim3(ceil_div(d.ldp, 2048), C, NB), dim3(256), 0, st, fm, w.xc, C,
+                                               d.P, d.ldp, NB));
+            } else {
+                th_pad_copy_kernel<<<dim3(ceil_div(d.ldp, 2048), C, NB), 256, 0, st>>>(fm, w.xc, C, d.P, d.ldp, NB);
+            }
             D2T_CUDA_TRY(cudaGetLastError());
             note_launch();
             xc = w.xc;
