@@ -8,7 +8,8 @@
 One STEP = the whole hot path, forward + backward, for 8 frame pairs on one GPU
 (BASELINE.json configs 2+3+4 together, SURVEY.md section 8d shapes):
     PointwiseCorrelation d=8 on c3/c4/c5 (C=512/1024/2048, 38x63), batch of 8 pairs      3 fwd + 3 bwd calls (tcgen05)
-    PSROIPool 7x7, cls (31 targets) + reg (4 targets), 300 RoIs, 2 frames per pair        32 fwd + 32 bwd calls
+    PSROIPool 7x7, cls (31 targets) + reg (4 targets), 300 RoIs, 2 frames per pair        2 fwd + 2 bwd batched calls
+                                                                                          (16 frames each; 32 + 32 per-frame calls in the reference)
     ROIPool 7x7 track head, 1891 channels, 300 RoIs per pair                              8 fwd +  8 bwd calls
 Pairs shard over GPUs with no data-path collective: weak scaling, value =
 pairs processed by all ranks / max-over-ranks device time.
